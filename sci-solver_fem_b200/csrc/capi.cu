@@ -1,0 +1,239 @@
+// capi.cu — extern "C" boundary (include/femsolver_b200.h) over fsb::Solver.
+#include <cstring>
+#include <string>
+
+#include "../../include/femsolver_b200.h"
+#include "solver.h"
+
+struct fsb_solver {
+  fsb::Solver* impl = nullptr;
+};
+
+static thread_local std::string g_create_error;
+
+namespace {
+
+template <typename F>
+int guarded(fsb_solver* s, F&& f) {
+  if (!s || !s->impl) return FSB_ERR_INVALID;
+  try {
+    f(*s->impl);
+    return FSB_OK;
+  } catch (const std::invalid_argument& e) {
+    s->impl->last_error = e.what();
+    return FSB_ERR_INVALID;
+  } catch (const fsb::CudaError& e) {
+    s->impl->last_error = e.what();
+    cudaGetLastError();
+    return FSB_ERR_CUDA;
+  } catch (const std::exception& e) {
+    s->impl->last_error = e.what();
+    return FSB_ERR_RUNTIME;
+  }
+}
+
+struct ParamRef { const char* name; int kind; size_t off; };  // kind 0 int, 1 double, 2 unsigned
+#define PI_(n) {#n, 0, offsetof(fsb::Params, n)}
+#define PD_(n) {#n, 1, offsetof(fsb::Params, n)}
+const ParamRef kParams[] = {
+  PI_(verbose), PI_(maxLevels), PI_(maxIters), PI_(preInnerIters), PI_(postInnerIters), PI_(postRelaxes), PI_(cycleIters),
+  PI_(dsType), PI_(topSize), PI_(randMisParameters), PI_(partitionMaxSize), PI_(aggregatorType), PI_(convergeType),
+  PI_(cycleType), PI_(solverType), PI_(device), PI_(blockSize), PD_(tolerance), PD_(smootherWeight), PD_(proOmega),
+  {"seed", 2, offsetof(fsb::Params, seed)}, PI_(refLevel0NoPerm), PI_(useGraphs), PI_(checkEvery)};
+
+const ParamRef* find_param(const char* name) {
+  for (const ParamRef& p : kParams) if (strcmp(p.name, name) == 0) return &p;
+  return nullptr;
+}
+
+long long copy_ints(const fsb::IBuf& b, int* buf, long long cap) {
+  long long n = (long long)b.size();
+  if (!buf) return n;
+  if (cap < n) return -1;
+  if (n) b.to_host(buf, n);
+  return n;
+}
+long long copy_vals(const fsb::DBuf& b, double* buf, long long cap) {
+  long long n = (long long)b.size();
+  if (!buf) return n;
+  if (cap < n) return -1;
+  if (n) b.to_host(buf, n);
+  return n;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fsb_version(void) { return 100; }
+
+int fsb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int fsb_create(fsb_solver** out, int device) {
+  if (!out) return FSB_ERR_INVALID;
+  *out = nullptr;
+  try {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+      cudaGetLastError();
+      g_create_error = "no CUDA device: this library has no CPU fallback";
+      return FSB_ERR_CUDA;
+    }
+    fsb_solver* s = new fsb_solver();
+    s->impl = new fsb::Solver(device);
+    *out = s;
+    return FSB_OK;
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    return FSB_ERR_CUDA;
+  }
+}
+
+void fsb_destroy(fsb_solver* s) {
+  if (!s) return;
+  delete s->impl;
+  delete s;
+}
+
+const char* fsb_last_error(const fsb_solver* s) {
+  if (!s || !s->impl) return g_create_error.c_str();
+  return s->impl->last_error.c_str();
+}
+
+int fsb_set_param(fsb_solver* s, const char* name, double value) {
+  if (!s || !s->impl || !name) return FSB_ERR_INVALID;
+  const ParamRef* p = find_param(name);
+  if (!p) { s->impl->last_error = std::string("unknown parameter: ") + name; return FSB_ERR_INVALID; }
+  char* base = reinterpret_cast<char*>(&s->impl->prm);
+  if (p->kind == 0) *reinterpret_cast<int*>(base + p->off) = (int)value;
+  else if (p->kind == 1) *reinterpret_cast<double*>(base + p->off) = value;
+  else *reinterpret_cast<unsigned*>(base + p->off) = (unsigned)value;
+  return FSB_OK;
+}
+
+int fsb_get_param(const fsb_solver* s, const char* name, double* value) {
+  if (!s || !s->impl || !name || !value) return FSB_ERR_INVALID;
+  const ParamRef* p = find_param(name);
+  if (!p) return FSB_ERR_INVALID;
+  const char* base = reinterpret_cast<const char*>(&s->impl->prm);
+  if (p->kind == 0) *value = *reinterpret_cast<const int*>(base + p->off);
+  else if (p->kind == 1) *value = *reinterpret_cast<const double*>(base + p->off);
+  else *value = *reinterpret_cast<const unsigned*>(base + p->off);
+  return FSB_OK;
+}
+
+int fsb_set_tet_mesh(fsb_solver* s, int nv, const double* xyz, int ne, const int* tets, const int* labels) {
+  return guarded(s, [&](fsb::Solver& S) { S.set_mesh(nv, xyz, ne, 4, tets, labels, false); });
+}
+int fsb_set_tri_mesh(fsb_solver* s, int nv, const double* xyz, int ne, const int* tris) {
+  return guarded(s, [&](fsb::Solver& S) { S.set_mesh(nv, xyz, ne, 3, tris, nullptr, false); });
+}
+int fsb_set_tet_mesh_device(fsb_solver* s, int nv, const double* xyz, int ne, const int* tets, const int* labels) {
+  return guarded(s, [&](fsb::Solver& S) { S.set_mesh(nv, xyz, ne, 4, tets, labels, true); });
+}
+int fsb_set_tri_mesh_device(fsb_solver* s, int nv, const double* xyz, int ne, const int* tris) {
+  return guarded(s, [&](fsb::Solver& S) { S.set_mesh(nv, xyz, ne, 3, tris, nullptr, true); });
+}
+int fsb_assemble(fsb_solver* s) { return guarded(s, [&](fsb::Solver& S) { S.assemble(); }); }
+int fsb_matrix_rows(const fsb_solver* s) { return (s && s->impl) ? s->impl->rows() : 0; }
+long long fsb_matrix_nnz(const fsb_solver* s) { return (s && s->impl) ? s->impl->nnz() : 0; }
+int fsb_get_matrix_csr(fsb_solver* s, int* rowptr, int* col, double* val) {
+  return guarded(s, [&](fsb::Solver& S) { S.get_matrix(rowptr, col, val); });
+}
+int fsb_set_matrix_values(fsb_solver* s, const double* val) {
+  return guarded(s, [&](fsb::Solver& S) { S.set_matrix_values(val, false); });
+}
+int fsb_set_matrix_csr(fsb_solver* s, int n, long long nnz, const int* rowptr, const int* col, const double* val) {
+  return guarded(s, [&](fsb::Solver& S) { S.set_matrix_csr(n, (int)nnz, rowptr, col, val); });
+}
+
+int fsb_setup(fsb_solver* s) { return guarded(s, [&](fsb::Solver& S) { S.setup(); }); }
+int fsb_num_levels(const fsb_solver* s) { return (s && s->impl) ? s->impl->num_levels() : 0; }
+int fsb_level_rows(const fsb_solver* s, int level) {
+  if (!s || !s->impl || level < 0 || level >= s->impl->num_levels()) return -1;
+  return s->impl->level(level).A.nrows;
+}
+long long fsb_level_nnz(const fsb_solver* s, int level) {
+  if (!s || !s->impl || level < 0 || level >= s->impl->num_levels()) return -1;
+  return s->impl->level(level).A.nnz;
+}
+
+long long fsb_level_int(fsb_solver* s, int level, const char* name, int* buf, long long cap) {
+  if (!s || !s->impl || level < 0 || level >= s->impl->num_levels()) return -1;
+  long long rc = -1;
+  int g = guarded(s, [&](fsb::Solver& S) {
+    const fsb::LevelData& L = S.level(level);
+    std::string n(name);
+    const fsb::IBuf* b = nullptr;
+    if (n == "permutation") b = &L.agg.permutation; else if (n == "ipermutation") b = &L.agg.ipermutation;
+    else if (n == "aggregateIdx") b = &L.agg.aggregateIdx; else if (n == "partitionIdx") b = &L.agg.partitionIdx;
+    else if (n == "partitionLabel") b = &L.agg.partitionLabel; else if (n == "xadjOut") b = &L.agg.xadjOut;
+    else if (n == "adjOut") b = &L.agg.adjOut; else if (n == "A_ptr") b = &L.A.ptr; else if (n == "A_col") b = &L.A.col;
+    else if (n == "P_ptr") b = &L.P.ptr; else if (n == "P_col") b = &L.P.col; else if (n == "R_ptr") b = &L.R.ptr;
+    else if (n == "R_col") b = &L.R.col; else if (n == "pstart") b = &L.pstart;
+    else throw std::invalid_argument("unknown level array: " + n);
+    rc = copy_ints(*b, buf, cap);
+  });
+  return g == FSB_OK ? rc : g;
+}
+
+long long fsb_level_val(fsb_solver* s, int level, const char* name, double* buf, long long cap) {
+  if (!s || !s->impl || level < 0 || level >= s->impl->num_levels()) return -1;
+  long long rc = -1;
+  int g = guarded(s, [&](fsb::Solver& S) {
+    const fsb::LevelData& L = S.level(level);
+    std::string n(name);
+    const fsb::DBuf* b = nullptr;
+    if (n == "A_val") b = &L.A.val; else if (n == "P_val") b = &L.P.val; else if (n == "R_val") b = &L.R.val;
+    else if (n == "diag") b = &L.diag; else if (n == "Ainv" && level == S.num_levels() - 1) b = &S.Ainv;
+    else throw std::invalid_argument("unknown level array: " + n);
+    rc = copy_vals(*b, buf, cap);
+  });
+  return g == FSB_OK ? rc : g;
+}
+
+static void report(fsb::Solver& S, int* iters, double* relres) {
+  if (iters) *iters = S.iterations;
+  if (relres) *relres = S.final_relres;
+}
+int fsb_solve(fsb_solver* s, const double* b, double* x, int* iters, double* relres) {
+  return guarded(s, [&](fsb::Solver& S) { S.solve(b, x, false); report(S, iters, relres); });
+}
+int fsb_solve_device(fsb_solver* s, const double* b, double* x, int* iters, double* relres) {
+  return guarded(s, [&](fsb::Solver& S) { S.solve(b, x, true); report(S, iters, relres); });
+}
+int fsb_solve_fem(fsb_solver* s, const double* b, double* x, int* iters, double* relres) {
+  return guarded(s, [&](fsb::Solver& S) { S.setup(); S.solve(b, x, false); report(S, iters, relres); });
+}
+int fsb_resid_history(const fsb_solver* s, double* buf, int cap) {
+  if (!s || !s->impl) return -1;
+  int n = (int)s->impl->resid_history.size();
+  if (!buf) return n;
+  if (cap < n) return -1;
+  memcpy(buf, s->impl->resid_history.data(), sizeof(double) * n);
+  return n;
+}
+
+int fsb_spmv_fine_device(fsb_solver* s, const double* x, double* y) {
+  return guarded(s, [&](fsb::Solver& S) { if (!S.has_setup) throw std::runtime_error("setup first"); S.spmv_fine(x, y); });
+}
+int fsb_precondition_device(fsb_solver* s, const double* r, double* z) {
+  return guarded(s, [&](fsb::Solver& S) { S.precondition(r, z); });
+}
+
+double fsb_time_ms(const fsb_solver* s, const char* stage) {
+  if (!s || !s->impl) return -1;
+  auto it = s->impl->times_ms.find(stage);
+  return it == s->impl->times_ms.end() ? -1.0 : it->second;
+}
+long long fsb_last_launches(const fsb_solver* s) { return (s && s->impl) ? s->impl->launches : 0; }
+void* fsb_stream(const fsb_solver* s) { return (s && s->impl) ? (void*)s->impl->ctx.stream : nullptr; }
+
+void fsb_tet_mass_integrals(double out10[10]) { fsb::tet_mass_integrals_host(out10); }
+void fsb_tri_quadrature(double zx[6], double zy[6], double wx[6], double wy[6]) { fsb::tri_quadrature_host(zx, zy, wx, wy); }
+
+}  // extern "C"

@@ -1,0 +1,106 @@
+// common.cuh — device buffers, error handling and CUB wrappers shared by every stage.
+// Product code (sm_100a only).  Nothing here touches oracle/.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+namespace fsb {
+
+struct CudaError : public std::runtime_error {
+  explicit CudaError(const std::string& s) : std::runtime_error(s) {}
+};
+
+#define FSB_CUDA(call)                                                                           \
+  do {                                                                                           \
+    cudaError_t e__ = (call);                                                                    \
+    if (e__ != cudaSuccess)                                                                      \
+      throw ::fsb::CudaError(std::string(#call) + " failed: " + cudaGetErrorString(e__) + " at " + \
+                             __FILE__ + ":" + std::to_string(__LINE__));                         \
+  } while (0)
+
+#define FSB_CHECK_LAUNCH() FSB_CUDA(cudaGetLastError())
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// The stream every kernel of a solver instance is launched on.
+struct Ctx {
+  cudaStream_t stream = nullptr;
+  int device = 0;
+  int num_sms = 148;
+};
+
+// Stream-ordered device buffer (cudaMallocAsync pool: setup makes hundreds of temporaries).
+template <typename T>
+class DevBuf {
+ public:
+  DevBuf() = default;
+  DevBuf(size_t n, cudaStream_t s) { alloc(n, s); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept { swap(o); }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); swap(o); }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void alloc(size_t n, cudaStream_t s) {
+    release();
+    n_ = n; s_ = s;
+    if (n) FSB_CUDA(cudaMallocAsync((void**)&p_, n * sizeof(T), s));
+  }
+  void release() {
+    if (p_) cudaFreeAsync(p_, s_);
+    p_ = nullptr; n_ = 0;
+  }
+  void swap(DevBuf& o) { std::swap(p_, o.p_); std::swap(n_, o.n_); std::swap(s_, o.s_); }
+  T* get() const { return p_; }
+  operator T*() const { return p_; }
+  size_t size() const { return n_; }
+  void zero() { if (n_) FSB_CUDA(cudaMemsetAsync(p_, 0, n_ * sizeof(T), s_)); }
+  void fill_bytes(int v) { if (n_) FSB_CUDA(cudaMemsetAsync(p_, v, n_ * sizeof(T), s_)); }
+  void from_host(const T* h, size_t n) { FSB_CUDA(cudaMemcpyAsync(p_, h, n * sizeof(T), cudaMemcpyHostToDevice, s_)); }
+  void from_device(const T* d, size_t n) { FSB_CUDA(cudaMemcpyAsync(p_, d, n * sizeof(T), cudaMemcpyDeviceToDevice, s_)); }
+  void to_host(T* h, size_t n) const {
+    FSB_CUDA(cudaMemcpyAsync(h, p_, n * sizeof(T), cudaMemcpyDeviceToHost, s_));
+    FSB_CUDA(cudaStreamSynchronize(s_));
+  }
+  std::vector<T> to_vector() const { std::vector<T> v(n_); if (n_) to_host(v.data(), n_); return v; }
+  T read(size_t i) const { T v; FSB_CUDA(cudaMemcpyAsync(&v, p_ + i, sizeof(T), cudaMemcpyDeviceToHost, s_)); FSB_CUDA(cudaStreamSynchronize(s_)); return v; }
+
+ private:
+  T* p_ = nullptr;
+  size_t n_ = 0;
+  cudaStream_t s_ = nullptr;
+};
+
+typedef DevBuf<int> IBuf;
+typedef DevBuf<double> DBuf;
+
+struct DCsr {
+  int nrows = 0, ncols = 0, nnz = 0;
+  IBuf ptr, col;
+  DBuf val;
+};
+
+// ---- primitives implemented in prims.cu (CUB under the hood; setup-time plumbing only) ----
+void sort_pairs_u64_u32(const uint64_t* kin, uint64_t* kout, const uint32_t* vin, uint32_t* vout, size_t n, int end_bit, cudaStream_t s);
+void sort_keys_u64(const uint64_t* kin, uint64_t* kout, size_t n, int end_bit, cudaStream_t s);
+void sort_pairs_i32_i32(const int* kin, int* kout, const int* vin, int* vout, size_t n, int end_bit, cudaStream_t s);  // stable, keys >= 0
+void exclusive_scan_i32(const int* in, int* out, size_t n, cudaStream_t s);
+void inclusive_scan_i32(const int* in, int* out, size_t n, cudaStream_t s);
+int reduce_max_i32(const int* in, size_t n, cudaStream_t s);
+long long reduce_sum_i32(const int* in, size_t n, cudaStream_t s);
+int count_equal_i32(const int* in, size_t n, int value, cudaStream_t s);
+void iota_i32(int* p, size_t n, cudaStream_t s);
+void fill_i32(int* p, size_t n, int v, cudaStream_t s);
+void fill_f64(double* p, size_t n, double v, cudaStream_t s);
+int bits_for(long long maxval);  // number of low bits needed to represent values in [0, maxval]
+
+}  // namespace fsb

@@ -1,0 +1,294 @@
+// hierarchy.cu — stage 2b: level construction on device: symmetric permutation of A,
+// smoothed prolongator, transpose, Galerkin product, coarsest-level inverse.
+//
+// Reference: SmoothedMG_AMG_Level::generateMatrixSymmetric_d (src/core/cuda/
+// smoothedMG_amg_level.cu:199-304, matrixpermute_kernel :45-80), generateProlongatorFull_d
+// (:320-387), generateNextLevelMatrixFull_d (:389-400, two cusp::multiply ESC SpGEMMs),
+// coarse LU (amg.cu:101-108).
+//
+// B200 design: no global expand-sort-compress.  Every product is formed row-wise (Gustavson)
+// by the thread that owns the output row, which keeps a small column-sorted accumulator list
+// in a private scratch segment; summation order is therefore fixed (k ascending, then the
+// B-row order), the output columns come out sorted, and the whole hierarchy is bit-reproducible.
+// Compiled with -fmad=false so that products and sums round separately, as on the host.
+#include <cub/cub.cuh>
+
+#include "fsb_internal.h"
+
+namespace fsb {
+namespace {
+
+__global__ void row_lengths_permuted(int n, const int* __restrict__ ptr, const int* __restrict__ perm, int* __restrict__ len) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) len[perm[i]] = ptr[i + 1] - ptr[i];
+}
+
+// matrixpermute_kernel: (row, col) -> (perm[row], perm[col]); rows re-sorted by column
+__global__ void permute_rows(int n, const int* __restrict__ ptrA, const int* __restrict__ colA, const double* __restrict__ valA,
+                             const int* __restrict__ perm, const int* __restrict__ ptrB, int* __restrict__ colB, double* __restrict__ valB) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int base = ptrB[perm[i]], cnt = 0;
+  for (int e = ptrA[i]; e < ptrA[i + 1]; e++) {
+    int cnew = perm[colA[e]];
+    double v = valA[e];
+    int q = base + cnt;  // insertion sort into the (short) destination row
+    while (q > base && colB[q - 1] > cnew) { colB[q] = colB[q - 1]; valB[q] = valB[q - 1]; q--; }
+    colB[q] = cnew; valB[q] = v;
+    cnt++;
+  }
+}
+
+__global__ void diag_kernel(int n, const int* __restrict__ ptr, const int* __restrict__ col, const double* __restrict__ val, double* __restrict__ diag) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double d = 0.0;
+  for (int e = ptr[i]; e < ptr[i + 1]; e++) if (col[e] == i) d = val[e];
+  diag[i] = d;
+}
+
+__global__ void agg_of_row(int nAgg, const int* __restrict__ aggregateIdx, int* __restrict__ aggOf) {
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= nAgg) return;
+  for (int r = aggregateIdx[a]; r < aggregateIdx[a + 1]; r++) aggOf[r] = a;
+}
+
+// sorted-list accumulate: returns the new count
+__device__ __forceinline__ int acc_insert(int* cols, double* vals, int cnt, int j, double v) {
+  int lo = 0, hi = cnt;
+  while (lo < hi) { int mid = (lo + hi) >> 1; if (cols[mid] < j) lo = mid + 1; else hi = mid; }
+  if (lo < cnt && cols[lo] == j) { vals[lo] += v; return cnt; }
+  for (int q = cnt; q > lo; q--) { cols[q] = cols[q - 1]; vals[q] = vals[q - 1]; }
+  cols[lo] = j; vals[lo] = 0.0 + v;
+  return cnt + 1;
+}
+
+// P = T - omega D^-1 A T, row-wise.  Terms of one (row, aggregate) are added in column order
+// and the tentative 1 last — the order the reference's stable sort + reduce_by_key produces.
+__global__ void prolongator_rows(int n, const int* __restrict__ ptr, const int* __restrict__ col, const double* __restrict__ val,
+                                 const double* __restrict__ diag, const int* __restrict__ aggOf, double omega,
+                                 int* __restrict__ scol, double* __restrict__ sval, int* __restrict__ count) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  long long base = (long long)ptr[i] + i;  // room for row length + 1 entries
+  int* cols = scol + base;
+  double* vals = sval + base;
+  int cnt = 0;
+  double d = diag[i];
+  for (int e = ptr[i]; e < ptr[i + 1]; e++) {
+    double term = (-omega * val[e] * 1.0) / d;
+    cnt = acc_insert(cols, vals, cnt, aggOf[col[e]], term);
+  }
+  cnt = acc_insert(cols, vals, cnt, aggOf[i], 1.0);
+  count[i] = cnt;
+}
+
+__global__ void compact_rows(int n, const long long* __restrict__ sbase, const int* __restrict__ scol, const double* __restrict__ sval,
+                             const int* __restrict__ ptrC, int* __restrict__ colC, double* __restrict__ valC) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  long long b = sbase[i];
+  int o = ptrC[i], cnt = ptrC[i + 1] - o;
+  for (int q = 0; q < cnt; q++) { colC[o + q] = scol[b + q]; valC[o + q] = sval[b + q]; }
+}
+
+__global__ void prolongator_bases(int n, const int* __restrict__ ptr, long long* __restrict__ sbase) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) sbase[i] = (long long)ptr[i] + i;
+}
+
+__global__ void spgemm_bound(int n, const int* __restrict__ ptrA, const int* __restrict__ colA, const int* __restrict__ ptrB, long long* __restrict__ ub) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  long long s = 0;
+  for (int e = ptrA[i]; e < ptrA[i + 1]; e++) { int k = colA[e]; s += ptrB[k + 1] - ptrB[k]; }
+  ub[i] = s;
+}
+
+__global__ void spgemm_rows(int n, const int* __restrict__ ptrA, const int* __restrict__ colA, const double* __restrict__ valA,
+                            const int* __restrict__ ptrB, const int* __restrict__ colB, const double* __restrict__ valB,
+                            const long long* __restrict__ sbase, int* __restrict__ scol, double* __restrict__ sval, int* __restrict__ count) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int* cols = scol + sbase[i];
+  double* vals = sval + sbase[i];
+  int cnt = 0;
+  for (int e = ptrA[i]; e < ptrA[i + 1]; e++) {
+    int k = colA[e];
+    double a = valA[e];
+    for (int f = ptrB[k]; f < ptrB[k + 1]; f++) cnt = acc_insert(cols, vals, cnt, colB[f], a * valB[f]);
+  }
+  count[i] = cnt;
+}
+
+__global__ void expand_rows(int n, const int* __restrict__ ptr, int* __restrict__ rows) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int e = ptr[i]; e < ptr[i + 1]; e++) rows[e] = i;
+}
+__global__ void count_cols(int nnz, const int* __restrict__ col, int* __restrict__ cnt) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < nnz) atomicAdd(&cnt[col[e] + 1], 1);
+}
+__global__ void gather_transposed(int nnz, const int* __restrict__ order, const int* __restrict__ rows, const double* __restrict__ val,
+                                  int* __restrict__ colT, double* __restrict__ valT) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < nnz) { int src = order[e]; colT[e] = rows[src]; valT[e] = val[src]; }
+}
+
+void exclusive_scan_i64(const long long* in, long long* out, size_t n, cudaStream_t s) {
+  void* tmp = nullptr; size_t bytes = 0;
+  FSB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int64_t)n, s));
+  FSB_CUDA(cudaMallocAsync(&tmp, bytes, s));
+  FSB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, bytes, in, out, (int64_t)n, s));
+  cudaFreeAsync(tmp, s);
+}
+
+// counts (n ints) -> ptr (n+1): exclusive scan with the total appended; returns the total
+int counts_to_ptr(const Ctx& c, IBuf& count_plus1, int n, IBuf& ptr) {
+  // count_plus1 has n+1 entries with the last one zeroed by the caller
+  ptr.alloc(n + 1, c.stream);
+  exclusive_scan_i32(count_plus1, ptr, n + 1, c.stream);
+  return ptr.read(n);
+}
+
+// ---- dense inverse of the coarsest operator: Gauss-Jordan with partial pivoting, one CTA ----
+__global__ void densify(int n, const int* __restrict__ ptr, const int* __restrict__ col, const double* __restrict__ val, double* __restrict__ M) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;  // M is n x 2n: [A | I]
+  if (i >= n) return;
+  for (int e = ptr[i]; e < ptr[i + 1]; e++) M[(size_t)i * 2 * n + col[e]] += val[e];
+  M[(size_t)i * 2 * n + n + i] = 1.0;
+}
+
+__global__ void __launch_bounds__(1024) gauss_jordan(int n, double* __restrict__ M, double* __restrict__ Ainv) {
+  __shared__ double s_val[1024];
+  __shared__ int s_idx[1024];
+  __shared__ int s_piv;
+  const int t = threadIdx.x, T = blockDim.x, W = 2 * n;
+  for (int k = 0; k < n; k++) {
+    double best = -1.0; int bi = k;
+    for (int i = k + t; i < n; i += T) { double a = fabs(M[(size_t)i * W + k]); if (a > best) { best = a; bi = i; } }
+    s_val[t] = best; s_idx[t] = bi;
+    __syncthreads();
+    for (int off = T >> 1; off > 0; off >>= 1) {
+      if (t < off) {
+        // first maximal row wins (what a sequential partial-pivot search picks)
+        if (s_val[t + off] > s_val[t] || (s_val[t + off] == s_val[t] && s_idx[t + off] < s_idx[t])) { s_val[t] = s_val[t + off]; s_idx[t] = s_idx[t + off]; }
+      }
+      __syncthreads();
+    }
+    if (t == 0) s_piv = s_idx[0];
+    __syncthreads();
+    int p = s_piv;
+    if (p != k) for (int j = t; j < W; j += T) { double a = M[(size_t)k * W + j]; M[(size_t)k * W + j] = M[(size_t)p * W + j]; M[(size_t)p * W + j] = a; }
+    __syncthreads();
+    double d = M[(size_t)k * W + k];
+    __syncthreads();
+    for (int j = t; j < W; j += T) M[(size_t)k * W + j] /= d;
+    __syncthreads();
+    // eliminate column k from every other row: thread -> (row, column-chunk)
+    for (long long q = t; q < (long long)n * W; q += T) {
+      int i = (int)(q / W), j = (int)(q - (long long)i * W);
+      if (i == k || j == k) continue;
+      double f = M[(size_t)i * W + k];
+      if (f != 0.0) M[(size_t)i * W + j] -= f * M[(size_t)k * W + j];
+    }
+    __syncthreads();
+    for (int i = t; i < n; i += T) if (i != k) M[(size_t)i * W + k] = 0.0;
+    __syncthreads();
+  }
+  for (long long q = t; q < (long long)n * n; q += T) {
+    int i = (int)(q / n), j = (int)(q - (long long)i * n);
+    Ainv[q] = M[(size_t)i * W + n + j];
+  }
+}
+
+}  // namespace
+
+void permute_csr(const Ctx& c, const DCsr& A, const int* perm, DCsr& B) {
+  cudaStream_t s = c.stream;
+  int n = A.nrows;
+  IBuf len(n + 1, s);
+  len.zero();
+  row_lengths_permuted<<<cdiv(n, 256), 256, 0, s>>>(n, A.ptr, perm, len);
+  B.nrows = A.nrows; B.ncols = A.ncols; B.nnz = A.nnz;
+  B.ptr.alloc(n + 1, s);
+  exclusive_scan_i32(len, B.ptr, n + 1, s);
+  B.col.alloc(A.nnz, s); B.val.alloc(A.nnz, s);
+  permute_rows<<<cdiv(n, 128), 128, 0, s>>>(n, A.ptr, A.col, A.val, perm, B.ptr, B.col, B.val);
+  FSB_CHECK_LAUNCH();
+}
+
+void extract_diag(const Ctx& c, const DCsr& A, double* diag) {
+  diag_kernel<<<cdiv(A.nrows, 256), 256, 0, c.stream>>>(A.nrows, A.ptr, A.col, A.val, diag);
+  FSB_CHECK_LAUNCH();
+}
+
+void build_prolongator(const Ctx& c, const DCsr& A, const double* diag, const int* aggregateIdx, int nAgg, double omega, DCsr& P) {
+  cudaStream_t s = c.stream;
+  int n = A.nrows;
+  IBuf aggOf(n, s), count(n + 1, s);
+  count.zero();
+  agg_of_row<<<cdiv(nAgg, 256), 256, 0, s>>>(nAgg, aggregateIdx, aggOf);
+  size_t cap = (size_t)A.nnz + n;
+  IBuf scol(cap, s); DBuf sval(cap, s);
+  DevBuf<long long> sbase(n, s);
+  prolongator_bases<<<cdiv(n, 256), 256, 0, s>>>(n, A.ptr, sbase);
+  prolongator_rows<<<cdiv(n, 128), 128, 0, s>>>(n, A.ptr, A.col, A.val, diag, aggOf, omega, scol, sval, count);
+  FSB_CHECK_LAUNCH();
+  P.nrows = n; P.ncols = nAgg;
+  P.nnz = counts_to_ptr(c, count, n, P.ptr);
+  P.col.alloc(P.nnz, s); P.val.alloc(P.nnz, s);
+  compact_rows<<<cdiv(n, 128), 128, 0, s>>>(n, sbase, scol, sval, P.ptr, P.col, P.val);
+  FSB_CHECK_LAUNCH();
+}
+
+// At = A^T via a stable radix sort of the entries by column (cusp::transpose,
+// smoothedMG_amg_level.cu:382): within a row of At the columns ascend.
+void transpose_csr(const Ctx& c, const DCsr& A, DCsr& At) {
+  cudaStream_t s = c.stream;
+  IBuf rows(A.nnz, s), iotaE(A.nnz, s), order(A.nnz, s), sortedCols(A.nnz, s), cnt(A.ncols + 1, s);
+  expand_rows<<<cdiv(A.nrows, 128), 128, 0, s>>>(A.nrows, A.ptr, rows);
+  iota_i32(iotaE, A.nnz, s);
+  sort_pairs_i32_i32(A.col, sortedCols, iotaE, order, A.nnz, bits_for(A.ncols), s);
+  cnt.zero();
+  count_cols<<<cdiv(A.nnz, 256), 256, 0, s>>>(A.nnz, A.col, cnt);
+  At.nrows = A.ncols; At.ncols = A.nrows; At.nnz = A.nnz;
+  At.ptr.alloc(A.ncols + 1, s);
+  inclusive_scan_i32(cnt, At.ptr, A.ncols + 1, s);
+  At.col.alloc(A.nnz, s); At.val.alloc(A.nnz, s);
+  gather_transposed<<<cdiv(A.nnz, 256), 256, 0, s>>>(A.nnz, order, rows, A.val, At.col, At.val);
+  FSB_CHECK_LAUNCH();
+}
+
+void spgemm(const Ctx& c, const DCsr& A, const DCsr& B, DCsr& C) {
+  cudaStream_t s = c.stream;
+  int n = A.nrows;
+  DevBuf<long long> ub((size_t)n + 1, s), sbase((size_t)n + 1, s);
+  ub.zero();
+  spgemm_bound<<<cdiv(n, 256), 256, 0, s>>>(n, A.ptr, A.col, B.ptr, ub);
+  exclusive_scan_i64(ub, sbase, (size_t)n + 1, s);
+  long long cap = sbase.read(n);
+  IBuf scol((size_t)cap, s), count(n + 1, s); DBuf sval((size_t)cap, s);
+  count.zero();
+  spgemm_rows<<<cdiv(n, 64), 64, 0, s>>>(n, A.ptr, A.col, A.val, B.ptr, B.col, B.val, sbase, scol, sval, count);
+  FSB_CHECK_LAUNCH();
+  C.nrows = n; C.ncols = B.ncols;
+  C.nnz = counts_to_ptr(c, count, n, C.ptr);
+  C.col.alloc(C.nnz, s); C.val.alloc(C.nnz, s);
+  compact_rows<<<cdiv(n, 128), 128, 0, s>>>(n, sbase, scol, sval, C.ptr, C.col, C.val);
+  FSB_CHECK_LAUNCH();
+}
+
+void dense_inverse(const Ctx& c, const DCsr& A, DBuf& Ainv) {
+  cudaStream_t s = c.stream;
+  int n = A.nrows;
+  DBuf M((size_t)n * 2 * n, s);
+  M.zero();
+  Ainv.alloc((size_t)n * n, s);
+  densify<<<cdiv(n, 128), 128, 0, s>>>(n, A.ptr, A.col, A.val, M);
+  gauss_jordan<<<1, 1024, 0, s>>>(n, M, Ainv);
+  FSB_CHECK_LAUNCH();
+}
+
+}  // namespace fsb

@@ -1,0 +1,355 @@
+// solver.cu — host orchestration: FEMSolver::getMatrixFromMesh / solveFEM equivalents.
+//
+// Reference call stacks: FEMSolver::getMatrixFromMesh (src/FEMSolver.cu:141-171),
+// FEMSolver::solveFEM (:58-93), AMG::setup (src/core/cuda/amg.cu:79-144), AMG::solve /
+// solve_iteration (:149-200), AMG_Level::cycle / cycle_level0 (amg_level.cu:22-128),
+// CG_Flex_Cycle (cgcycle.cu:6-69).
+#include "solver.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "kernels.h"
+
+namespace fsb {
+
+Solver::Solver(int device) {
+  ctx.device = device;
+  FSB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  FSB_CUDA(cudaGetDeviceProperties(&prop, device));
+  ctx.num_sms = prop.multiProcessorCount;
+  FSB_CUDA(cudaStreamCreateWithFlags(&ctx.stream, cudaStreamNonBlocking));
+  // keep freed setup temporaries in the pool: setup allocates hundreds of short-lived buffers
+  cudaMemPool_t pool;
+  FSB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+  uint64_t thr = UINT64_MAX;
+  FSB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  FSB_CUDA(cudaEventCreate(&ev0_));
+  FSB_CUDA(cudaEventCreate(&ev1_));
+  prm.device = device;
+}
+
+Solver::~Solver() {
+  destroy_graph();
+  levels.clear();
+  if (ev0_) cudaEventDestroy(ev0_);
+  if (ev1_) cudaEventDestroy(ev1_);
+  // buffers are stream-ordered: drain before the stream goes away
+  cudaStreamSynchronize(ctx.stream);
+}
+
+void Solver::destroy_graph() {
+  if (iter_graph_) { cudaGraphExecDestroy(iter_graph_); iter_graph_ = nullptr; }
+}
+
+void Solver::tic(const char*) { FSB_CUDA(cudaEventRecord(ev0_, ctx.stream)); }
+void Solver::toc(const char* name) {
+  FSB_CUDA(cudaEventRecord(ev1_, ctx.stream));
+  FSB_CUDA(cudaEventSynchronize(ev1_));
+  float ms = 0;
+  FSB_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
+  times_ms[name] = ms;
+}
+
+// ----------------------------------------------------------------------------- stage 1
+void Solver::set_mesh(int nv, const double* xyz, int ne, int npe, const int* elems, const int* labels, bool on_device) {
+  if (npe != 3 && npe != 4) throw std::invalid_argument("npe must be 3 (triangles) or 4 (tetrahedra)");
+  FSB_CUDA(cudaSetDevice(ctx.device));
+  cudaStream_t s = ctx.stream;
+  mesh.nv = nv; mesh.ne = ne; mesh.npe = npe;
+  mesh.xyz.alloc((size_t)nv * 3, s);
+  mesh.elems.alloc((size_t)ne * npe, s);
+  cudaMemcpyKind k = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  FSB_CUDA(cudaMemcpyAsync(mesh.xyz.get(), xyz, sizeof(double) * 3 * nv, k, s));
+  FSB_CUDA(cudaMemcpyAsync(mesh.elems.get(), elems, sizeof(int) * (size_t)ne * npe, k, s));
+  if (labels && npe == 4) {
+    mesh.labels.alloc(ne, s);
+    FSB_CUDA(cudaMemcpyAsync(mesh.labels.get(), labels, sizeof(int) * ne, k, s));
+  } else mesh.labels.release();
+  FSB_CUDA(cudaStreamSynchronize(s));
+  has_setup = false;
+}
+
+void Solver::assemble() {
+  if (mesh.nv == 0) throw std::runtime_error("no mesh");
+  FSB_CUDA(cudaSetDevice(ctx.device));
+  cudaStream_t s = ctx.stream;
+  tic("pattern");
+  build_pattern(ctx, mesh, pat);
+  toc("pattern");
+  tic("assemble");
+  A0.nrows = A0.ncols = pat.n; A0.nnz = pat.nnz;
+  A0.ptr.alloc(pat.n + 1, s); A0.col.alloc(pat.nnz, s); A0.val.alloc(pat.nnz, s);
+  A0.ptr.from_device(pat.ptr, pat.n + 1);
+  A0.col.from_device(pat.col, pat.nnz);
+  assemble_values(ctx, mesh, pat, A0.val);
+  toc("assemble");
+  // the gather lists are only needed while assembling
+  pat.contrib.release(); pat.seg.release();
+  custom_matrix = false;
+  has_setup = false;
+}
+
+void Solver::get_matrix(int* ptr, int* col, double* val) {
+  if (A0.nrows == 0) throw std::invalid_argument("Error no matrix specified");
+  if (ptr) A0.ptr.to_host(ptr, A0.nrows + 1);
+  if (col) A0.col.to_host(col, A0.nnz);
+  if (val) A0.val.to_host(val, A0.nnz);
+}
+
+void Solver::set_matrix_values(const double* val, bool on_device) {
+  if (A0.nrows == 0) throw std::invalid_argument("Error no matrix specified");
+  FSB_CUDA(cudaMemcpyAsync(A0.val.get(), val, sizeof(double) * A0.nnz, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx.stream));
+  FSB_CUDA(cudaStreamSynchronize(ctx.stream));
+  has_setup = false;
+}
+
+void Solver::set_matrix_csr(int n, int nnz, const int* ptr, const int* col, const double* val) {
+  if (pat.n != 0 && n != pat.n) throw std::invalid_argument("matrix size does not match the mesh");
+  cudaStream_t s = ctx.stream;
+  A0.nrows = A0.ncols = n; A0.nnz = nnz;
+  A0.ptr.alloc(n + 1, s); A0.col.alloc(nnz, s); A0.val.alloc(nnz, s);
+  A0.ptr.from_host(ptr, n + 1); A0.col.from_host(col, nnz); A0.val.from_host(val, nnz);
+  FSB_CUDA(cudaStreamSynchronize(s));
+  custom_matrix = true;
+  has_setup = false;
+}
+
+// ----------------------------------------------------------------------------- stage 2
+__global__ static void pstart_kernel(int nparts, const int* __restrict__ partitionIdx, const int* __restrict__ aggregateIdx, int* __restrict__ pstart) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p <= nparts) pstart[p] = aggregateIdx[partitionIdx[p]];
+}
+__global__ static void part_rows_kernel(int nparts, const int* __restrict__ pstart, int* __restrict__ rows) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < nparts) rows[p] = pstart[p + 1] - pstart[p];
+}
+
+void Solver::setup() {
+  if (A0.nrows == 0) throw std::invalid_argument("Error no matrix specified");  // FEMSolver::checkMatrixForValidContents
+  if (pat.n == 0) throw std::runtime_error("setup needs the mesh graph: call assemble() first");
+  if (prm.aggregatorType != 0) throw std::invalid_argument("only aggregatorType_ 0 (OldMIS) is implemented in this build");
+  if (prm.dsType != 0) throw std::invalid_argument("only dsType_ 0 is implemented (dsType_ 1 cannot run upstream either)");
+  if (prm.partitionMaxSize > 1024) throw std::invalid_argument("partitionMaxSize_ must be <= 1024");
+  FSB_CUDA(cudaSetDevice(ctx.device));
+  cudaStream_t s = ctx.stream;
+  destroy_graph();
+  levels.clear();
+  tic("setup");
+  levels.emplace_back();
+  {
+    LevelData& L = levels[0];
+    L.n = A0.nrows; L.level_id = 0;
+    L.A.nrows = L.A.ncols = A0.nrows; L.A.nnz = A0.nnz;
+    L.A.ptr.alloc(A0.nrows + 1, s); L.A.col.alloc(A0.nnz, s); L.A.val.alloc(A0.nnz, s);
+    L.A.ptr.from_device(A0.ptr, A0.nrows + 1); L.A.col.from_device(A0.col, A0.nnz); L.A.val.from_device(A0.val, A0.nnz);
+    graph_from_pattern(ctx, pat.n, pat.ptr, pat.col, L.xadj, L.adj);
+  }
+  int num_levels = 1;
+  while (true) {
+    LevelData& L = levels.back();
+    int N = L.A.nrows;
+    if (prm.verbose) printf("Rows: %d of max: %d\n", N, prm.topSize);
+    if (N < prm.topSize || num_levels >= prm.maxLevels) {  // amg.cu:101
+      if (N > 4096) throw std::runtime_error("coarsest level too large for the dense inverse");
+      dense_inverse(ctx, L.A, Ainv);
+      break;
+    }
+    // createNextLevel (smoothedMG_amg_level.cu:402-494)
+    aggregate_old_mis(ctx, N, L.xadj, L.adj, prm.randMisParameters, prm.partitionMaxSize, prm.seed, L.agg);
+    L.nnout = L.agg.nAgg; L.nparts = L.agg.nParts;
+    L.pstart.alloc(L.nparts + 1, s);
+    pstart_kernel<<<cdiv(L.nparts + 1, 256), 256, 0, s>>>(L.nparts, L.agg.partitionIdx, L.agg.aggregateIdx, L.pstart);
+    {
+      IBuf rows(L.nparts, s);
+      part_rows_kernel<<<cdiv(L.nparts, 256), 256, 0, s>>>(L.nparts, L.pstart, rows);
+      L.maxPartRows = reduce_max_i32(rows, L.nparts, s);
+    }
+    if (L.maxPartRows > 1024) throw std::runtime_error("largest block size is larger than shared size");  // gauss_seidel.cu:2059-2064
+    {
+      DCsr B;
+      permute_csr(ctx, L.A, L.agg.permutation, B);
+      L.A.ptr.swap(B.ptr); L.A.col.swap(B.col); L.A.val.swap(B.val);
+    }
+    L.diag.alloc(N, s);
+    extract_diag(ctx, L.A, L.diag);
+    build_prolongator(ctx, L.A, L.diag, L.agg.aggregateIdx, L.nnout, prm.proOmega, L.P);
+    transpose_csr(ctx, L.P, L.R);
+    DCsr AP, Ac;
+    spgemm(ctx, L.A, L.P, AP);
+    spgemm(ctx, L.R, AP, Ac);
+    L.b.alloc(N, s); L.x.alloc(N, s); L.x2.alloc(N, s); L.r.alloc(N, s);
+    L.bc.alloc(L.nnout, s); L.xc.alloc(L.nnout, s);
+    LevelData nx;
+    nx.n = L.nnout; nx.level_id = num_levels;
+    nx.A.nrows = Ac.nrows; nx.A.ncols = Ac.ncols; nx.A.nnz = Ac.nnz;
+    nx.A.ptr.swap(Ac.ptr); nx.A.col.swap(Ac.col); nx.A.val.swap(Ac.val);
+    nx.xadj.alloc(L.agg.xadjOut.size(), s); nx.adj.alloc(L.agg.adjOut.size(), s);
+    nx.xadj.from_device(L.agg.xadjOut, L.agg.xadjOut.size());
+    nx.adj.from_device(L.agg.adjOut, L.agg.adjOut.size());
+    if (prm.verbose) printf("level %d: rows %d nnz %d aggregates %d partitions %d (largest %d rows)\n", L.level_id, N, L.A.nnz, L.nnout, L.nparts, L.maxPartRows);
+    levels.push_back(std::move(nx));
+    num_levels++;
+  }
+  toc("setup");
+  has_setup = true;
+}
+
+// ----------------------------------------------------------------------------- stage 3
+// One V-cycle on level `lev`.  b_src is read through `gather` (external -> internal numbering,
+// null when b_src is already internal); the result goes to x_dst in internal numbering
+// (scatter == null) or is scattered to the external numbering through `scatter`.
+void Solver::vcycle(int lev, const double* b_src, const int* gather, double* x_dst, const int* scatter, double* /*unused*/) {
+  LevelData& L = levels[lev];
+  const int* done = cg_active_ ? &scal.get()->done : nullptr;
+  if (lev == (int)levels.size() - 1) {  // coarsest: direct solve (amg_level.cu:25-31)
+    launch_coarse_solve(ctx, L.n, Ainv, b_src, x_dst, done);
+    return;
+  }
+  const double w = prm.smootherWeight;
+  const double* b_eff = gather ? L.b.get() : b_src;
+  launch_pre_smooth(ctx, L, b_src, gather, gather ? L.b.get() : nullptr, w, prm.preInnerIters, L.x, done);
+  launch_spmv(ctx, L.A, L.x, L.r, 1, b_eff, done);            // r = b - A x
+  launch_spmv(ctx, L.R, L.r, L.bc, 0, nullptr, done);         // bc = R r
+  const bool next_is_coarsest = (lev + 1 == (int)levels.size() - 1);
+  const int* ip = next_is_coarsest ? nullptr : levels[lev + 1].agg.ipermutation.get();
+  vcycle(lev + 1, L.bc, ip, L.xc, ip, nullptr);
+  launch_spmv(ctx, L.P, L.xc, L.x, 2, nullptr, done);         // x += P xc
+  double* xin = L.x;
+  double* xtmp = L.x2;
+  for (int rel = 0; rel < prm.postRelaxes; rel++) {
+    bool lastpass = (rel == prm.postRelaxes - 1);
+    if (lastpass) launch_post_smooth(ctx, L, b_eff, xin, w, prm.postInnerIters, scatter ? nullptr : x_dst, scatter, scatter ? x_dst : nullptr, done);
+    else { launch_post_smooth(ctx, L, b_eff, xin, w, prm.postInnerIters, xtmp, nullptr, nullptr, done); std::swap(xin, xtmp); }
+  }
+  if (prm.postRelaxes <= 0) {  // degenerate configuration: no post-relaxation pass
+    if (scatter) launch_scatter(ctx, L.n, scatter, xin, x_dst);
+    else FSB_CUDA(cudaMemcpyAsync(x_dst, xin, sizeof(double) * L.n, cudaMemcpyDeviceToDevice, ctx.stream));
+  }
+}
+
+void Solver::spmv_fine(const double* x, double* y) { launch_spmv(ctx, levels.at(0).A, x, y, 0, nullptr, nullptr); FSB_CUDA(cudaStreamSynchronize(ctx.stream)); }
+
+void Solver::precondition(const double* r, double* z) {
+  if (!has_setup) throw std::runtime_error("precondition before setup");
+  cg_active_ = false;
+  vcycle(0, r, nullptr, z, nullptr, nullptr);
+  FSB_CUDA(cudaStreamSynchronize(ctx.stream));
+}
+
+void Solver::enqueue_pcg_iteration() {
+  const int n = levels[0].n;
+  PcgScalars* sc = scal.get();
+  launch_spmv_dot(ctx, levels[0].A, cg_p, cg_y, partials, sc);               // y = A p, alpha = rz / (p.y)
+  launch_cg_update(ctx, n, cg_x, cg_r, cg_p, cg_y, partials, sc, hist);      // x += alpha p, r -= alpha y, ||r||, test
+  vcycle(0, cg_r, nullptr, cg_z, nullptr, nullptr);                          // z = M^-1 r
+  launch_dot(ctx, n, cg_r, cg_z, partials, sc, 2);                           // rz_new, beta
+  launch_cg_pdir(ctx, n, cg_p, cg_z, sc, 0);                                 // p = z + beta p
+}
+
+void Solver::pcg(const double* b_user, double* x_user) {
+  cudaStream_t s = ctx.stream;
+  LevelData& L0 = levels[0];
+  const int n = L0.n;
+  const bool single = levels.size() == 1;
+  const bool permute = !single && !prm.refLevel0NoPerm;
+  // work vectors persist across solves so a captured iteration graph stays valid
+  auto ensure = [&](DBuf& v, size_t m) { if (v.size() != m) v.alloc(m, s); };
+  ensure(cg_b, n); ensure(cg_x, n); ensure(cg_r, n); ensure(cg_z, n); ensure(cg_p, n); ensure(cg_y, n);
+  size_t npart = std::max<size_t>((size_t)cdiv((long long)n * 32, 256), (size_t)ctx.num_sms * 8) + 1;
+  ensure(partials, npart);
+  ensure(hist, (size_t)prm.maxIters + 2);
+  if (scal.size() != 1) scal.alloc(1, s);
+  PcgScalars* sc = scal.get();
+  cg_active_ = true;
+  GraphKey key = {cg_b.get(), cg_x.get(), cg_r.get(), cg_z.get(), cg_p.get(), cg_y.get(), partials.get(), hist.get(), (void*)sc,
+                  prm.preInnerIters, prm.postInnerIters, prm.postRelaxes, prm.smootherWeight};
+  if (iter_graph_ && memcmp(&key, &graph_key_, sizeof(GraphKey)) != 0) destroy_graph();
+  graph_key_ = key;
+  launch_cg_init(ctx, sc, prm.tolerance, prm.maxIters);
+  if (permute) {  // the whole iteration lives in the level-0 permuted numbering
+    launch_gather(ctx, n, L0.agg.ipermutation, b_user, cg_b);
+    launch_gather(ctx, n, L0.agg.ipermutation, x_user, cg_x);
+  } else {
+    cg_b.from_device(b_user, n); cg_x.from_device(x_user, n);
+  }
+  launch_dot(ctx, n, cg_b, cg_b, partials, sc, 0);                 // bnorm
+  launch_spmv(ctx, L0.A, cg_x, cg_r, 1, cg_b, nullptr);            // r = b - A x
+  vcycle(0, cg_r, nullptr, cg_z, nullptr, nullptr);                // z = M^-1 r
+  launch_cg_pdir(ctx, n, cg_p, cg_z, sc, 1);                       // p = z
+  launch_dot(ctx, n, cg_r, cg_z, partials, sc, 1);                 // rz_old
+  FSB_CUDA(cudaStreamSynchronize(s));
+
+  if (prm.useGraphs && !iter_graph_) {
+    cudaGraph_t g;
+    FSB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    enqueue_pcg_iteration();
+    FSB_CUDA(cudaStreamEndCapture(s, &g));
+    FSB_CUDA(cudaGraphInstantiate(&iter_graph_, g, 0));
+    FSB_CUDA(cudaGraphDestroy(g));
+  }
+  long long per_iter = 0;
+  {
+    long long before = g_launch_counter;
+    // count the kernels of one iteration without launching: known structure
+    per_iter = 4 + 1 + (long long)(levels.size() - 1) * (4 + std::max(prm.postRelaxes, 1));
+    (void)before;
+  }
+  PcgScalars h;
+  int enq = 0;
+  const int chunk = std::max(1, prm.checkEvery);
+  while (true) {
+    for (int i = 0; i < chunk; i++) {
+      if (iter_graph_) { FSB_CUDA(cudaGraphLaunch(iter_graph_, s)); g_launch_counter += per_iter; }
+      else enqueue_pcg_iteration();
+      enq++;
+    }
+    FSB_CUDA(cudaMemcpyAsync(&h, sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, s));
+    FSB_CUDA(cudaStreamSynchronize(s));
+    if (h.done || enq > prm.maxIters + chunk) break;
+  }
+  iterations = h.niter;
+  resid_history.resize(h.hist_len);
+  if (h.hist_len) hist.to_host(resid_history.data(), h.hist_len);
+  final_relres = h.hist_len ? resid_history.back() : -1;
+  if (permute) launch_scatter(ctx, n, L0.agg.ipermutation, cg_x, x_user);
+  else FSB_CUDA(cudaMemcpyAsync(x_user, cg_x.get(), sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
+  FSB_CUDA(cudaStreamSynchronize(s));
+}
+
+void Solver::solve(const double* b, double* x, bool on_device) {
+  if (!has_setup) throw std::runtime_error("solve before setup");
+  FSB_CUDA(cudaSetDevice(ctx.device));
+  cudaStream_t s = ctx.stream;
+  const int n = levels[0].n;
+  g_launch_counter = 0;
+  DBuf bd, xd;
+  const double* bp = b;
+  double* xp = x;
+  if (!on_device) {
+    bd.alloc(n, s); xd.alloc(n, s);
+    bd.from_host(b, n); xd.from_host(x, n);
+    bp = bd; xp = xd;
+  }
+  tic("solve");
+  if (prm.solverType == 1) {
+    pcg(bp, xp);
+  } else {
+    // AMG_SOLVER: exactly ONE V-cycle, whatever maxIters_/tolerance_ say (amg.cu:187-194);
+    // the incoming x is overwritten (every cycle starts from a zero guess).
+    cg_active_ = false;
+    const bool single = levels.size() == 1;
+    const int* ip = (single || prm.refLevel0NoPerm) ? nullptr : levels[0].agg.ipermutation.get();
+    DBuf xo(n, s);
+    vcycle(0, bp, ip, xo, ip, nullptr);
+    FSB_CUDA(cudaMemcpyAsync(xp, xo.get(), sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
+    iterations = 1; final_relres = -1; resid_history.clear();
+  }
+  toc("solve");
+  launches = g_launch_counter;
+  if (!on_device) xd.to_host(x, n);
+}
+
+}  // namespace fsb

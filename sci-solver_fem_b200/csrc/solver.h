@@ -1,0 +1,101 @@
+// solver.h — the host layer of the path: FEMSolver-equivalent state machine
+// (mesh -> assemble -> AMG setup -> solve) over the device kernels.
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "fsb_internal.h"
+
+namespace fsb {
+
+// parameter surface of the reference's FEMSolver (src/FEMSolver.h:28-66, defaults FEMSolver.cu:11-34)
+struct Params {
+  int verbose = 0;
+  int maxLevels = 100, maxIters = 100, preInnerIters = 5, postInnerIters = 5, postRelaxes = 1, cycleIters = 1;
+  int dsType = 0, topSize = 256, randMisParameters = 90102, partitionMaxSize = 512, aggregatorType = 0;
+  int convergeType = 0, cycleType = 0, solverType = 0, device = 0, blockSize = 256;
+  double tolerance = 1e-6, smootherWeight = 1.0, proOmega = 0.67;
+  // additive surface: deterministic aggregation seed; reference level-0 quirk switch
+  unsigned seed = 0;
+  int refLevel0NoPerm = 0;
+  int useGraphs = 1;   // capture one PCG iteration into a CUDA graph
+  int checkEvery = 2;  // PCG iterations enqueued between convergence polls
+};
+
+// device-resident PCG state: no scalar ever crosses PCIe inside the iteration
+struct PcgScalars {
+  double rz_old, rz_new, py, alpha, beta, rr, bnorm, tol;
+  int done, niter, maxit, hist_len;
+  unsigned int ticket[4];
+};
+
+struct LevelData {
+  int n = 0, nnout = 0, nparts = 0, maxPartRows = 0, level_id = 0;
+  DCsr A;             // permuted numbering (rows of a partition contiguous); coarsest: external numbering
+  DBuf diag;
+  DCsr P, R;          // P: rows internal(l), cols external(l+1); R = P^T
+  Aggregation agg;
+  IBuf pstart;        // first row of each partition (nparts+1)
+  IBuf xadj, adj;     // graph handed to the aggregator (external numbering)
+  DBuf b, x, x2, r;   // work vectors, internal numbering
+  DBuf bc, xc;        // restricted residual / coarse correction, external numbering of level l+1
+};
+
+class Solver {
+ public:
+  explicit Solver(int device);
+  ~Solver();
+  Params prm;
+  std::string last_error;
+
+  // stage 1
+  void set_mesh(int nv, const double* xyz, int ne, int npe, const int* elems, const int* labels, bool on_device);
+  void assemble();                      // pattern + element loop  (FEMSolver::getMatrixFromMesh)
+  int rows() const { return A0.nrows; }
+  int nnz() const { return A0.nnz; }
+  void get_matrix(int* ptr, int* col, double* val);
+  void set_matrix_values(const double* val, bool on_device);
+  void set_matrix_csr(int n, int nnz, const int* ptr, const int* col, const double* val);  // e.g. readMatlabSparseMatrix result
+  // stage 2
+  void setup();                         // AMG::setup
+  int num_levels() const { return (int)levels.size(); }
+  const LevelData& level(int l) const { return levels.at(l); }
+  // stage 3
+  void solve(const double* b, double* x, bool on_device);  // AMG::solve; x = initial guess in, solution out
+  int iterations = 0;
+  double final_relres = -1;
+  std::vector<double> resid_history;
+  std::map<std::string, double> times_ms;
+  // kernel-level entry points for tests / microbenchmarks (device pointers, level-0 internal numbering)
+  void spmv_fine(const double* x, double* y);
+  void precondition(const double* r, double* z);   // one V-cycle, z = M^-1 r
+  long long launches = 0;              // kernels launched by the last solve()
+
+  Ctx ctx;
+  Mesh mesh;
+  Pattern pat;
+  DCsr A0;                              // user-order fine matrix
+  bool custom_matrix = false;
+  std::vector<LevelData> levels;
+  DBuf Ainv;                            // dense inverse of the coarsest operator
+  bool has_setup = false;
+
+ private:
+  void vcycle(int lev, const double* b_ext, const int* gather, double* x_ext, const int* scatter, double* x_int_out);
+  void pcg(const double* b_user, double* x_user);
+  void enqueue_pcg_iteration();
+  void tic(const char* name);
+  void toc(const char* name);
+  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+  // PCG state
+  DBuf cg_b, cg_x, cg_r, cg_z, cg_p, cg_y, partials, hist;
+  DevBuf<PcgScalars> scal;
+  cudaGraphExec_t iter_graph_ = nullptr;
+  struct GraphKey { void* p[9]; int pre, post, relaxes; double w; };
+  GraphKey graph_key_ = {};
+  bool cg_active_ = false;
+  void destroy_graph();
+};
+
+}  // namespace fsb

@@ -1,0 +1,251 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle on the same inputs.
+
+Bars (BASELINE.json north_star): CSR pattern and aggregates bit-exact; matrix values and the
+hierarchy within 1e-12 relative (observed: bit-identical); solution within 1e-6 relative L2,
+PCG iteration count within +-2.
+"""
+import numpy as np
+import pytest
+
+import sci_solver_fem_b200 as fsb
+from tests.util import egg_carton, golden, kuhn, make_gpu, make_oracle, rel
+
+pytestmark = pytest.mark.gpu
+
+PCG = dict(solverType=1, tolerance=1e-8, maxIters=200, seed=0)
+INT_ARRAYS = ["permutation", "ipermutation", "aggregateIdx", "partitionIdx", "partitionLabel", "xadjOut", "adjOut",
+              "A_ptr", "A_col", "P_ptr", "P_col", "R_ptr", "R_col"]
+
+
+def meshes():
+    v, t = kuhn(12)
+    yield "kuhn12", v, t, None
+    g = golden("tetVol")
+    yield "tetVol", g["verts"], g["tets"], g["labels"]
+    g = golden("CubeMesh_size256step16")  # inverted tets + non-conforming faces
+    yield "cube256", g["verts"], g["tets"], g["labels"]
+    g = golden("simple2d")
+    yield "simple2d", g["verts"], g["tris"], None
+    g = golden("sphere_290verts")
+    yield "sphere", g["verts"], g["tris"], None
+
+
+@pytest.mark.parametrize("name,verts,elems,labels", list(meshes()), ids=lambda x: x if isinstance(x, str) else None)
+def test_pattern_and_values(name, verts, elems, labels):
+    o, ptr, col, val = make_oracle(verts, elems, labels)
+    s = make_gpu(verts, elems, labels)
+    gptr, gcol, gval = s.matrix_csr()
+    assert np.array_equal(gptr, ptr), "row offsets differ"
+    assert np.array_equal(gcol, col), "column indices differ"
+    scale = np.abs(val).max()
+    assert np.abs(gval - val).max() <= 1e-12 * scale
+    # the deterministic gather + -fmad=false element kernel reproduces the host-order sum to the bit
+    assert np.array_equal(gval, val), "assembled values are not bit-identical (max diff %g)" % np.abs(gval - val).max()
+
+
+def test_material_labels():
+    v, t = kuhn(8)
+    lab = fsb.meshio.kuhn_cell_labels(8, block=2)
+    o, ptr, col, val = make_oracle(v, t, lab)
+    s = make_gpu(v, t, lab)
+    assert np.array_equal(s.matrix_csr()[2], val)
+
+
+def _setup_pair(verts, elems, labels=None, **params):
+    o, ptr, col, val = make_oracle(verts, elems, labels, **params)
+    nl = o.setup()
+    s = make_gpu(verts, elems, labels, **params)
+    s.setup()
+    return o, s, nl
+
+
+@pytest.mark.parametrize("N,seed", [(12, 0), (20, 0), (20, 7)])
+def test_hierarchy_bit_exact(N, seed):
+    v, t = kuhn(N)
+    o, s, nl = _setup_pair(v, t, seed=seed)
+    assert s.num_levels() == nl
+    for lev in range(nl):
+        assert s.level_rows(lev) == o.level_rows(lev)
+    for lev in range(nl - 1):
+        for name in INT_ARRAYS:
+            a, b = s.level_int(lev, name), o.level_int(lev, name)
+            assert a.shape == b.shape, (lev, name, a.shape, b.shape)
+            assert np.array_equal(a, b), (lev, name, int(np.argmax(a != b)))
+        for name in ["A_val", "P_val", "R_val", "diag"]:
+            a, b = s.level_val(lev, name), o.level_val(lev, name)
+            assert np.abs(a - b).max() <= 1e-12 * np.abs(b).max(), (lev, name)
+            assert np.array_equal(a, b), (lev, name, "not bit-identical", np.abs(a - b).max())
+    # coarsest operator
+    a, b = s.level_val(nl - 1, "A_val"), o.level_val(nl - 1, "A_val")
+    assert np.array_equal(s.level_int(nl - 1, "A_col"), o.level_int(nl - 1, "A_col"))
+    assert np.array_equal(a, b)
+
+
+def test_hierarchy_tri_and_unstructured():
+    g = golden("simple2d")
+    o, s, nl = _setup_pair(g["verts"], g["tris"], seed=3)
+    assert s.num_levels() == nl and nl >= 2
+    for lev in range(nl - 1):
+        for name in INT_ARRAYS:
+            assert np.array_equal(s.level_int(lev, name), o.level_int(lev, name)), (lev, name)
+    g = golden("tetVol")
+    o, s, nl = _setup_pair(g["verts"], g["tets"], seed=0)
+    for lev in range(nl - 1):
+        for name in INT_ARRAYS:
+            assert np.array_equal(s.level_int(lev, name), o.level_int(lev, name)), (lev, name)
+
+
+def test_coarse_inverse():
+    v, t = kuhn(12)
+    o, s, nl = _setup_pair(v, t)
+    n = s.level_rows(nl - 1)
+    import scipy.sparse as sp
+    A = sp.csr_matrix((s.level_val(nl - 1, "A_val"), s.level_int(nl - 1, "A_col"), s.level_int(nl - 1, "A_ptr")), shape=(n, n)).toarray()
+    Ainv = s.level_val(nl - 1, "Ainv").reshape(n, n)
+    assert np.abs(Ainv @ A - np.eye(n)).max() < 1e-9
+
+
+@pytest.mark.parametrize("N", [12, 24])
+def test_pcg_parity(N):
+    v, t = kuhn(N)
+    o, s, nl = _setup_pair(v, t, **PCG)
+    xstar = egg_carton(v)
+    b = o.spmv(xstar)
+    xo, ito = o.solve(b)
+    xg = s.solve(np.zeros_like(b), b)
+    assert abs(s.iterations - ito) <= 2, (s.iterations, ito)
+    assert s.relres <= 1e-8
+    assert rel(xg, xo) <= 1e-6
+    ho, hg = o.resid_history(), s.resid_history()
+    m = min(len(ho), len(hg))
+    assert np.allclose(hg[:m], ho[:m], rtol=1e-6), "residual histories diverge"
+    # true residual with the oracle's operator
+    assert np.linalg.norm(b - o.spmv(xg)) / np.linalg.norm(b) <= 2e-8
+
+
+def test_single_vcycle_amg_solver():
+    """solverType_ = 0 runs exactly one V-cycle."""
+    v, t = kuhn(12)
+    o, s, nl = _setup_pair(v, t, solverType=0, seed=0)
+    b = o.spmv(egg_carton(v))
+    xo, _ = o.solve(b)
+    xg = s.solve(np.zeros_like(b), b)
+    assert s.iterations == 1
+    assert rel(xg, xo) <= 1e-10
+
+
+def test_reference_level0_quirk_mode():
+    """refLevel0NoPerm_ = 1 reproduces the reference's missing level-0 permutation."""
+    v, t = kuhn(12)
+    o, s, nl = _setup_pair(v, t, refLevel0NoPerm=1, **PCG)
+    b = o.spmv(egg_carton(v))
+    xo, ito = o.solve(b)
+    xg = s.solve(np.zeros_like(b), b)
+    assert abs(s.iterations - ito) <= 2
+    assert rel(xg, xo) <= 1e-6
+
+
+def test_tiny_mesh_is_single_level():
+    v, t = kuhn(4)  # 125 rows < topSize_
+    o, s, nl = _setup_pair(v, t, **PCG)
+    assert nl == 1 and s.num_levels() == 1
+    b = o.spmv(egg_carton(v) + 1.0)
+    xo, ito = o.solve(b)
+    xg = s.solve(np.zeros_like(b), b)
+    assert s.iterations == ito == 0 or abs(s.iterations - ito) <= 1
+    assert rel(xg, xo) <= 1e-8
+
+
+def test_max_iters_cap_and_initial_guess():
+    v, t = kuhn(12)
+    o, s, nl = _setup_pair(v, t, solverType=1, tolerance=1e-14, maxIters=3, seed=0)
+    rng = np.random.default_rng(1234)
+    b = rng.uniform(-1, 1, len(v))
+    x0 = rng.uniform(-1, 1, len(v))
+    xo, ito = o.solve(b, x0)
+    xg = s.solve(x0.copy(), b)
+    assert s.iterations == ito == 3
+    assert rel(xg, xo) <= 1e-9
+
+
+def test_smoother_parameters():
+    v, t = kuhn(12)
+    prm = dict(PCG, preInnerIters=2, postInnerIters=3, postRelaxes=2, smootherWeight=0.8, proOmega=0.5, partitionMaxSize=300)
+    o, s, nl = _setup_pair(v, t, **prm)
+    b = o.spmv(egg_carton(v))
+    xo, ito = o.solve(b)
+    xg = s.solve(np.zeros_like(b), b)
+    assert abs(s.iterations - ito) <= 2
+    assert rel(xg, xo) <= 1e-6
+
+
+def test_tetvol_known_answer():
+    """The reference's one genuine known-answer fixture (src/test/tetVol.cc) at a meaningful tolerance."""
+    g = golden("tetVol")
+    s = make_gpu(g["verts"], g["tets"], g["labels"], **PCG)
+    fptr, fcol, fval = fsb.meshio.csc_to_csr(int(g["A_nrows"]), int(g["A_ncols"]), g["A_jc"], g["A_ir"], g["A_pr"])
+    s.set_matrix_from_csr(fptr, fcol, fval)
+    x = s.solveFEM(np.zeros(len(g["b"])), g["b"])
+    assert s.relres <= 1e-8
+    assert rel(x, g["ans"]) <= 1e-4
+    assert np.linalg.norm(x - g["ans"]) < 25  # tetVol.cc:24
+
+
+@pytest.mark.parametrize("name,key,thr", [("simple3d", "tets", 1.0), ("simple2d", "tris", 100.0), ("tetVol", "tets", 25.0)])
+def test_reference_gtests_default_parameters(name, key, thr):
+    """sanity3D.cc / sanity2D.cc / tetVol.cc as shipped: default parameters = one V-cycle, -A -b fixtures."""
+    g = golden(name)
+    s = make_gpu(g["verts"], g[key], g["labels"] if "labels" in g else None)
+    fptr, fcol, fval = fsb.meshio.csc_to_csr(int(g["A_nrows"]), int(g["A_ncols"]), g["A_jc"], g["A_ir"], g["A_pr"])
+    s.set_matrix_from_csr(fptr, fcol, fval)
+    x = s.solveFEM(np.ones(len(g["b"])), g["b"].copy())
+    assert np.linalg.norm(x - g["ans"]) < thr
+
+
+def test_properties_at_scale():
+    """Size-independent properties on a mesh the oracle would take long on (N=64, 275k rows)."""
+    v, t = kuhn(64)
+    s = make_gpu(v, t, **PCG)
+    ptr, col, val = s.matrix_csr()
+    import scipy.sparse as sp
+    A = sp.csr_matrix((val, col, ptr))
+    assert abs(A - A.T).max() <= 1e-12 * abs(A).max()
+    # K has zero row sums, so sum(A) = sum(M) = volume of the unit cube
+    assert abs(A.sum() - 1.0) < 1e-9
+    xstar = egg_carton(v)
+    b = A @ xstar
+    s.setup()
+    for lev in range(s.num_levels() - 1):
+        perm, iperm = s.level_int(lev, "permutation"), s.level_int(lev, "ipermutation")
+        assert np.array_equal(perm[iperm], np.arange(perm.size))
+        aidx, pidx = s.level_int(lev, "aggregateIdx"), s.level_int(lev, "partitionIdx")
+        assert aidx[0] == 0 and aidx[-1] == perm.size and np.all(np.diff(aidx) >= 9)  # minAggregateSize
+        assert np.all(np.diff(aidx[pidx]) <= 512)                                     # partitionMaxSize_
+        # un-normalised tentative prolongator: P has row sums 1 - omega*rowsum(A)/diag
+        n, m = s.level_rows(lev), s.level_rows(lev + 1)
+        P = sp.csr_matrix((s.level_val(lev, "P_val"), s.level_int(lev, "P_col"), s.level_int(lev, "P_ptr")), shape=(n, m))
+        Al = sp.csr_matrix((s.level_val(lev, "A_val"), s.level_int(lev, "A_col"), s.level_int(lev, "A_ptr")), shape=(n, n))
+        Ac = sp.csr_matrix((s.level_val(lev + 1, "A_val"), s.level_int(lev + 1, "A_col"), s.level_int(lev + 1, "A_ptr")), shape=(m, m))
+        if lev + 1 < s.num_levels() - 1:  # stored permuted: compare spectra-free invariant
+            assert abs(Ac.sum() - (P.T @ Al @ P).sum()) <= 1e-9 * abs(Ac.sum())
+        else:
+            assert abs(Ac - P.T @ Al @ P).max() <= 1e-11 * abs(Ac).max()
+    x1 = s.solve(np.zeros_like(b), b)
+    assert s.relres <= 1e-8
+    assert np.linalg.norm(b - A @ x1) / np.linalg.norm(b) <= 2e-8
+    assert rel(x1, xstar) <= 1e-5
+    it1 = s.iterations
+    x2 = s.solve(np.zeros_like(b), b)
+    assert s.iterations == it1 and np.array_equal(x1, x2), "solve is not bit-reproducible"
+
+
+def test_errors():
+    s = fsb.FEMSolver(None)
+    with pytest.raises(ValueError, match="Error no matrix specified"):
+        s.solveFEM(np.zeros(3), np.zeros(3))
+    v, t = kuhn(4)
+    s = make_gpu(v, t)
+    s.aggregatorType_ = 3
+    s.topSize_ = 16
+    with pytest.raises(ValueError):
+        s.setup()

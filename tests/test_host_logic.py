@@ -1,0 +1,116 @@
+"""CPU-only tests of the host-side pieces: data formats, the C-ABI surface, the import contract."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import sci_solver_fem_b200 as fsb
+from tests.util import golden, kuhn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+meshio = fsb.meshio
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    L = fsb.load_library()
+    hdr = open(os.path.join(ROOT, "include", "femsolver_b200.h")).read()
+    declared = set(re.findall(r"\b(fsb_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(fsb.EXPORTED_SYMBOLS), declared ^ set(fsb.EXPORTED_SYMBOLS)
+    raw = C.CDLL(os.path.join(ROOT, "sci-solver_fem_b200", "libfemsolver_b200.so"))
+    for name in declared:
+        assert hasattr(raw, name), name
+    assert L.fsb_version() >= 100
+
+
+def test_no_cpu_fallback_without_device():
+    L = fsb.load_library()
+    if L.fsb_device_count() > 0:
+        pytest.skip("a device is present")
+    with pytest.raises(fsb.FEMSolverError, match="no CPU fallback"):
+        fsb.FEMSolver(None)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "sci-solver_fem_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if "build" in dirpath.split(os.sep):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "fem_oracle" not in src and "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_host_quadrature_tables_match_oracle_bitwise():
+    from oracle.oracle import lib
+    L = fsb.load_library()
+    a, b = np.zeros(10), np.zeros(10)
+    L.fsb_tet_mass_integrals(a.ctypes.data_as(C.c_void_p))
+    lib().orc_tet_mass_integrals(b.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(a, b)
+    exact = np.array([2, 1, 1, 1, 2, 1, 1, 2, 1, 2]) / 15.0
+    assert np.abs(a - exact).max() < 1e-14
+    zx, zy, wx, wy = (np.zeros(6) for _ in range(4))
+    L.fsb_tri_quadrature(*(z.ctypes.data_as(C.c_void_p) for z in (zx, zy, wx, wy)))
+    # Newton stops at |step| < 1e-6 (FEM3D.cu:221), so the rules are Gauss rules only to ~1e-11
+    assert abs(wx.sum() - 2.0) < 1e-10 and abs(wy.sum() - 2.0) < 1e-10   # int 1 dx, int (1-y) dy on [-1,1]
+    assert zx[0] == -1 and zx[-1] == 1 and zy[0] == -1
+
+
+def test_mat_roundtrip(tmp_path):
+    x = np.random.default_rng(0).normal(size=37)
+    p = str(tmp_path / "x.mat")
+    meshio.write_mat_array(p, x)
+    assert np.array_equal(meshio.read_mat_array(p), x)
+    raw = open(p, "rb").read()
+    assert raw.startswith(b"MATLAB 5.0 MAT-file, Platform: GLNXA64, Created by SCI-Solver_FEM.")
+    assert raw[124:128] == b"\x00\x01IM" and len(raw) == 128 + 8 + 48 + 37 * 8
+    import scipy.io
+    assert np.array_equal(scipy.io.loadmat(p)["x_h"].ravel(), x)
+
+
+def test_mat_sparse_fixture_parse():
+    g = golden("simple3d")
+    ptr, col, val = meshio.csc_to_csr(int(g["A_nrows"]), int(g["A_ncols"]), g["A_jc"], g["A_ir"], g["A_pr"])
+    assert ptr[-1] == 5000 and np.array_equal(col, np.arange(5000)) and np.allclose(val, 8 * np.pi ** 2 + 1, rtol=1e-6)
+
+
+def test_node_ele_roundtrip_and_float_rounding(tmp_path):
+    v, t = kuhn(3, h=0.1)
+    base = str(tmp_path / "m")
+    meshio.write_node_ele(base, v, t, labels=np.arange(len(t)) % 7)
+    v2, t2, lab2 = meshio.read_node_ele(base)
+    assert np.array_equal(t2, t) and np.array_equal(lab2, np.arange(len(t)) % 7)
+    assert np.array_equal(v2, v.astype(np.float32).astype(np.float64))   # %f into float (tetmesh.cu:285-292)
+    # one-based files are shifted down
+    with open(base + ".ele") as f:
+        lines = f.read().splitlines()
+    with open(base + ".ele", "w") as f:
+        f.write(lines[0] + "\n")
+        for ln in lines[1:]:
+            p = ln.split()
+            f.write(" ".join([p[0]] + [str(int(q) + 1) for q in p[1:5]] + p[5:]) + "\n")
+    _, t3, _ = meshio.read_node_ele(base)
+    assert np.array_equal(t3, t)
+
+
+def test_ply_roundtrip(tmp_path):
+    v, f = meshio.grid_tri(4, 3)
+    p = str(tmp_path / "g.ply")
+    meshio.write_ply_ascii(p, v, f)
+    v2, f2 = meshio.read_ply_ascii(p)
+    assert np.array_equal(v2, v) and np.array_equal(f2, f)
+    g = golden("simple2d")
+    assert g["verts"].shape == (2500, 3) and g["tris"].shape == (4802, 3)
+
+
+def test_kuhn_cube_counts_and_orientation():
+    v, t = kuhn(6)
+    assert v.shape == (343, 3) and t.shape == (6 * 216, 4)
+    X = v[t]
+    vol = np.linalg.det(X[:, 1:] - X[:, :1]) / 6
+    assert np.all(vol > 0) and abs(vol.sum() - 1) < 1e-6
+    lab = meshio.kuhn_cell_labels(16, block=8)
+    assert lab.shape == (6 * 16 ** 3,) and set(np.unique(lab)) <= set(range(1, 7))

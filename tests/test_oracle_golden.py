@@ -1,0 +1,241 @@
+"""Pins the CPU oracle (oracle/fem_oracle.cpp) against the reference's own test fixtures and against
+SciPy as independent ground truth.  CPU only."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spl
+
+import sci_solver_fem_b200 as fsb
+from oracle.oracle import Oracle, randomized_mis
+from tests.util import egg_carton, golden, kuhn, make_oracle, rel
+
+meshio = fsb.meshio
+
+
+def file_matrix(g):
+    return meshio.csc_to_csr(int(g["A_nrows"]), int(g["A_ncols"]), g["A_jc"], g["A_ir"], g["A_pr"])
+
+
+def test_pattern_equals_tetvol_fixture():
+    """tetVolA.mat (a SciRun Laplacian) has exactly the mesh pattern: pins need_neighbors + tetmesh2ell."""
+    g = golden("tetVol")
+    o = Oracle(64)
+    ptr, col = o.pattern(len(g["verts"]), g["tets"])
+    fptr, fcol, _ = file_matrix(g)
+    assert col.size == 129844
+    assert np.array_equal(ptr, fptr) and np.array_equal(col, fcol)
+
+
+@pytest.mark.parametrize("name,nnz", [("CubeMesh_size256step16", 82321), ("CubeMesh_size256step16_correct", 66961)])
+def test_pattern_sizes_of_example_meshes(name, nnz):
+    g = golden(name)
+    o = Oracle(64)
+    ptr, col = o.pattern(len(g["verts"]), g["tets"])
+    assert col.size == nnz
+    assert np.all(np.diff(ptr) >= 1)
+    for i in (0, 100, 4912):  # ascending columns including the diagonal
+        row = col[ptr[i]:ptr[i + 1]]
+        assert np.all(np.diff(row) > 0) and i in row
+
+
+def test_kuhn_generator_reproduces_reference_mesh():
+    g = golden("CubeMesh_size256step16_correct")
+    v, t = kuhn(16, h=16.0)
+    assert np.array_equal(t, g["tets"])
+    assert np.array_equal(v, g["verts"])
+
+
+def test_tetvol_known_answer_pcg():
+    g = golden("tetVol")
+    o = Oracle(64, solverType=1, tolerance=1e-8, maxIters=200, seed=0)
+    o.pattern(len(g["verts"]), g["tets"])
+    fptr, fcol, fval = file_matrix(g)
+    o.set_values(fval)
+    assert o.setup() == 3
+    x, it = o.solve(g["b"])
+    A = sp.csr_matrix((fval, fcol, fptr))
+    assert it < 20
+    assert np.linalg.norm(g["b"] - A @ x) / np.linalg.norm(g["b"]) <= 1e-8
+    assert rel(x, g["ans"]) <= 1e-4          # fixture itself: ||b - A ans||/||b|| = 6.7e-6
+    assert np.linalg.norm(x - g["ans"]) < 25  # the reference's own assertion (tetVol.cc:24)
+    xs = spl.spsolve(A.tocsc(), g["b"])
+    assert rel(x, xs) <= 1e-6
+
+
+@pytest.mark.parametrize("precision", [64, 32])
+@pytest.mark.parametrize("name,key,thr,diag", [("simple3d", "tets", 1.0, 79.9568), ("simple2d", "tris", 100.0, 26.1327)])
+def test_diagonal_fixtures_one_vcycle(name, key, thr, diag, precision):
+    """sanity3D.cc / sanity2D.cc: file matrix c*I merged onto the mesh pattern, default parameters
+    (solverType_ 0 = one V-cycle).  For a (numerically) diagonal system the first Jacobi step is exact."""
+    g = golden(name)
+    o = Oracle(precision, seed=0)
+    ptr, col = o.pattern(len(g["verts"]), g[key])
+    fptr, fcol, fval = file_matrix(g)
+    assert np.allclose(fval, diag, rtol=1e-5) and np.array_equal(fcol, np.arange(len(fcol)))
+    n = ptr.size - 1
+    M = sp.csr_matrix((np.full(col.size, 1e-12), col, ptr), shape=(n, n)) + sp.csr_matrix((fval, fcol, fptr), shape=(n, n))
+    M.sort_indices()
+    assert np.array_equal(M.indices, col)
+    o.set_values(M.data)
+    o.setup()
+    x, it = o.solve(g["b"], np.ones(n))
+    assert it == 1
+    assert np.linalg.norm(x - g["ans"]) < thr
+    assert rel(x, g["b"] / diag) < 1e-5
+
+
+def test_assembly_against_independent_p1_formulas():
+    """K + M of the restated element loop vs textbook P1 matrices built with numpy."""
+    v, t = kuhn(5)
+    o, ptr, col, val = make_oracle(v, t)
+    n = len(v)
+    rows, cols, vals = [], [], []
+    for tet in t:
+        X = np.hstack([v[tet], np.ones((4, 1))])
+        C = np.linalg.inv(X)
+        G = C[:3, :].T
+        vol = abs(np.linalg.det(X)) / 6
+        K = vol * G @ G.T
+        Mm = vol / 20 * (np.ones((4, 4)) + np.eye(4))
+        for a in range(4):
+            for b in range(4):
+                rows.append(tet[a]); cols.append(tet[b]); vals.append(K[a, b] + Mm[a, b])
+    Aref = sp.csr_matrix((vals, (rows, cols)), shape=(n, n))
+    A = sp.csr_matrix((val, col, ptr), shape=(n, n))
+    assert abs(A - Aref).max() <= 1e-12 * abs(Aref).max()
+
+
+def test_closed_form_mass_matches_quadrature():
+    v, t = kuhn(6)
+    o = Oracle(64)
+    o.pattern(len(v), t)
+    a = o.assemble(v)
+    b = o.assemble(v, closed_form=True)
+    assert np.abs(a - b).max() <= 1e-12 * np.abs(a).max()
+    g = golden("simple2d")
+    o = Oracle(64)
+    o.pattern(len(g["verts"]), g["tris"])
+    a = o.assemble(g["verts"])
+    b = o.assemble(g["verts"], closed_form=True)
+    assert np.abs(a - b).max() <= 1e-12 * np.abs(a).max()
+
+
+def test_material_coefficients():
+    v, t = kuhn(4)
+    lab = np.full(len(t), 3, dtype=np.int32)
+    o = Oracle(64)
+    ptr, col = o.pattern(len(v), t)
+    a1 = o.assemble(v, np.zeros(len(t), dtype=np.int32), closed_form=True)
+    a3 = o.assemble(v, lab, closed_form=True)
+    # A = c K + M: with c = 3 the stiffness part triples; M from the row sums (K has zero row sums)
+    A1 = sp.csr_matrix((a1, col, ptr)); A3 = sp.csr_matrix((a3, col, ptr))
+    assert np.allclose(np.asarray(A1.sum(1)).ravel(), np.asarray(A3.sum(1)).ravel(), atol=1e-14)
+    D = (A3 - A1) - 2 * (A1 - sp.diags(np.asarray(A1.sum(1)).ravel()) * 0)  # (3K+M)-(K+M) = 2K
+    K2 = (A3 - A1)
+    assert abs(np.asarray(K2.sum(1))).max() < 1e-12
+
+
+def test_mis_is_maximal_and_independent():
+    v, t = kuhn(10)
+    o = Oracle(64)
+    ptr, col = o.pattern(len(v), t)
+    n = len(v)
+    A = sp.csr_matrix((np.ones(col.size), col, ptr), shape=(n, n))
+    A.setdiag(0); A.eliminate_zeros()
+    for k in (1, 2):
+        mis = randomized_mis(A.indptr, A.indices, k, 0)
+        assert set(np.unique(mis)) <= {0, 1}
+        R = A.copy()
+        for _ in range(k - 1):
+            R = R @ A + A
+        R.setdiag(0); R.eliminate_zeros()
+        R.data[:] = 1
+        roots = mis == 1
+        assert (R[roots][:, roots]).nnz == 0, "two roots within distance k"
+        covered = (R[:, roots].sum(1).A1 > 0) | roots
+        assert covered.all(), "a node is farther than k from every root"
+        assert np.array_equal(mis, randomized_mis(A.indptr, A.indices, k, 0))          # deterministic given the seed
+    # glibc maps srand(0) to srand(1); compare two genuinely different seeds
+    assert not np.array_equal(randomized_mis(A.indptr, A.indices, 2, 1), randomized_mis(A.indptr, A.indices, 2, 2))
+
+
+def test_aggregation_invariants():
+    v, t = kuhn(14)
+    o, ptr, col, val = make_oracle(v, t, seed=0)
+    nl = o.setup()
+    assert nl >= 2
+    n = len(v)
+    perm, iperm = o.level_int(0, "permutation"), o.level_int(0, "ipermutation")
+    assert np.array_equal(np.sort(perm), np.arange(n)) and np.array_equal(perm[iperm], np.arange(n))
+    aidx, pidx, plab = o.level_int(0, "aggregateIdx"), o.level_int(0, "partitionIdx"), o.level_int(0, "partitionLabel")
+    assert aidx[0] == 0 and aidx[-1] == n and np.all(np.diff(aidx) >= 9)
+    assert pidx[0] == 0 and pidx[-1] == len(aidx) - 1
+    assert np.all(np.diff(plab) >= 0) and np.all(np.diff(aidx[pidx]) <= 512)
+    # permuted operator is P A P^T
+    A = sp.csr_matrix((val, col, ptr), shape=(n, n))
+    Ap = sp.csr_matrix((o.level_val(0, "A_val"), o.level_int(0, "A_col"), o.level_int(0, "A_ptr")), shape=(n, n))
+    assert abs(Ap - A[iperm][:, iperm]).max() == 0
+    # Galerkin product
+    m = o.level_rows(1)
+    P = sp.csr_matrix((o.level_val(0, "P_val"), o.level_int(0, "P_col"), o.level_int(0, "P_ptr")), shape=(n, m))
+    R = sp.csr_matrix((o.level_val(0, "R_val"), o.level_int(0, "R_col"), o.level_int(0, "R_ptr")), shape=(m, n))
+    assert abs(R - P.T).max() == 0
+    Ac = sp.csr_matrix((o.level_val(1, "A_val"), o.level_int(1, "A_col"), o.level_int(1, "A_ptr")), shape=(m, m))
+    if nl > 2:
+        p1 = o.level_int(1, "ipermutation")
+        Ac_ext = (P.T @ A[iperm][:, iperm] @ P).tocsr()
+        assert abs(Ac - Ac_ext[p1][:, p1]).max() <= 1e-12 * abs(Ac).max()
+    else:
+        assert abs(Ac - P.T @ Ap @ P).max() <= 1e-12 * abs(Ac).max()
+    # prolongator definition: P = (I - w D^-1 A) T
+    agg = np.repeat(np.arange(len(aidx) - 1), np.diff(aidx))
+    T = sp.csr_matrix((np.ones(n), (np.arange(n), agg)), shape=(n, m))
+    Pdef = T - 0.67 * sp.diags(1.0 / Ap.diagonal()) @ Ap @ T
+    assert abs(P - Pdef).max() <= 1e-13
+
+
+@pytest.mark.parametrize("N", [10, 18])
+def test_pcg_against_scipy(N):
+    v, t = kuhn(N)
+    o, ptr, col, val = make_oracle(v, t, solverType=1, tolerance=1e-10, maxIters=200, seed=0)
+    o.setup()
+    A = sp.csr_matrix((val, col, ptr))
+    xstar = egg_carton(v)
+    b = A @ xstar
+    x, it = o.solve(b)
+    assert o.final_relres() <= 1e-10 and 0 < it < 60
+    assert rel(x, spl.spsolve(A.tocsc(), b)) <= 1e-8
+    h = o.resid_history()
+    assert len(h) == it + 1 and h[-1] <= 1e-10
+
+
+def test_reference_precision_and_level0_quirk_modes():
+    """precision=32 restates the reference's mixed precision; refLevel0NoPerm restates F3:
+    without the level-0 permutation the reference solves (P A P^T) x = b with b in user order."""
+    v, t = kuhn(10)
+    o64, ptr, col, val = make_oracle(v, t, solverType=1, tolerance=1e-8, maxIters=200, seed=0)
+    o64.setup()
+    A = sp.csr_matrix((val, col, ptr))
+    b = A @ egg_carton(v)
+    x64, it64 = o64.solve(b)
+    o32, *_ = make_oracle(v, t, precision=32, solverType=1, tolerance=1e-6, maxIters=200, seed=0)
+    o32.setup()
+    x32, it32 = o32.solve(b)
+    assert rel(x32, x64) < 1e-4
+    oq, *_ = make_oracle(v, t, solverType=1, tolerance=1e-8, maxIters=200, seed=0, refLevel0NoPerm=1)
+    oq.setup()
+    xq, _ = oq.solve(b)
+    ip = oq.level_int(0, "ipermutation")
+    Aperm = A[ip][:, ip]
+    assert np.linalg.norm(b - Aperm @ xq) / np.linalg.norm(b) <= 2e-8   # the system the reference actually solves
+    assert rel(xq, x64) > 1e-3                                          # ... which is not A x = b
+
+
+def test_topsize_single_level():
+    v, t = kuhn(4)
+    o, ptr, col, val = make_oracle(v, t, solverType=1, tolerance=1e-8, seed=0)
+    assert o.setup() == 1
+    A = sp.csr_matrix((val, col, ptr))
+    b = A @ (egg_carton(v) + 1)
+    x, it = o.solve(b)
+    assert it == 0 and rel(x, egg_carton(v) + 1) < 1e-10
