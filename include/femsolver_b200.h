@@ -47,7 +47,7 @@ const char* fsb_last_error(const fsb_solver* s); /* s may be NULL: error of the 
  * (maxLevels, maxIters, preInnerIters, postInnerIters, postRelaxes, cycleIters, dsType, topSize,
  *  randMisParameters, partitionMaxSize, aggregatorType, convergeType, tolerance, cycleType,
  *  solverType, smootherWeight, proOmega, device, blockSize, verbose) plus the additive ones
- * (seed, refLevel0NoPerm, useGraphs, checkEvery). */
+ * (seed, refLevel0NoPerm, useGraphs, checkEvery, profile). */
 int fsb_set_param(fsb_solver* s, const char* name, double value);
 int fsb_get_param(const fsb_solver* s, const char* name, double* value);
 
@@ -94,6 +94,10 @@ int fsb_precondition_device(fsb_solver* s, const double* r_dev, double* z_dev);
  * "pattern", "assemble", "setup", "solve" */
 double fsb_time_ms(const fsb_solver* s, const char* stage);
 long long fsb_last_launches(const fsb_solver* s); /* kernels launched by the last fsb_solve* */
+/* with parameter profile=1 the next solve times every kernel with CUDA events (graphs off); the
+ * report is text, one line per (kernel, level): "name level launches total_ms".
+ * buf == NULL returns the size needed. */
+int fsb_profile_report(fsb_solver* s, char* buf, int cap);
 void* fsb_stream(const fsb_solver* s);            /* cudaStream_t the kernels run on */
 
 /* host-side tables the element kernels consume (no device needed) */

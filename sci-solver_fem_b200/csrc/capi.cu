@@ -39,7 +39,7 @@ const ParamRef kParams[] = {
   PI_(verbose), PI_(maxLevels), PI_(maxIters), PI_(preInnerIters), PI_(postInnerIters), PI_(postRelaxes), PI_(cycleIters),
   PI_(dsType), PI_(topSize), PI_(randMisParameters), PI_(partitionMaxSize), PI_(aggregatorType), PI_(convergeType),
   PI_(cycleType), PI_(solverType), PI_(device), PI_(blockSize), PD_(tolerance), PD_(smootherWeight), PD_(proOmega),
-  {"seed", 2, offsetof(fsb::Params, seed)}, PI_(refLevel0NoPerm), PI_(useGraphs), PI_(checkEvery)};
+  {"seed", 2, offsetof(fsb::Params, seed)}, PI_(refLevel0NoPerm), PI_(useGraphs), PI_(checkEvery), PI_(profile)};
 
 const ParamRef* find_param(const char* name) {
   for (const ParamRef& p : kParams) if (strcmp(p.name, name) == 0) return &p;
@@ -231,6 +231,15 @@ double fsb_time_ms(const fsb_solver* s, const char* stage) {
   return it == s->impl->times_ms.end() ? -1.0 : it->second;
 }
 long long fsb_last_launches(const fsb_solver* s) { return (s && s->impl) ? s->impl->launches : 0; }
+int fsb_profile_report(fsb_solver* s, char* buf, int cap) {
+  if (!s || !s->impl) return -1;
+  std::string r;
+  try { r = s->impl->profile_report(); } catch (const std::exception& e) { s->impl->last_error = e.what(); return -1; }
+  if (!buf) return (int)r.size() + 1;
+  if (cap < (int)r.size() + 1) return -1;
+  memcpy(buf, r.c_str(), r.size() + 1);
+  return (int)r.size() + 1;
+}
 void* fsb_stream(const fsb_solver* s) { return (s && s->impl) ? (void*)s->impl->ctx.stream : nullptr; }
 
 void fsb_tet_mass_integrals(double out10[10]) { fsb::tet_mass_integrals_host(out10); }

@@ -29,11 +29,40 @@ struct CudaError : public std::runtime_error {
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Optional per-launch timing (CUDA events around every solve-phase kernel; used by bench.py's
+// roofline pass, never inside a timed region).
+struct Profiler {
+  struct Rec { const char* name; int level; cudaEvent_t a, b; };
+  bool on = false;
+  int cur_level = 0;
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+  void clear() { for (auto& r : recs) { pool.push_back(r.a); pool.push_back(r.b); } recs.clear(); }
+  ~Profiler() { clear(); for (auto e : pool) cudaEventDestroy(e); }
+};
+
 // The stream every kernel of a solver instance is launched on.
 struct Ctx {
   cudaStream_t stream = nullptr;
   int device = 0;
   int num_sms = 148;
+  Profiler* prof = nullptr;
+};
+
+struct ProfScope {
+  Profiler* p; size_t idx; cudaStream_t s;
+  ProfScope(const Ctx& c, const char* name) : p(c.prof && c.prof->on ? c.prof : nullptr), idx(0), s(c.stream) {
+    if (!p) return;
+    Profiler::Rec r{name, p->cur_level, p->get(), p->get()};
+    cudaEventRecord(r.a, s);
+    idx = p->recs.size();
+    p->recs.push_back(r);
+  }
+  ~ProfScope() { if (p) cudaEventRecord(p->recs[idx].b, s); }
 };
 
 // Stream-ordered device buffer (cudaMallocAsync pool: setup makes hundreds of temporaries).

@@ -14,6 +14,8 @@
 // shuffles, then a last-CTA pass over per-CTA partials), so a solve is bit-reproducible.
 // Every kernel exits immediately once the device-side `done` flag is set, which lets the host
 // enqueue iterations ahead of the convergence poll.
+#include <cooperative_groups.h>
+
 #include "kernels.h"
 
 namespace fsb {
@@ -60,31 +62,73 @@ __device__ __forceinline__ double final_sum(const double* partials, int n, doubl
   return block_sum(v, s_warp);
 }
 
-// ------------------------------------------------------------------ SpMV family
-// G lanes cooperate on one row: coalesced (col,val) loads, shuffle reduction.
-template <int G, int MODE, bool DOT>
-__global__ void __launch_bounds__(256) spmv_kernel(int n, const int* __restrict__ ptr, const int* __restrict__ col,
-                                                   const double* __restrict__ val, const double* __restrict__ x,
-                                                   double* __restrict__ y, const double* __restrict__ b,
-                                                   double* __restrict__ partials, PcgScalars* __restrict__ sc, const int* __restrict__ done) {
+// ------------------------------------------------------------------ SpMV family (CSR-stream)
+// A CTA owns SPMV_ROWS consecutive rows.  Their entries are contiguous in CSR, so the CTA streams
+// them with fully coalesced, deeply unrolled loads (every thread keeps several independent
+// val/col/x chains in flight), parks the products in shared memory and then thread t adds up the
+// products of row t in column order: fixed summation order, no atomics, long rows handled by tiling.
+constexpr int SPMV_ROWS = 256;
+constexpr int SPMV_CAP = 4096;  // products per tile (32 KB)
+
+template <int MODE, bool DOT>  // MODE 0: y = A x   1: y = b - A x   2: y += A x   3: y -= A x
+__global__ void __launch_bounds__(SPMV_ROWS) csr_stream_kernel(int n, const int* __restrict__ ptr, const int* __restrict__ col,
+                                                               const double* __restrict__ val, const double* __restrict__ x,
+                                                               double* __restrict__ y, const double* __restrict__ b,
+                                                               double* __restrict__ partials, PcgScalars* __restrict__ sc,
+                                                               const int* __restrict__ done) {
+  __shared__ double prod[SPMV_CAP];
+  __shared__ int sptr[SPMV_ROWS + 1];
   __shared__ double s_warp[32];
   __shared__ int s_flag;
   if (done && *done) return;
-  const int lane = threadIdx.x % G;
-  const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / G;
-  double s = 0.0;
-  if (row < n) {
-    int e1 = ptr[row + 1];
-    for (int e = ptr[row] + lane; e < e1; e += G) s += val[e] * __ldg(x + col[e]);
-  }
+  const int t = threadIdx.x;
+  const int r0 = blockIdx.x * SPMV_ROWS;
+  const int nr = min(SPMV_ROWS, n - r0);
+  // every thread learns the CTA's entry range directly (two broadcast loads): the streaming loads
+  // below do not wait for a barrier
+  const int e0 = __ldg(ptr + r0), e1 = __ldg(ptr + r0 + nr);
+  if (t <= nr) sptr[t] = ptr[r0 + t];
+  if (t == 0) sptr[nr] = e1;
+  double acc = 0.0;
+  bool first = true;
+  for (int ts = e0; ts < e1; ts += SPMV_CAP) {
+    const int te = min(ts + SPMV_CAP, e1);
+    int e = ts + t;
+    for (; e + 7 * SPMV_ROWS < te; e += 8 * SPMV_ROWS) {  // 8 independent (col, val) -> x chains per thread
+      int c[8]; double v[8], xv[8];
 #pragma unroll
-  for (int o = G >> 1; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, G);
+      for (int u = 0; u < 8; u++) { c[u] = __ldg(col + e + u * SPMV_ROWS); v[u] = __ldg(val + e + u * SPMV_ROWS); }
+#pragma unroll
+      for (int u = 0; u < 8; u++) xv[u] = __ldg(x + c[u]);
+#pragma unroll
+      for (int u = 0; u < 8; u++) prod[e + u * SPMV_ROWS - ts] = v[u] * xv[u];
+    }
+    for (; e + 3 * SPMV_ROWS < te; e += 4 * SPMV_ROWS) {
+      int c[4]; double v[4], xv[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) { c[u] = __ldg(col + e + u * SPMV_ROWS); v[u] = __ldg(val + e + u * SPMV_ROWS); }
+#pragma unroll
+      for (int u = 0; u < 4; u++) xv[u] = __ldg(x + c[u]);
+#pragma unroll
+      for (int u = 0; u < 4; u++) prod[e + u * SPMV_ROWS - ts] = v[u] * xv[u];
+    }
+    for (; e < te; e += SPMV_ROWS) prod[e - ts] = __ldg(val + e) * __ldg(x + __ldg(col + e));
+    __syncthreads();
+    const int ra = (t < nr) ? sptr[t] : 0, rb = (t < nr) ? sptr[t + 1] : 0;
+    const int a = max(ra, ts), bnd = min(rb, te);
+    for (int q = a; q < bnd; q++) acc += prod[q - ts];
+    if (te < e1) __syncthreads();
+    first = false;
+  }
+  if (first) __syncthreads();
   double contrib = 0.0;
-  if (row < n && lane == 0) {
-    if (MODE == 0) y[row] = s;
-    else if (MODE == 1) y[row] = b[row] - s;
-    else y[row] = y[row] + s;
-    if (DOT) contrib = x[row] * s;
+  if (t < nr) {
+    const int row = r0 + t;
+    if (MODE == 0) y[row] = acc;
+    else if (MODE == 1) y[row] = b[row] - acc;
+    else if (MODE == 2) y[row] = y[row] + acc;
+    else y[row] = y[row] - acc;
+    if (DOT) contrib = x[row] * acc;
   }
   if (DOT) {
     double bs = block_sum(contrib, s_warp);
@@ -95,105 +139,270 @@ __global__ void __launch_bounds__(256) spmv_kernel(int n, const int* __restrict_
   }
 }
 
+template <int MODE>
+__global__ void spmv_vector_kernel(int n, const int* __restrict__ ptr, const int* __restrict__ col, const double* __restrict__ val,
+                                   const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ b,
+                                   const int* __restrict__ done);
+
 template <int MODE, bool DOT>
-void spmv_dispatch(const Ctx& c, const DCsr& A, const double* x, double* y, const double* b, double* partials, PcgScalars* sc, const int* done) {
+void spmv_dispatch(const Ctx& c, const DCsr& A, const double* x, double* y, const double* b, double* partials, PcgScalars* sc,
+                   const int* done, const char* name) {
   int n = A.nrows;
   if (n == 0) return;
-  double avg = (double)A.nnz / n;
-  int G = avg > 24 ? 32 : avg > 12 ? 16 : avg > 6 ? 8 : 4;
-  int blocks = cdiv((long long)n * G, 256);
   g_launch_counter++;
-  switch (G) {
-    case 32: spmv_kernel<32, MODE, DOT><<<blocks, 256, 0, c.stream>>>(n, A.ptr, A.col, A.val, x, y, b, partials, sc, done); break;
-    case 16: spmv_kernel<16, MODE, DOT><<<blocks, 256, 0, c.stream>>>(n, A.ptr, A.col, A.val, x, y, b, partials, sc, done); break;
-    case 8: spmv_kernel<8, MODE, DOT><<<blocks, 256, 0, c.stream>>>(n, A.ptr, A.col, A.val, x, y, b, partials, sc, done); break;
-    default: spmv_kernel<4, MODE, DOT><<<blocks, 256, 0, c.stream>>>(n, A.ptr, A.col, A.val, x, y, b, partials, sc, done); break;
-  }
+  ProfScope ps(c, name);
+  if (!DOT && (double)A.nnz > 32.0 * n)  // long rows: one warp per row
+    spmv_vector_kernel<MODE><<<cdiv((long long)n * 32, 256), 256, 0, c.stream>>>(n, A.ptr, A.col, A.val, x, y, b, done);
+  else
+    csr_stream_kernel<MODE, DOT><<<cdiv(n, SPMV_ROWS), SPMV_ROWS, 0, c.stream>>>(n, A.ptr, A.col, A.val, x, y, b, partials, sc, done);
   FSB_CHECK_LAUNCH();
 }
 
 // ------------------------------------------------------------------ fused smoother
-// One CTA per partition, thread t <-> row pstart+t, x double-buffered in shared memory.
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) pre_smooth_kernel(const int* __restrict__ pstart, const int* __restrict__ ptr,
-                                                           const int* __restrict__ col, const double* __restrict__ val,
-                                                           const double* __restrict__ diag, const double* __restrict__ b_src,
-                                                           const int* __restrict__ gather, double* __restrict__ b_int, double w,
-                                                           int nsweeps, double* __restrict__ x, const int* __restrict__ done) {
+// (a) register-resident sliced-ELL kernel (fine levels).  One CTA per partition, thread t owns row
+// t.  The intra-partition off-diagonal entries of the partition are stored column-major
+// (entry k of row t at ell[base + k*np + t], 16-bit local column), so the loads are perfectly
+// coalesced and go straight into registers; the nu sweeps + the residual pass then touch HBM no
+// more: x lives double-buffered in shared memory.  Threads beyond the partition's rows exit.
+template <int MAXK, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, (BLOCK <= 512 && MAXK <= 16) ? 2 : 1)
+smooth_ell_kernel(const int* __restrict__ pstart, const long long* __restrict__ ellptr, const int* __restrict__ ellK,
+                  const double* __restrict__ ellval, const unsigned short* __restrict__ ellcol, const double* __restrict__ diag,
+                  const double* __restrict__ b_src, const int* __restrict__ gather, double* __restrict__ b_int,
+                  const double* __restrict__ x_in, double w, int nsweeps, double* __restrict__ x_out,
+                  const int* __restrict__ scatter, double* __restrict__ x_ext, double* __restrict__ r_out,
+                  const int* __restrict__ done) {
   __shared__ double sx[2][BLOCK];
   if (done && *done) return;
   const int r0 = pstart[blockIdx.x], np = pstart[blockIdx.x + 1] - r0, t = threadIdx.x, row = r0 + t;
-  const bool active = t < np;
-  double b = 0.0, d = 1.0;
-  int e0 = 0, e1 = 0;
-  if (active) {
-    b = b_src[gather ? gather[row] : row];
-    d = diag[row];
-    if (b_int) b_int[row] = b;
-    e0 = ptr[row]; e1 = ptr[row + 1];
-    sx[0][t] = w * b / d;
+  if (t >= np) return;  // exited threads do not take part in the barriers below
+  const int K = ellK[blockIdx.x];
+  const double* ev = ellval + ellptr[blockIdx.x] + t;
+  const unsigned short* ec = ellcol + ellptr[blockIdx.x] + t;
+  double v[MAXK];
+  unsigned cpk[MAXK / 2];  // two 16-bit local columns per register
+#pragma unroll
+  for (int k = 0; k < MAXK; k += 2) {
+    unsigned c0 = t, c1 = t;
+    v[k] = 0.0; v[k + 1] = 0.0;
+    if (k < K) { v[k] = ev[(size_t)k * np]; c0 = ec[(size_t)k * np]; }
+    if (k + 1 < K) { v[k + 1] = ev[(size_t)(k + 1) * np]; c1 = ec[(size_t)(k + 1) * np]; }
+    cpk[k >> 1] = (c0 << 3) | (c1 << 19);  // byte offsets into the x tile
   }
-  __syncthreads();
+  const double b = b_src[gather ? gather[row] : row];
+  const double d = diag[row];
+  const double wd = w / d;  // one division per stage instead of one per sweep (rounding-level deviation)
+  if (b_int) b_int[row] = b;
+  sx[0][t] = x_in ? x_in[row] : w * b / d;
+  // barrier over the np participating threads only
+  const int nbar = (np + 31) & ~31;
+  asm volatile("bar.sync 1, %0;" ::"r"(nbar));
   int cur = 0;
   for (int it = 0; it < nsweeps; it++) {
-    if (active) {
-      double s = 0.0;
-      for (int e = e0; e < e1; e++) {
-        int cc = col[e] - r0;
-        if ((unsigned)cc < (unsigned)np && cc != t) s += val[e] * sx[cur][cc];
-      }
-      double xv = sx[cur][t];
-      sx[cur ^ 1][t] = xv + w * (b - s - d * xv) / d;
+    const char* xs = reinterpret_cast<const char*>(sx[cur]);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;  // four independent FMA chains (fixed order)
+#pragma unroll
+    for (int k = 0; k < MAXK; k += 4) {
+      s0 += v[k] * *reinterpret_cast<const double*>(xs + (cpk[k >> 1] & 0xffffu));
+      s1 += v[k + 1] * *reinterpret_cast<const double*>(xs + (cpk[k >> 1] >> 16));
+      s2 += v[k + 2] * *reinterpret_cast<const double*>(xs + (cpk[(k >> 1) + 1] & 0xffffu));
+      s3 += v[k + 3] * *reinterpret_cast<const double*>(xs + (cpk[(k >> 1) + 1] >> 16));
     }
-    __syncthreads();
+    const double s = (s0 + s1) + (s2 + s3);
+    const double xv = sx[cur][t];
+    sx[cur ^ 1][t] = xv + wd * (b - s - d * xv);
+    asm volatile("bar.sync 1, %0;" ::"r"(nbar));
     cur ^= 1;
   }
-  if (active) x[row] = sx[cur][t];
+  const double xv = sx[cur][t];
+  if (x_out) x_out[row] = xv;
+  if (scatter) x_ext[scatter[row]] = xv;
+  if (r_out) {  // in-partition residual b - A_in x - d x (gauss_seidel.cu:1352-1375)
+    const char* xs = reinterpret_cast<const char*>(sx[cur]);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+    for (int k = 0; k < MAXK; k += 4) {
+      s0 += v[k] * *reinterpret_cast<const double*>(xs + (cpk[k >> 1] & 0xffffu));
+      s1 += v[k + 1] * *reinterpret_cast<const double*>(xs + (cpk[k >> 1] >> 16));
+      s2 += v[k + 2] * *reinterpret_cast<const double*>(xs + (cpk[(k >> 1) + 1] & 0xffffu));
+      s3 += v[k + 3] * *reinterpret_cast<const double*>(xs + (cpk[(k >> 1) + 1] >> 16));
+    }
+    r_out[row] = b - ((s0 + s1) + (s2 + s3)) - d * xv;
+  }
 }
 
+// (b) cooperative CSR kernel (coarse levels: long rows, few partitions).  G lanes share a row,
+// rows of the partition are processed BLOCK/G at a time, matrix entries stream from L1/L2.
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) post_smooth_kernel(const int* __restrict__ pstart, const int* __restrict__ ptr,
+__global__ void __launch_bounds__(BLOCK) smooth_coop_kernel(int G, const int* __restrict__ pstart, const int* __restrict__ ptr,
                                                             const int* __restrict__ col, const double* __restrict__ val,
-                                                            const double* __restrict__ diag, const double* __restrict__ b_int,
+                                                            const double* __restrict__ diag, const double* __restrict__ b_src,
+                                                            const int* __restrict__ gather, double* __restrict__ b_int,
                                                             const double* __restrict__ x_in, double w, int nsweeps,
                                                             double* __restrict__ x_out, const int* __restrict__ scatter,
-                                                            double* __restrict__ x_ext, const int* __restrict__ done) {
-  __shared__ double sx[2][BLOCK];
+                                                            double* __restrict__ x_ext, double* __restrict__ r_out,
+                                                            const int* __restrict__ done) {
+  __shared__ double sx[2][1024], sb[1024], sd[1024], swd[1024];
   if (done && *done) return;
-  const int r0 = pstart[blockIdx.x], np = pstart[blockIdx.x + 1] - r0, t = threadIdx.x, row = r0 + t;
-  const bool active = t < np;
-  double b = 0.0, d = 1.0;
-  int e0 = 0, e1 = 0;
-  if (active) {
-    b = b_int[row];
-    d = diag[row];
-    e0 = ptr[row]; e1 = ptr[row + 1];
-    // b' = b - A_out x : neighbours' x frozen at the value they had when the pass started
-    for (int e = e0; e < e1; e++) {
-      int cg = col[e];
-      if ((unsigned)(cg - r0) >= (unsigned)np) b -= val[e] * __ldg(x_in + cg);
-    }
-    sx[0][t] = x_in[row];
+  const int r0 = pstart[blockIdx.x], np = pstart[blockIdx.x + 1] - r0, tid = threadIdx.x;
+  for (int t = tid; t < np; t += BLOCK) {
+    const int row = r0 + t;
+    const double b = b_src[gather ? gather[row] : row], d = diag[row];
+    sb[t] = b; sd[t] = d; swd[t] = w / d;
+    if (b_int) b_int[row] = b;
+    sx[0][t] = x_in ? x_in[row] : w * b / d;
   }
   __syncthreads();
+  const int lane = tid & (G - 1), grp = tid / G, RP = BLOCK / G;
+  const int npasses = nsweeps + (r_out ? 1 : 0);
   int cur = 0;
-  for (int it = 0; it < nsweeps; it++) {
-    if (active) {
+  for (int it = 0; it < npasses; it++) {
+    const bool sweep = it < nsweeps;
+    for (int rb = 0; rb < np; rb += RP) {
+      const int t = rb + grp;
       double s = 0.0;
-      for (int e = e0; e < e1; e++) {
-        int cc = col[e] - r0;
-        if ((unsigned)cc < (unsigned)np && cc != t) s += val[e] * sx[cur][cc];
+      if (t < np) {
+        const int row = r0 + t, e1 = ptr[row + 1];
+        for (int e = ptr[row] + lane; e < e1; e += G) {
+          const int cc = col[e] - r0;
+          if ((unsigned)cc < (unsigned)np && cc != t) s += val[e] * sx[cur][cc];
+        }
       }
-      double xv = sx[cur][t];
-      sx[cur ^ 1][t] = xv + w * (b - s - d * xv) / d;
+      for (int o = G >> 1; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, G);
+      if (t < np && lane == 0) {
+        const double xv = sx[cur][t];
+        if (sweep) sx[cur ^ 1][t] = xv + swd[t] * (sb[t] - s - sd[t] * xv);
+        else r_out[r0 + t] = sb[t] - s - sd[t] * xv;
+      }
     }
     __syncthreads();
-    cur ^= 1;
+    if (sweep) cur ^= 1;
   }
-  if (active) {
-    double xv = sx[cur][t];
-    if (x_out) x_out[row] = xv;
-    if (scatter) x_ext[scatter[row]] = xv;
+  for (int t = tid; t < np; t += BLOCK) {
+    const double xv = sx[cur][t];
+    if (x_out) x_out[r0 + t] = xv;
+    if (scatter) x_ext[scatter[r0 + t]] = xv;
+  }
+}
+
+// (c) cluster kernel (coarse levels: long rows, few partitions).  A partition is owned by a
+// thread-block CLUSTER of C CTAs: every CTA stages the CSR slice of its np/C rows in shared memory
+// once (16-bit local columns; diagonal and inter-partition entries neutralised to 0 * x[t]) and
+// keeps a full copy of the partition's x.  After each sweep the CTAs push their new x values into
+// all C copies through distributed shared memory and meet at a cluster barrier, so the whole
+// smoothing stage runs out of shared memory on C SMs per partition instead of one.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) smooth_cluster_kernel(int C, int G, int cap, int npmax, int chunkmax,
+                                                               const int* __restrict__ pstart, const int* __restrict__ ptr,
+                                                               const int* __restrict__ col, const double* __restrict__ val,
+                                                               const double* __restrict__ diag, const double* __restrict__ b_src,
+                                                               const int* __restrict__ gather, double* __restrict__ b_int,
+                                                               const double* __restrict__ x_in, double w, int nsweeps,
+                                                               double* __restrict__ x_out, const int* __restrict__ scatter,
+                                                               double* __restrict__ x_ext, double* __restrict__ r_out,
+                                                               const int* __restrict__ done) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sval = reinterpret_cast<double*>(smem_raw);
+  double* sx0 = sval + cap;
+  double* sx1 = sx0 + npmax;
+  double* sb = sx1 + npmax;
+  double* sd = sb + chunkmax;
+  double* swd = sd + chunkmax;
+  int* srp = reinterpret_cast<int*>(swd + chunkmax);
+  unsigned short* scol = reinterpret_cast<unsigned short*>(srp + chunkmax + 1);
+  if (done && *done) return;  // uniform over the whole grid
+  const int crank = (int)cluster.block_rank();
+  const int p = blockIdx.x / C;
+  const int r0 = pstart[p], np = pstart[p + 1] - r0, tid = threadIdx.x;
+  const int chunk = (np + C - 1) / C;
+  const int m0 = min(crank * chunk, np);
+  const int mn = min(chunk, np - m0);  // this CTA owns local rows [m0, m0 + mn)
+  // full initial x (every CTA computes its own copy), own rows' b / d / slice
+  for (int t = tid; t < np; t += BLOCK) {
+    const int row = r0 + t;
+    double x0;
+    if (x_in) x0 = x_in[row];
+    else x0 = w * b_src[gather ? gather[row] : row] / diag[row];
+    sx0[t] = x0;
+  }
+  const int e0 = ptr[r0 + m0];
+  for (int t = tid; t < mn; t += BLOCK) {
+    const int row = r0 + m0 + t;
+    const double b = b_src[gather ? gather[row] : row], d = diag[row];
+    sb[t] = b; sd[t] = d; swd[t] = w / d;
+    if (b_int) b_int[row] = b;
+  }
+  for (int t = tid; t <= mn; t += BLOCK) srp[t] = ptr[r0 + m0 + t] - e0;
+  __syncthreads();
+  const int lane = tid & (G - 1), grp = tid / G, RP = BLOCK / G;
+  for (int t = grp; t < mn; t += RP) {  // stage: lanes of a group read consecutive entries
+    const int qb = srp[t + 1], tl = m0 + t;
+    for (int q = srp[t] + lane; q < qb; q += G) {
+      const int cc = col[e0 + q] - r0;
+      const bool in = (unsigned)cc < (unsigned)np && cc != tl;
+      sval[q] = in ? val[e0 + q] : 0.0;
+      scol[q] = (unsigned short)(in ? cc : tl);
+    }
+  }
+  cluster.sync();  // all CTAs of the cluster are resident and initialised before remote writes start
+  double* xc = sx0;
+  double* xn = sx1;
+  for (int it = 0; it < nsweeps; it++) {
+    for (int rb = 0; rb < mn; rb += RP) {
+      const int t = rb + grp;
+      double s = 0.0;
+      if (t < mn) {
+        const int qb = srp[t + 1];
+        for (int q = srp[t] + lane; q < qb; q += G) s += sval[q] * xc[scol[q]];
+      }
+      for (int o = G >> 1; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, G);
+      if (t < mn && lane == 0) {
+        const double xv = xc[m0 + t];
+        const double xnew = xv + swd[t] * (sb[t] - s - sd[t] * xv);
+        for (int c = 0; c < C; c++) cluster.map_shared_rank(xn, c)[m0 + t] = xnew;  // DSMEM broadcast
+      }
+    }
+    cluster.sync();
+    double* tmp = xc; xc = xn; xn = tmp;
+  }
+  if (r_out) {
+    for (int rb = 0; rb < mn; rb += RP) {
+      const int t = rb + grp;
+      double s = 0.0;
+      if (t < mn) {
+        const int qb = srp[t + 1];
+        for (int q = srp[t] + lane; q < qb; q += G) s += sval[q] * xc[scol[q]];
+      }
+      for (int o = G >> 1; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, G);
+      if (t < mn && lane == 0) r_out[r0 + m0 + t] = sb[t] - s - sd[t] * xc[m0 + t];
+    }
+  }
+  for (int t = tid; t < mn; t += BLOCK) {
+    const double xv = xc[m0 + t];
+    if (x_out) x_out[r0 + m0 + t] = xv;
+    if (scatter) x_ext[scatter[r0 + m0 + t]] = xv;
+  }
+}
+
+// warp-per-row SpMV for long rows (restriction operators, coarse operators)
+template <int MODE>
+__global__ void __launch_bounds__(256) spmv_vector_kernel(int n, const int* __restrict__ ptr, const int* __restrict__ col,
+                                                          const double* __restrict__ val, const double* __restrict__ x,
+                                                          double* __restrict__ y, const double* __restrict__ b, const int* __restrict__ done) {
+  if (done && *done) return;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= n) return;
+  double s = 0.0;
+  const int e1 = ptr[row + 1];
+  for (int e = ptr[row] + lane; e < e1; e += 32) s += val[e] * __ldg(x + col[e]);
+  s = warp_sum(s);
+  if (lane == 0) {
+    if (MODE == 0) y[row] = s;
+    else if (MODE == 1) y[row] = b[row] - s;
+    else if (MODE == 2) y[row] = y[row] + s;
+    else y[row] = y[row] - s;
   }
 }
 
@@ -284,42 +493,52 @@ inline int vec_blocks(const Ctx& c, int n) { return std::max(1, std::min(cdiv(n,
 
 }  // namespace
 
-void launch_spmv(const Ctx& c, const DCsr& A, const double* x, double* y, int mode, const double* b, const int* done) {
-  if (mode == 0) spmv_dispatch<0, false>(c, A, x, y, b, nullptr, nullptr, done);
-  else if (mode == 1) spmv_dispatch<1, false>(c, A, x, y, b, nullptr, nullptr, done);
-  else spmv_dispatch<2, false>(c, A, x, y, b, nullptr, nullptr, done);
+void launch_spmv(const Ctx& c, const DCsr& A, const double* x, double* y, int mode, const double* b, const int* done, const char* name) {
+  if (mode == 0) spmv_dispatch<0, false>(c, A, x, y, b, nullptr, nullptr, done, name);
+  else if (mode == 1) spmv_dispatch<1, false>(c, A, x, y, b, nullptr, nullptr, done, name);
+  else if (mode == 2) spmv_dispatch<2, false>(c, A, x, y, b, nullptr, nullptr, done, name);
+  else spmv_dispatch<3, false>(c, A, x, y, b, nullptr, nullptr, done, name);
 }
 
 void launch_spmv_dot(const Ctx& c, const DCsr& A, const double* x, double* y, double* partials, PcgScalars* sc) {
-  spmv_dispatch<0, true>(c, A, x, y, nullptr, partials, sc, &sc->done);
+  spmv_dispatch<0, true>(c, A, x, y, nullptr, partials, sc, &sc->done, "spmv_dot");
 }
 
-void launch_pre_smooth(const Ctx& c, const LevelData& L, const double* b_src, const int* gather, double* b_int, double w,
-                       int nsweeps, double* x, const int* done) {
+void launch_smooth(const Ctx& c, const LevelData& L, const double* b_src, const int* gather, double* b_int, const double* x_in,
+                   double w, int nsweeps, double* x_out, const int* scatter, double* x_ext, double* r_out, const int* done) {
   g_launch_counter++;
-  if (L.maxPartRows <= 256)
-    pre_smooth_kernel<256><<<L.nparts, 256, 0, c.stream>>>(L.pstart, L.A.ptr, L.A.col, L.A.val, L.diag, b_src, gather, b_int, w, nsweeps, x, done);
-  else if (L.maxPartRows <= 512)
-    pre_smooth_kernel<512><<<L.nparts, 512, 0, c.stream>>>(L.pstart, L.A.ptr, L.A.col, L.A.val, L.diag, b_src, gather, b_int, w, nsweeps, x, done);
-  else
-    pre_smooth_kernel<1024><<<L.nparts, 1024, 0, c.stream>>>(L.pstart, L.A.ptr, L.A.col, L.A.val, L.diag, b_src, gather, b_int, w, nsweeps, x, done);
-  FSB_CHECK_LAUNCH();
-}
-
-void launch_post_smooth(const Ctx& c, const LevelData& L, const double* b_int, const double* x_in, double w, int nsweeps,
-                        double* x_out, const int* scatter, double* x_ext, const int* done) {
-  g_launch_counter++;
-  if (L.maxPartRows <= 256)
-    post_smooth_kernel<256><<<L.nparts, 256, 0, c.stream>>>(L.pstart, L.A.ptr, L.A.col, L.A.val, L.diag, b_int, x_in, w, nsweeps, x_out, scatter, x_ext, done);
-  else if (L.maxPartRows <= 512)
-    post_smooth_kernel<512><<<L.nparts, 512, 0, c.stream>>>(L.pstart, L.A.ptr, L.A.col, L.A.val, L.diag, b_int, x_in, w, nsweeps, x_out, scatter, x_ext, done);
-  else
-    post_smooth_kernel<1024><<<L.nparts, 1024, 0, c.stream>>>(L.pstart, L.A.ptr, L.A.col, L.A.val, L.diag, b_int, x_in, w, nsweeps, x_out, scatter, x_ext, done);
+  ProfScope ps(c, x_in ? "post_smooth" : "pre_smooth");
+  cudaStream_t s = c.stream;
+  const int threads = std::max(32, (L.maxPartRows + 31) & ~31);
+#define FSB_ELL_ARGS L.pstart, L.ellptr, L.ellK, L.ellval, L.ellcol, L.diag, b_src, gather, b_int, x_in, w, nsweeps, x_out, scatter, x_ext, r_out, done
+  if (L.use_ell && L.ellMaxK <= 16 && L.maxPartRows <= 512) smooth_ell_kernel<16, 512><<<L.nparts, threads, 0, s>>>(FSB_ELL_ARGS);
+  else if (L.use_ell && L.ellMaxK <= 16) smooth_ell_kernel<16, 1024><<<L.nparts, threads, 0, s>>>(FSB_ELL_ARGS);
+  else if (L.use_ell && L.ellMaxK <= 32 && L.maxPartRows <= 512) smooth_ell_kernel<32, 512><<<L.nparts, threads, 0, s>>>(FSB_ELL_ARGS);
+  else if (L.smemBytes > 0) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      FSB_CUDA(cudaFuncSetAttribute(smooth_cluster_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(L.nparts * L.clusterC); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = L.smemBytes; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = L.clusterC; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    FSB_CUDA(cudaLaunchKernelEx(&cfg, smooth_cluster_kernel<512>, L.clusterC, L.coopG, L.maxChunkNnz, L.maxPartRows, L.maxChunkRows,
+                                (const int*)L.pstart.get(), (const int*)L.A.ptr.get(), (const int*)L.A.col.get(), (const double*)L.A.val.get(),
+                                (const double*)L.diag.get(), b_src, gather, b_int, x_in, w, nsweeps, x_out, scatter, x_ext, r_out, done));
+  } else
+    smooth_coop_kernel<512><<<L.nparts, 512, 0, s>>>(L.coopG, L.pstart, L.A.ptr, L.A.col, L.A.val, L.diag, b_src, gather, b_int, x_in, w,
+                                                    nsweeps, x_out, scatter, x_ext, r_out, done);
+#undef FSB_ELL_ARGS
   FSB_CHECK_LAUNCH();
 }
 
 void launch_coarse_solve(const Ctx& c, int n, const double* Ainv, const double* b, double* x, const int* done) {
   g_launch_counter++;
+  ProfScope ps(c, "coarse_solve");
   coarse_gemv_kernel<<<cdiv(n, 8), 256, 0, c.stream>>>(n, Ainv, b, x, done);
   FSB_CHECK_LAUNCH();
 }
@@ -331,6 +550,7 @@ void launch_cg_init(const Ctx& c, PcgScalars* sc, double tol, int maxit) {
 
 void launch_dot(const Ctx& c, int n, const double* a, const double* b, double* partials, PcgScalars* sc, int which) {
   g_launch_counter++;
+  ProfScope ps(c, "dot");
   int blocks = vec_blocks(c, n);
   if (which == 0) dot_kernel<0><<<blocks, 256, 0, c.stream>>>(n, a, b, partials, sc);
   else if (which == 1) dot_kernel<1><<<blocks, 256, 0, c.stream>>>(n, a, b, partials, sc);
@@ -340,12 +560,14 @@ void launch_dot(const Ctx& c, int n, const double* a, const double* b, double* p
 
 void launch_cg_update(const Ctx& c, int n, double* x, double* r, const double* p, const double* y, double* partials, PcgScalars* sc, double* hist) {
   g_launch_counter++;
+  ProfScope ps(c, "cg_update");
   cg_update_kernel<<<vec_blocks(c, n), 256, 0, c.stream>>>(n, x, r, p, y, partials, sc, hist);
   FSB_CHECK_LAUNCH();
 }
 
 void launch_cg_pdir(const Ctx& c, int n, double* p, const double* z, const PcgScalars* sc, int first) {
   g_launch_counter++;
+  ProfScope ps(c, "cg_pdir");
   cg_pdir_kernel<<<vec_blocks(c, n), 256, 0, c.stream>>>(n, p, z, sc, first);
   FSB_CHECK_LAUNCH();
 }

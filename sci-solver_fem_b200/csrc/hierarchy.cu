@@ -14,6 +14,7 @@
 #include <cub/cub.cuh>
 
 #include "fsb_internal.h"
+#include "solver.h"
 
 namespace fsb {
 namespace {
@@ -288,6 +289,134 @@ void dense_inverse(const Ctx& c, const DCsr& A, DBuf& Ainv) {
   Ainv.alloc((size_t)n * n, s);
   densify<<<cdiv(n, 128), 128, 0, s>>>(n, A.ptr, A.col, A.val, M);
   gauss_jordan<<<1, 1024, 0, s>>>(n, M, Ainv);
+  FSB_CHECK_LAUNCH();
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Partition split.  The reference splits the permuted matrix into A_in (intra-partition strict
+// upper triangle, packed 16|16 local coordinates, smoothedMG_amg_level.cu:24-43, 199-304) and
+// A_out (inter-partition entries).  Here: A_out as CSR over all rows, and — where rows are short
+// enough to live in registers — the intra-partition off-diagonal entries of BOTH triangles as one
+// column-major ELL slab per partition (16-bit local columns), so the smoother is atomic-free.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void row_partition_kernel(int nparts, const int* __restrict__ pstart, int* __restrict__ rowPart) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nparts) return;
+  for (int r = pstart[p]; r < pstart[p + 1]; r++) rowPart[r] = p;
+}
+
+__global__ void count_in_out_kernel(int n, const int* __restrict__ ptr, const int* __restrict__ col, const int* __restrict__ rowPart,
+                                    const int* __restrict__ pstart, int* __restrict__ nin, int* __restrict__ nout, int* __restrict__ partK) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  int p = rowPart[r], r0 = pstart[p], np = pstart[p + 1] - r0, ci = 0, co = 0;
+  for (int e = ptr[r]; e < ptr[r + 1]; e++) {
+    int c = col[e];
+    if ((unsigned)(c - r0) < (unsigned)np) { if (c != r) ci++; } else co++;
+  }
+  nin[r] = ci; nout[r] = co;
+  atomicMax(&partK[p], ci);
+}
+
+__global__ void fill_out_kernel(int n, const int* __restrict__ ptr, const int* __restrict__ col, const double* __restrict__ val,
+                                const int* __restrict__ rowPart, const int* __restrict__ pstart, const int* __restrict__ optr,
+                                int* __restrict__ ocol, double* __restrict__ oval) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  int p = rowPart[r], r0 = pstart[p], np = pstart[p + 1] - r0, o = optr[r];
+  for (int e = ptr[r]; e < ptr[r + 1]; e++) {
+    int c = col[e];
+    if ((unsigned)(c - r0) >= (unsigned)np) { ocol[o] = c; oval[o] = val[e]; o++; }
+  }
+}
+
+__global__ void chunk_nnz_kernel(int nparts, int C, const int* __restrict__ pstart, const int* __restrict__ ptr, int* __restrict__ cnnz) {
+  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nparts * C) return;
+  int p = q / C, c = q % C;
+  int r0 = pstart[p], np = pstart[p + 1] - r0, chunk = (np + C - 1) / C;
+  int m0 = min(c * chunk, np), m1 = min(m0 + chunk, np);
+  cnnz[q] = ptr[r0 + m1] - ptr[r0 + m0];
+}
+
+__global__ void slab_size_kernel(int nparts, const int* __restrict__ pstart, const int* __restrict__ partK, long long* __restrict__ sz) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < nparts) sz[p] = (long long)partK[p] * (pstart[p + 1] - pstart[p]);
+}
+
+__global__ void fill_ell_kernel(int n, const int* __restrict__ ptr, const int* __restrict__ col, const double* __restrict__ val,
+                                const int* __restrict__ rowPart, const int* __restrict__ pstart, const int* __restrict__ partK,
+                                const long long* __restrict__ ellptr, double* __restrict__ ellval, unsigned short* __restrict__ ellcol) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  int p = rowPart[r], r0 = pstart[p], np = pstart[p + 1] - r0, t = r - r0, K = partK[p], k = 0;
+  long long base = ellptr[p] + t;
+  for (int e = ptr[r]; e < ptr[r + 1]; e++) {
+    int c = col[e];
+    if ((unsigned)(c - r0) < (unsigned)np && c != r) {
+      ellval[base + (long long)k * np] = val[e];
+      ellcol[base + (long long)k * np] = (unsigned short)(c - r0);
+      k++;
+    }
+  }
+  for (; k < K; k++) { ellval[base + (long long)k * np] = 0.0; ellcol[base + (long long)k * np] = (unsigned short)t; }
+}
+
+}  // namespace
+
+void split_partitions(const Ctx& c, LevelData& L) {
+  cudaStream_t s = c.stream;
+  const int n = L.n, np = L.nparts;
+  IBuf rowPart(n, s), nin(n, s), nout(n + 1, s), partK(np, s);
+  nout.zero(); partK.zero();
+  row_partition_kernel<<<cdiv(np, 128), 128, 0, s>>>(np, L.pstart, rowPart);
+  count_in_out_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, L.A.ptr, L.A.col, rowPart, L.pstart, nin, nout, partK);
+  L.Aout.nrows = n; L.Aout.ncols = n;
+  L.Aout.ptr.alloc(n + 1, s);
+  exclusive_scan_i32(nout, L.Aout.ptr, n + 1, s);
+  L.Aout.nnz = L.Aout.ptr.read(n);
+  L.Aout.col.alloc(std::max(1, L.Aout.nnz), s); L.Aout.val.alloc(std::max(1, L.Aout.nnz), s);
+  fill_out_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, L.A.ptr, L.A.col, L.A.val, rowPart, L.pstart, L.Aout.ptr, L.Aout.col, L.Aout.val);
+  L.ellMaxK = reduce_max_i32(partK, np, s);
+  double avg = (double)L.A.nnz / std::max(1, n);
+  L.coopG = avg > 48 ? 32 : avg > 24 ? 16 : avg > 12 ? 8 : avg > 6 ? 4 : 2;
+  L.use_ell = (L.ellMaxK <= 16) || (L.ellMaxK <= 32 && L.maxPartRows <= 512);
+  L.smemBytes = 0;
+  if (!L.use_ell) {
+    // smallest cluster size whose per-CTA slice fits comfortably (two CTAs per SM), else the
+    // largest portable cluster if that fits at all; otherwise the L1/L2-streaming fallback
+    for (int pass = 0; pass < 2 && L.smemBytes == 0; pass++) {
+      for (int C = 1; C <= 8; C *= 2) {
+        IBuf cnnz((size_t)np * C, s);
+        chunk_nnz_kernel<<<cdiv((long long)np * C, 256), 256, 0, s>>>(np, C, L.pstart, L.A.ptr, cnnz);
+        int mx = reduce_max_i32(cnnz, (size_t)np * C, s);
+        int chunkRows = (L.maxPartRows + C - 1) / C;
+        // layout of smooth_cluster_kernel: val[cap] | 2 x double[npmax] | 3 x double[chunkmax] | int[chunkmax+1] | u16[cap]
+        size_t bytes = (size_t)mx * 8 + (size_t)L.maxPartRows * 16 + (size_t)chunkRows * 24 + ((size_t)chunkRows + 1) * 4 + (size_t)mx * 2 + 32;
+        size_t limit = pass == 0 ? 100 * 1024 : 220 * 1024;
+        if (bytes <= limit) { L.clusterC = C; L.maxChunkNnz = mx; L.maxChunkRows = chunkRows; L.smemBytes = (int)bytes; break; }
+      }
+    }
+  }
+  if (L.use_ell) {
+    DevBuf<long long> sz((size_t)np + 1, s);
+    sz.zero();
+    slab_size_kernel<<<cdiv(np, 256), 256, 0, s>>>(np, L.pstart, partK, sz);
+    L.ellptr.alloc((size_t)np + 1, s);
+    void* tmp = nullptr; size_t bytes = 0;
+    FSB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, sz.get(), L.ellptr.get(), np + 1, s));
+    FSB_CUDA(cudaMallocAsync(&tmp, bytes, s));
+    FSB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, bytes, sz.get(), L.ellptr.get(), np + 1, s));
+    cudaFreeAsync(tmp, s);
+    long long total = L.ellptr.read(np);
+    L.ellK.swap(partK);
+    L.ellval.alloc((size_t)std::max<long long>(total, 1), s);
+    L.ellcol.alloc((size_t)std::max<long long>(total, 1), s);
+    fill_ell_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, L.A.ptr, L.A.col, L.A.val, rowPart, L.pstart, L.ellK, L.ellptr, L.ellval, L.ellcol);
+  }
   FSB_CHECK_LAUNCH();
 }
 

@@ -4,21 +4,19 @@
 
 namespace fsb {
 
-// y = A x (mode 0), y = b - A x (mode 1), y = y + A x (mode 2); lanes-per-row chosen from nnz/row.
-void launch_spmv(const Ctx& c, const DCsr& A, const double* x, double* y, int mode, const double* b, const int* done);
+// y = A x (mode 0), y = b - A x (1), y += A x (2), y -= A x (3); CSR-stream kernel. `name` tags the profile.
+void launch_spmv(const Ctx& c, const DCsr& A, const double* x, double* y, int mode, const double* b, const int* done, const char* name);
 // y = A x and the dot product x.y folded into the same pass; the last CTA finishes
 // py and alpha = rz_old / py in device memory.
 void launch_spmv_dot(const Ctx& c, const DCsr& A, const double* x, double* y, double* partials, PcgScalars* sc);
 
-// fused pre-smoothing of one level: x = w b / d, nsweeps partition-local Jacobi sweeps.
-// b_src is read through `gather` (level > 0: external -> internal numbering) and, when b_int
-// is non-null, saved in internal numbering for the residual and post-smoothing stages.
-void launch_pre_smooth(const Ctx& c, const LevelData& L, const double* b_src, const int* gather, double* b_int,
-                       double w, int nsweeps, double* x, const int* done);
-// fused post-smoothing: b' = b - A_out x_in, nsweeps sweeps from x_in, result to x_out
-// (internal) and/or scattered to x_ext through `scatter`.
-void launch_post_smooth(const Ctx& c, const LevelData& L, const double* b_int, const double* x_in, double w, int nsweeps,
-                        double* x_out, const int* scatter, double* x_ext, const int* done);
+// fused smoothing stage of one level (partition-local Jacobi sweeps, x resident on chip):
+//   pre  (x_in == null): x = w b / d, nsweeps sweeps, x -> x_out, in-partition residual -> r_out
+//   post (x_in != null): nsweeps sweeps from x_in with b = b_src (already b - A_out x_in)
+// b_src is read through `gather` (level > 0: external -> internal numbering) and saved to b_int when
+// non-null; the result goes to x_out (internal) and/or is scattered to x_ext through `scatter`.
+void launch_smooth(const Ctx& c, const LevelData& L, const double* b_src, const int* gather, double* b_int, const double* x_in,
+                   double w, int nsweeps, double* x_out, const int* scatter, double* x_ext, double* r_out, const int* done);
 void launch_coarse_solve(const Ctx& c, int n, const double* Ainv, const double* b, double* x, const int* done);
 
 // PCG vector kernels (device-resident scalars)

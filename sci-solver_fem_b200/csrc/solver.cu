@@ -29,6 +29,7 @@ Solver::Solver(int device) {
   FSB_CUDA(cudaEventCreate(&ev0_));
   FSB_CUDA(cudaEventCreate(&ev1_));
   prm.device = device;
+  ctx.prof = &profiler;
 }
 
 Solver::~Solver() {
@@ -175,6 +176,7 @@ void Solver::setup() {
     }
     L.diag.alloc(N, s);
     extract_diag(ctx, L.A, L.diag);
+    split_partitions(ctx, L);
     build_prolongator(ctx, L.A, L.diag, L.agg.aggregateIdx, L.nnout, prm.proOmega, L.P);
     transpose_csr(ctx, L.P, L.R);
     DCsr AP, Ac;
@@ -204,25 +206,29 @@ void Solver::setup() {
 void Solver::vcycle(int lev, const double* b_src, const int* gather, double* x_dst, const int* scatter, double* /*unused*/) {
   LevelData& L = levels[lev];
   const int* done = cg_active_ ? &scal.get()->done : nullptr;
+  profiler.cur_level = lev;
   if (lev == (int)levels.size() - 1) {  // coarsest: direct solve (amg_level.cu:25-31)
     launch_coarse_solve(ctx, L.n, Ainv, b_src, x_dst, done);
     return;
   }
   const double w = prm.smootherWeight;
   const double* b_eff = gather ? L.b.get() : b_src;
-  launch_pre_smooth(ctx, L, b_src, gather, gather ? L.b.get() : nullptr, w, prm.preInnerIters, L.x, done);
-  launch_spmv(ctx, L.A, L.x, L.r, 1, b_eff, done);            // r = b - A x
-  launch_spmv(ctx, L.R, L.r, L.bc, 0, nullptr, done);         // bc = R r
+  // pre: x = w b/d, nu1 sweeps, r = b - A_in x - d x  (one kernel, matrix slab read once)
+  launch_smooth(ctx, L, b_src, gather, gather ? L.b.get() : nullptr, nullptr, w, prm.preInnerIters, L.x, nullptr, nullptr, L.r, done);
+  launch_spmv(ctx, L.Aout, L.x, L.r, 3, nullptr, done, "residual_out");   // r -= A_out x   (preAout_kernel)
+  launch_spmv(ctx, L.R, L.r, L.bc, 0, nullptr, done, "restrict");         // bc = R r
   const bool next_is_coarsest = (lev + 1 == (int)levels.size() - 1);
   const int* ip = next_is_coarsest ? nullptr : levels[lev + 1].agg.ipermutation.get();
   vcycle(lev + 1, L.bc, ip, L.xc, ip, nullptr);
-  launch_spmv(ctx, L.P, L.xc, L.x, 2, nullptr, done);         // x += P xc
+  profiler.cur_level = lev;
+  launch_spmv(ctx, L.P, L.xc, L.x, 2, nullptr, done, "prolong_add");      // x += P xc
   double* xin = L.x;
   double* xtmp = L.x2;
   for (int rel = 0; rel < prm.postRelaxes; rel++) {
     bool lastpass = (rel == prm.postRelaxes - 1);
-    if (lastpass) launch_post_smooth(ctx, L, b_eff, xin, w, prm.postInnerIters, scatter ? nullptr : x_dst, scatter, scatter ? x_dst : nullptr, done);
-    else { launch_post_smooth(ctx, L, b_eff, xin, w, prm.postInnerIters, xtmp, nullptr, nullptr, done); std::swap(xin, xtmp); }
+    launch_spmv(ctx, L.Aout, xin, L.r, 1, b_eff, done, "bprime");         // b' = b - A_out x (x frozen for this pass)
+    if (lastpass) launch_smooth(ctx, L, L.r, nullptr, nullptr, xin, w, prm.postInnerIters, scatter ? nullptr : x_dst, scatter, scatter ? x_dst : nullptr, nullptr, done);
+    else { launch_smooth(ctx, L, L.r, nullptr, nullptr, xin, w, prm.postInnerIters, xtmp, nullptr, nullptr, nullptr, done); std::swap(xin, xtmp); }
   }
   if (prm.postRelaxes <= 0) {  // degenerate configuration: no post-relaxation pass
     if (scatter) launch_scatter(ctx, L.n, scatter, xin, x_dst);
@@ -230,7 +236,7 @@ void Solver::vcycle(int lev, const double* b_src, const int* gather, double* x_d
   }
 }
 
-void Solver::spmv_fine(const double* x, double* y) { launch_spmv(ctx, levels.at(0).A, x, y, 0, nullptr, nullptr); FSB_CUDA(cudaStreamSynchronize(ctx.stream)); }
+void Solver::spmv_fine(const double* x, double* y) { launch_spmv(ctx, levels.at(0).A, x, y, 0, nullptr, nullptr, "spmv"); FSB_CUDA(cudaStreamSynchronize(ctx.stream)); }
 
 void Solver::precondition(const double* r, double* z) {
   if (!has_setup) throw std::runtime_error("precondition before setup");
@@ -276,13 +282,16 @@ void Solver::pcg(const double* b_user, double* x_user) {
     cg_b.from_device(b_user, n); cg_x.from_device(x_user, n);
   }
   launch_dot(ctx, n, cg_b, cg_b, partials, sc, 0);                 // bnorm
-  launch_spmv(ctx, L0.A, cg_x, cg_r, 1, cg_b, nullptr);            // r = b - A x
+  launch_spmv(ctx, L0.A, cg_x, cg_r, 1, cg_b, nullptr, "residual"); // r = b - A x
   vcycle(0, cg_r, nullptr, cg_z, nullptr, nullptr);                // z = M^-1 r
   launch_cg_pdir(ctx, n, cg_p, cg_z, sc, 1);                       // p = z
   launch_dot(ctx, n, cg_r, cg_z, partials, sc, 1);                 // rz_old
   FSB_CUDA(cudaStreamSynchronize(s));
 
-  if (prm.useGraphs && !iter_graph_) {
+  profiler.cur_level = 0;
+  const bool graphs = prm.useGraphs && !prm.profile;
+  if (!graphs) destroy_graph();
+  if (graphs && !iter_graph_) {
     cudaGraph_t g;
     FSB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
     enqueue_pcg_iteration();
@@ -294,7 +303,7 @@ void Solver::pcg(const double* b_user, double* x_user) {
   {
     long long before = g_launch_counter;
     // count the kernels of one iteration without launching: known structure
-    per_iter = 4 + 1 + (long long)(levels.size() - 1) * (4 + std::max(prm.postRelaxes, 1));
+    per_iter = 4 + 1 + (long long)(levels.size() - 1) * (4 + 2 * std::max(prm.postRelaxes, 1));
     (void)before;
   }
   PcgScalars h;
@@ -325,6 +334,8 @@ void Solver::solve(const double* b, double* x, bool on_device) {
   cudaStream_t s = ctx.stream;
   const int n = levels[0].n;
   g_launch_counter = 0;
+  profiler.clear();
+  profiler.on = prm.profile != 0;
   DBuf bd, xd;
   const double* bp = b;
   double* xp = x;
@@ -349,7 +360,26 @@ void Solver::solve(const double* b, double* x, bool on_device) {
   }
   toc("solve");
   launches = g_launch_counter;
+  profiler.on = false;
   if (!on_device) xd.to_host(x, n);
+}
+
+std::string Solver::profile_report() {
+  std::map<std::pair<std::string, int>, std::pair<long long, double>> agg;
+  FSB_CUDA(cudaStreamSynchronize(ctx.stream));
+  for (auto& r : profiler.recs) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) { cudaGetLastError(); continue; }
+    auto& a = agg[{r.name, r.level}];
+    a.first++; a.second += ms;
+  }
+  std::string out;
+  char line[256];
+  for (auto& kv : agg) {
+    snprintf(line, sizeof line, "%s %d %lld %.6f\n", kv.first.first.c_str(), kv.first.second, kv.second.first, kv.second.second);
+    out += line;
+  }
+  return out;
 }
 
 }  // namespace fsb

@@ -21,6 +21,7 @@ struct Params {
   int refLevel0NoPerm = 0;
   int useGraphs = 1;   // capture one PCG iteration into a CUDA graph
   int checkEvery = 2;  // PCG iterations enqueued between convergence polls
+  int profile = 0;     // 1: time every solve-phase kernel with CUDA events (disables graphs for that solve)
 };
 
 // device-resident PCG state: no scalar ever crosses PCIe inside the iteration
@@ -37,6 +38,17 @@ struct LevelData {
   DCsr P, R;          // P: rows internal(l), cols external(l+1); R = P^T
   Aggregation agg;
   IBuf pstart;        // first row of each partition (nparts+1)
+  DCsr Aout;          // inter-partition entries (rows internal numbering, global columns)
+  bool use_ell = false;  // intra-partition off-diagonal entries as per-partition column-major ELL slabs
+  int ellMaxK = 0, coopG = 1;
+  int clusterC = 1;      // CTAs per partition of the cluster smoother
+  int maxChunkNnz = 0;   // largest number of CSR entries of one CTA's row chunk
+  int maxChunkRows = 0;
+  int smemBytes = 0;     // > 0: the cluster smoother is usable (chunk fits in shared memory)
+  DevBuf<long long> ellptr;  // nparts+1 slab offsets (entries)
+  IBuf ellK;                 // slab width of each partition
+  DBuf ellval;
+  DevBuf<unsigned short> ellcol;
   IBuf xadj, adj;     // graph handed to the aggregator (external numbering)
   DBuf b, x, x2, r;   // work vectors, internal numbering
   DBuf bc, xc;        // restricted residual / coarse correction, external numbering of level l+1
@@ -71,6 +83,8 @@ class Solver {
   void spmv_fine(const double* x, double* y);
   void precondition(const double* r, double* z);   // one V-cycle, z = M^-1 r
   long long launches = 0;              // kernels launched by the last solve()
+  std::string profile_report();        // "name level launches total_ms" lines of the last profiled solve
+  Profiler profiler;
 
   Ctx ctx;
   Mesh mesh;

@@ -1,0 +1,431 @@
+// FEMSolver.cpp — the reference's FEMSolver surface (src/FEMSolver.cu) over the C-ABI of
+// libfemsolver_b200.so.  Host side only: parsing, format conversion, parameter forwarding; every
+// numerical stage (pattern, assembly, AMG setup, PCG / V-cycle) runs in the CUDA library.
+#include "FEMSolver.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <sstream>
+#include <stdexcept>
+
+#include "../../include/femsolver_b200.h"
+
+bool TriMesh::verbose = false;
+
+// ------------------------------------------------------------------------------------------- meshes
+static bool next_data_line(std::ifstream& f, std::string& line) {
+  while (f.good()) {
+    std::getline(f, line);
+    if (line.empty() || line.at(0) == '#') continue;
+    return true;
+  }
+  return false;
+}
+
+// TetMesh::read, tetmesh.cu:251-376: %f into float, 0/1-based auto-detect, optional label column,
+// second decrement when the minimum index is 1.
+TetMesh* TetMesh::read(const char* nodefilename, const char* elefilename, const bool verb) {
+  TetMesh* mesh = new TetMesh();
+  mesh->set_verbose(verb);
+  std::ifstream nodefile(nodefilename), elefile(elefilename);
+  if (!nodefile.is_open() || !elefile.is_open()) {
+    printf("node or ele file open failed!\n");
+    exit(0);
+  }
+  std::string line;
+  int nv = 0, tmp;
+  if (!next_data_line(nodefile, line) || sscanf(line.c_str(), "%d %d %d %d", &nv, &tmp, &tmp, &tmp) != 4) {
+    std::cerr << "Bad Node file" << std::endl;
+    exit(0);
+  }
+  mesh->vertices.resize(nv);
+  size_t i = 0;
+  while (i < (size_t)nv && next_data_line(nodefile, line)) {
+    float x, y, z;
+    if (sscanf(line.c_str(), "%d %f %f %f", &tmp, &x, &y, &z) != 4) {
+      std::cerr << "Bad Node file, line # " << i << std::endl;
+      exit(0);
+    }
+    mesh->vertices[i][0] = x; mesh->vertices[i][1] = y; mesh->vertices[i][2] = z;
+    i++;
+  }
+  int ne = 0, haslabel = 0;
+  if (!next_data_line(elefile, line) || sscanf(line.c_str(), "%d %d %d", &ne, &tmp, &haslabel) != 3) {
+    std::cerr << "Bad Ele file" << std::endl;
+    exit(0);
+  }
+  mesh->tets.resize(ne);
+  mesh->matlabels.resize(ne, 0);
+  bool zero_based = false;
+  i = 0;
+  while (i < (size_t)ne && next_data_line(elefile, line)) {
+    int t[4], mat = 0;
+    int got = haslabel == 0 ? sscanf(line.c_str(), "%d %d %d %d %d", &tmp, &t[0], &t[1], &t[2], &t[3])
+                            : sscanf(line.c_str(), "%d %d %d %d %d %d", &tmp, &t[0], &t[1], &t[2], &t[3], &mat);
+    if (got != (haslabel == 0 ? 5 : 6)) {
+      std::cerr << "Bad Ele file, line # " << i << std::endl;
+      exit(0);
+    }
+    if (haslabel != 0) mesh->matlabels[i] = mat;
+    for (int j = 0; j < 4; j++) { mesh->tets[i][j] = t[j]; if (t[j] == 0) zero_based = true; }
+    i++;
+  }
+  if (!zero_based) for (auto& t : mesh->tets) for (int j = 0; j < 4; j++) t[j]--;
+  int minidx = INT32_MAX;
+  for (auto& t : mesh->tets) for (int j = 0; j < 4; j++) minidx = std::min(minidx, t[j]);
+  if (minidx == 1) for (auto& t : mesh->tets) for (int j = 0; j < 4; j++) t[j]--;
+  return mesh;
+}
+
+// ASCII PLY with x y z first (TriMesh_io.cu:259, :874-878 use %lf)
+TriMesh* TriMesh::read(const char* filename) {
+  std::ifstream f(filename);
+  if (!f.is_open()) return NULL;
+  std::string tok, line;
+  std::getline(f, line);
+  if (line.substr(0, 3) != "ply") return NULL;
+  int nv = 0, nf = 0, nprop = 0;
+  bool in_vertex = false, ascii = false;
+  while (std::getline(f, line)) {
+    std::istringstream ss(line);
+    ss >> tok;
+    if (tok == "format") { ss >> tok; ascii = (tok == "ascii"); }
+    else if (tok == "element") { ss >> tok; in_vertex = (tok == "vertex"); if (tok == "vertex") ss >> nv; else if (tok == "face") ss >> nf; }
+    else if (tok == "property" && in_vertex) nprop++;
+    else if (tok == "end_header") break;
+  }
+  if (!ascii || nprop < 3) return NULL;
+  TriMesh* m = new TriMesh();
+  m->vertices.resize(nv);
+  for (int i = 0; i < nv; i++) {
+    for (int j = 0; j < nprop; j++) { double v; if (!(f >> v)) { delete m; return NULL; } if (j < 3) m->vertices[i][j] = v; }
+  }
+  m->faces.resize(nf);
+  for (int i = 0; i < nf; i++) {
+    int k; if (!(f >> k) || k != 3) { delete m; return NULL; }
+    f >> m->faces[i][0] >> m->faces[i][1] >> m->faces[i][2];
+  }
+  return m;
+}
+
+// neighbours in discovery order (tetmesh.cu:112-170 / TriMesh_connectivity.cu:96-131).  The solver
+// itself takes adjacency from the device-built pattern; these exist for callers that read
+// `mesh->neighbors` directly.
+template <typename Mesh, typename Elems>
+static void neighbors_by_discovery(Mesh* m, const Elems& elems, int npe) {
+  if (!m->neighbors.empty()) return;
+  m->neighbors.resize(m->vertices.size());
+  for (size_t e = 0; e < elems.size(); e++)
+    for (int j = 0; j < npe; j++) {
+      std::vector<int>& me = m->neighbors[elems[e][j]];
+      for (int d = 1; d < npe; d++) {
+        int nb = elems[e][(j + d) % npe];
+        if (std::find(me.begin(), me.end(), nb) == me.end()) me.push_back(nb);
+      }
+    }
+}
+void TetMesh::need_neighbors() { neighbors_by_discovery(this, tets, 4); }
+void TriMesh::need_neighbors() { neighbors_by_discovery(this, faces, 3); }
+
+// ------------------------------------------------------------------------------------------- FEMSolver
+static void check(fsb_solver* s, int rc) {
+  if (rc == FSB_OK) return;
+  std::string msg = fsb_last_error(s);
+  if (rc == FSB_ERR_INVALID) throw std::invalid_argument(msg);
+  // upstream: FatalError -> backtrace + exit(1) (core/include/error.h:52-55)
+  std::cerr << "FEMSolver (B200) fatal error: " << msg << std::endl;
+  exit(1);
+}
+
+FEMSolver::FEMSolver(std::string fname, bool isTetMesh, bool verbose)
+    : verbose_(verbose), filename_(fname), maxLevels_(100), maxIters_(100), preInnerIters_(5), postInnerIters_(5), postRelaxes_(1),
+      cycleIters_(1), dsType_(0), topSize_(256), randMisParameters_(90102), partitionMaxSize_(512), aggregatorType_(0),
+      convergeType_(0), tolerance_(1e-6), cycleType_(0), solverType_(0), smootherWeight_(1.0), proOmega_(0.67), device_(0),
+      blockSize_(256), tetMesh_(NULL), triMesh_(NULL), seed_(0), refLevel0NoPerm_(0), iterations_(0), relres_(-1), impl_(NULL),
+      A_from_file_(false) {
+  if (fsb_create(&impl_, device_) != FSB_OK) {
+    std::cerr << "FEMSolver (B200): " << fsb_last_error(NULL) << std::endl;
+    exit(1);
+  }
+  if (isTetMesh) {
+    this->tetMesh_ = TetMesh::read((this->filename_ + ".node").c_str(), (this->filename_ + ".ele").c_str(), verbose);
+  } else {
+    TriMesh::verbose = verbose;
+    this->triMesh_ = TriMesh::read(this->filename_.c_str());
+  }
+  this->getMatrixFromMesh();
+}
+
+FEMSolver::~FEMSolver() {
+  if (this->tetMesh_ != NULL) delete this->tetMesh_;
+  if (this->triMesh_ != NULL) delete this->triMesh_;
+  fsb_destroy(impl_);
+}
+
+void FEMSolver::pushParams() {
+  struct { const char* n; double v; } p[] = {
+    {"verbose", (double)verbose_}, {"maxLevels", (double)maxLevels_}, {"maxIters", (double)maxIters_},
+    {"preInnerIters", (double)preInnerIters_}, {"postInnerIters", (double)postInnerIters_}, {"postRelaxes", (double)postRelaxes_},
+    {"cycleIters", (double)cycleIters_}, {"dsType", (double)dsType_}, {"topSize", (double)topSize_},
+    {"randMisParameters", (double)randMisParameters_}, {"partitionMaxSize", (double)partitionMaxSize_},
+    {"aggregatorType", (double)aggregatorType_}, {"convergeType", (double)convergeType_}, {"tolerance", tolerance_},
+    {"cycleType", (double)cycleType_}, {"solverType", (double)solverType_}, {"smootherWeight", smootherWeight_},
+    {"proOmega", proOmega_}, {"blockSize", (double)blockSize_}, {"seed", (double)seed_}, {"refLevel0NoPerm", (double)refLevel0NoPerm_}};
+  for (auto& q : p) check(impl_, fsb_set_param(impl_, q.n, q.v));
+}
+
+// device CSR (fp64) -> the public float ELL mirror: slot 0 = diagonal, then ascending neighbours,
+// invalid_index padding (cutil.cu:197-226); also fills mesh->neighbors (sorted, as after tetmesh2ell).
+void FEMSolver::pullMatrix() {
+  int n = fsb_matrix_rows(impl_);
+  long long nnz = fsb_matrix_nnz(impl_);
+  std::vector<int> ptr(n + 1), col(nnz);
+  std::vector<double> val(nnz);
+  check(impl_, fsb_get_matrix_csr(impl_, ptr.data(), col.data(), val.data()));
+  int maxrow = 0;
+  for (int i = 0; i < n; i++) maxrow = std::max(maxrow, ptr[i + 1] - ptr[i]);
+  A_h_.resize(n, n, nnz, maxrow, 32);
+  std::vector<std::vector<int> >& nb = tetMesh_ ? tetMesh_->neighbors : triMesh_->neighbors;
+  nb.assign(n, std::vector<int>());
+  for (int i = 0; i < n; i++) {
+    int slot = 1;
+    for (int e = ptr[i]; e < ptr[i + 1]; e++) {
+      if (col[e] == i) { A_h_.column_indices(i, 0) = i; A_h_.values(i, 0) = (float)val[e]; }
+      else { A_h_.column_indices(i, slot) = col[e]; A_h_.values(i, slot) = (float)val[e]; nb[i].push_back(col[e]); slot++; }
+    }
+  }
+}
+
+void FEMSolver::getMatrixFromMesh() {
+  if (this->triMesh_ == NULL && this->tetMesh_ == NULL) exit(0);  // FEMSolver.cu:142-143
+  pushParams();
+  if (tetMesh_) {
+    size_t nv = tetMesh_->vertices.size(), ne = tetMesh_->tets.size();
+    std::vector<double> xyz(3 * nv);
+    std::vector<int> el(4 * ne);
+    for (size_t i = 0; i < nv; i++) for (int j = 0; j < 3; j++) xyz[3 * i + j] = tetMesh_->vertices[i][j];
+    for (size_t i = 0; i < ne; i++) for (int j = 0; j < 4; j++) el[4 * i + j] = tetMesh_->tets[i][j];
+    check(impl_, fsb_set_tet_mesh(impl_, (int)nv, xyz.data(), (int)ne, el.data(), tetMesh_->matlabels.empty() ? NULL : tetMesh_->matlabels.data()));
+  } else {
+    size_t nv = triMesh_->vertices.size(), ne = triMesh_->faces.size();
+    std::vector<double> xyz(3 * nv);
+    std::vector<int> el(3 * ne);
+    for (size_t i = 0; i < nv; i++) for (int j = 0; j < 3; j++) xyz[3 * i + j] = triMesh_->vertices[i][j];
+    for (size_t i = 0; i < ne; i++) for (int j = 0; j < 3; j++) el[3 * i + j] = triMesh_->faces[i][j];
+    check(impl_, fsb_set_tri_mesh(impl_, (int)nv, xyz.data(), (int)ne, el.data()));
+  }
+  check(impl_, fsb_assemble(impl_));
+  pullMatrix();
+  A_from_file_ = false;
+}
+
+size_t FEMSolver::getMatrixRows() { return this->A_h_.num_rows; }
+
+void FEMSolver::checkMatrixForValidContents(Matrix_ell_h* A_h) {
+  if (A_h->num_rows == 0) {
+    if (this->verbose_) printf("Error no matrix specified\n");
+    throw std::invalid_argument("Error no matrix specified");
+  }
+}
+
+void FEMSolver::solveFEM(Vector_h_CG* x_h, Vector_h_CG* b_h) {
+  this->checkMatrixForValidContents(&this->A_h_);
+  pushParams();
+  if (A_from_file_) {
+    // the reference solves whatever is in A_h_ (float values, FEMSolver.cu:63): ELL -> CSR, ascending columns
+    size_t n = A_h_.num_rows, K = A_h_.column_indices.num_cols;
+    std::vector<int> ptr(n + 1, 0), col;
+    std::vector<double> val;
+    std::vector<std::pair<int, double> > row;
+    for (size_t i = 0; i < n; i++) {
+      row.clear();
+      for (size_t j = 0; j < K; j++) {
+        int c = A_h_.column_indices(i, j);
+        if (c != Matrix_ell_h::invalid_index) row.push_back(std::make_pair(c, (double)A_h_.values(i, j)));
+      }
+      std::sort(row.begin(), row.end());
+      for (auto& e : row) { col.push_back(e.first); val.push_back(e.second); }
+      ptr[i + 1] = (int)col.size();
+    }
+    check(impl_, fsb_set_matrix_csr(impl_, (int)n, (long long)col.size(), ptr.data(), col.data(), val.data()));
+  }
+  int iters = 0; double relres = -1;
+  check(impl_, fsb_solve_fem(impl_, b_h->data(), x_h->data(), &iters, &relres));
+  iterations_ = iters; relres_ = relres;
+  if (this->verbose_) printf("Computing time : %.10lf ms\n", fsb_time_ms(impl_, "setup") + fsb_time_ms(impl_, "solve"));
+}
+
+// ------------------------------------------------------------------------------------------- MATLAB v5 / VTK
+namespace {
+struct Reader {
+  std::ifstream in;
+  template <typename T> T get() { T v = T(); in.read((char*)&v, sizeof(T)); return v; }
+  void skip(size_t n) { in.seekg((std::streamoff)n, std::ios::cur); }
+};
+// array-name element: small-data form or long form (FEMSolver.cu:232-256)
+int skip_name(Reader& r, bool allow_long) {
+  uint16_t type = r.get<uint16_t>();
+  uint32_t len = r.get<uint16_t>();
+  int align = 4;
+  if (len == 0 && allow_long) { len = r.get<uint32_t>(); align = 8; }
+  if (type != 1 && type != 2) {
+    std::cerr << "WARNING: Invalid variable type (" << type << ") for array name characters (Must be 8-bit)." << std::endl;
+    return -1;
+  }
+  if (len % align) len += align - len % align;
+  r.skip(len);
+  return 0;
+}
+}  // namespace
+
+int FEMSolver::readMatlabSparseMatrix(const std::string& filename) {
+  Reader r;
+  r.in.open(filename.c_str(), std::ios::binary);
+  if (!r.in.is_open()) { std::cerr << "could not open file: " << filename << std::endl; return 1; }
+  r.skip(128);
+  int32_t type = r.get<int32_t>();
+  if (type == 15) { std::cerr << "Compression not supported. Save matlab data with '-v6' option." << std::endl; return 1; }
+  if (type != 14) { std::cerr << filename << " is not a matlab matrix." << std::endl; return 1; }
+  r.get<uint32_t>();
+  type = r.get<int32_t>();
+  if (type != 6 && type != 5) { std::cerr << "Invalid type for sparse matrix. Must be 32bit." << std::endl; return 1; }
+  r.get<int32_t>();
+  uint32_t mclass = r.get<uint32_t>() & 0xFF;
+  if (mclass != 5) { std::cerr << "This is not a sparse matrix file." << std::endl; return 1; }
+  r.get<uint32_t>();
+  type = r.get<int32_t>();
+  int32_t bytes = r.get<int32_t>();
+  if ((type != 6 && type != 5) || bytes != 8) {
+    std::cerr << "Matrix of wrong dimension type or # of dimensions." << std::endl;
+    std::cerr << "Matrix must be 2 dimensions and of 32bit type." << std::endl;
+    return 1;
+  }
+  int32_t x_dim = r.get<int32_t>(), y_dim = r.get<int32_t>();
+  if (skip_name(r, true) != 0) return -1;
+  auto read_ints = [&](std::vector<int32_t>& v, const char* what) -> bool {
+    int32_t t = r.get<int32_t>();
+    if (t != 6 && t != 5) { std::cerr << "Invalid " << what << " for sparse matrix. Must be 32bit." << std::endl; return false; }
+    int32_t nb = r.get<int32_t>();
+    v.assign(nb / 4, 0);
+    r.in.read((char*)v.data(), nb);
+    r.skip(nb % 8);
+    return true;
+  };
+  std::vector<int32_t> row_vals, col_vals;
+  if (!read_ints(row_vals, "type row index") || !read_ints(col_vals, "column index type")) return 1;
+  type = r.get<int32_t>();
+  if (type != 9) { std::cerr << "Invalid value for sparse matrix. Must be double float." << std::endl; return 1; }
+  bytes = r.get<int32_t>();
+  std::vector<double> vals(bytes / 8, 0);
+  r.in.read((char*)vals.data(), bytes);
+  // merge: every slot of the mesh pattern holds 1e-12f, the file entries are added on top (FEMSolver.cu:341-354)
+  size_t n = (size_t)x_dim;
+  if (n != A_h_.num_rows) { std::cerr << "matrix size does not match the mesh" << std::endl; return 1; }
+  std::vector<std::vector<std::pair<int, float> > > rows(n);
+  const std::vector<std::vector<int> >& nb = tetMesh_ ? tetMesh_->neighbors : triMesh_->neighbors;
+  for (size_t i = 0; i < n; i++) {
+    rows[i].push_back(std::make_pair((int)i, 1e-12f));
+    for (int c : nb[i]) rows[i].push_back(std::make_pair(c, 1e-12f));
+  }
+  for (int32_t j = 0; j < y_dim; j++)
+    for (int32_t q = col_vals[j]; q < col_vals[j + 1]; q++) {
+      std::vector<std::pair<int, float> >& rw = rows[row_vals[q]];
+      float v = static_cast<float>(vals[q]);
+      bool found = false;
+      for (auto& e : rw) if (e.first == j) { e.second = e.second + v; found = true; break; }
+      if (!found) rw.push_back(std::make_pair((int)j, v));
+    }
+  size_t maxrow = 0, nnz = 0;
+  for (auto& rw : rows) { std::sort(rw.begin(), rw.end()); maxrow = std::max(maxrow, rw.size()); nnz += rw.size(); }
+  A_h_.resize(n, (size_t)y_dim, nnz, maxrow, 32);
+  for (size_t i = 0; i < n; i++)
+    for (size_t j = 0; j < rows[i].size(); j++) { A_h_.column_indices(i, j) = rows[i][j].first; A_h_.values(i, j) = rows[i][j].second; }
+  A_from_file_ = true;
+  return 0;
+}
+
+int FEMSolver::readMatlabArray(const std::string& filename, Vector_h_CG* rhs) {
+  Reader r;
+  r.in.open(filename.c_str(), std::ios::in | std::ios::binary);
+  if (!r.in.is_open()) { std::cerr << "could not open file: " << filename << std::endl; return -1; }
+  r.skip(128);
+  int32_t type = r.get<int32_t>();
+  if (type == 15) { std::cerr << "Compression not supported. Save matlab data with '-v6' option." << std::endl; return -1; }
+  if (type != 14) { std::cerr << filename << " is not a matlab matrix." << std::endl; return -1; }
+  r.get<uint32_t>();
+  type = r.get<int32_t>();
+  if (type != 6) { std::cerr << "Invalid type for normal matrix. Must be double precision." << std::endl; return -1; }
+  r.get<int32_t>();
+  uint32_t mclass = r.get<uint32_t>() & 0xFF;
+  if (mclass == 5) { std::cerr << "This import routine is not for a sparse matrix file." << std::endl; return -1; }
+  r.get<uint32_t>();
+  type = r.get<int32_t>();
+  int32_t bytes = r.get<int32_t>();
+  if ((type != 6 && type != 5) || bytes != 8) {
+    std::cerr << "Matrix of wrong dimension type or # of dimensions." << std::endl;
+    return -1;
+  }
+  r.get<int32_t>(); r.get<int32_t>();
+  if (skip_name(r, false) != 0) return -1;
+  type = r.get<int32_t>();
+  if (type != 9) { std::cerr << "Matrix data type must be miDOUBLE (type is " << type << ")." << std::endl; return -1; }
+  uint32_t len = r.get<uint32_t>();
+  std::vector<double> v(len / 8, 0);
+  r.in.read((char*)v.data(), len);
+  rhs->clear();
+  for (size_t j = 0; j < v.size(); j++) rhs->push_back(v[j]);
+  return 0;
+}
+
+int FEMSolver::writeMatlabArray(const std::string& filename, const Vector_h_CG& array) {
+  std::ofstream file(filename.c_str(), std::ios::out | std::ios::binary);
+  if (!file.is_open()) return 1;
+  std::string desc = "MATLAB 5.0 MAT-file, Platform: GLNXA64, Created by SCI-Solver_FEM.";
+  desc.resize(116, ' ');
+  file.write(desc.c_str(), desc.length());
+  char zeros[8] = {0};
+  file.write(zeros, 8);
+  int16_t version = 0x0100;
+  file.write((char*)&version, 2);
+  file.write("IM", 2);
+  int32_t n = (int32_t)array.size();
+  int32_t hdr[] = {14, 48 + n * 8, 6, 8, 6, 0, 5, 8, n, 1};
+  file.write((char*)hdr, sizeof hdr);
+  int16_t nameTag[] = {1, 3};
+  file.write((char*)nameTag, 4);
+  file.write("x_h\0", 4);
+  int32_t dat[] = {9, n * 8};
+  file.write((char*)dat, sizeof dat);
+  for (size_t i = 0; i < array.size(); i++) { double v = array[i]; file.write((char*)&v, 8); }
+  return 0;
+}
+
+void FEMSolver::writeVTK(std::vector<double> values, std::string fname) {
+  FILE* f = fopen((fname + ".vtk").c_str(), "w+");
+  if (!f) return;
+  fprintf(f, "# vtk DataFile Version 3.0\nvtk output\nASCII\nDATASET UNSTRUCTURED_GRID\n");
+  if (tetMesh_) {
+    int nv = (int)tetMesh_->vertices.size(), nt = (int)tetMesh_->tets.size();
+    fprintf(f, "POINTS %d float\n", nv);
+    for (int i = 0; i < nv; i++) fprintf(f, "%.12f %.12f %.12f\n", tetMesh_->vertices[i][0], tetMesh_->vertices[i][1], tetMesh_->vertices[i][2]);
+    fprintf(f, "CELLS %d %d\n", nt, nt * 5);
+    for (int i = 0; i < nt; i++) fprintf(f, "4 %d %d %d %d\n", tetMesh_->tets[i][0], tetMesh_->tets[i][1], tetMesh_->tets[i][2], tetMesh_->tets[i][3]);
+    fprintf(f, "CELL_TYPES %d\n", nt);
+    for (int i = 0; i < nt; i++) fprintf(f, "10\n");
+    fprintf(f, "POINT_DATA %d\nSCALARS traveltime float 1\nLOOKUP_TABLE default\n", nv);
+    for (size_t i = 0; i < values.size(); i++) fprintf(f, "%.12f\n ", values[i]);
+  } else if (triMesh_) {
+    int nv = (int)triMesh_->vertices.size(), nt = (int)triMesh_->faces.size();
+    fprintf(f, "POINTS %d float\n", nv);
+    for (int i = 0; i < nv; i++) fprintf(f, "%.12f %.12f %.12f\n", triMesh_->vertices[i][0], triMesh_->vertices[i][1], triMesh_->vertices[i][2]);
+    fprintf(f, "CELLS %d %d\n", nt, nt * 4);
+    for (int i = 0; i < nt; i++) fprintf(f, "3 %d %d %d\n", triMesh_->faces[i][0], triMesh_->faces[i][1], triMesh_->faces[i][2]);
+    fprintf(f, "CELL_TYPES %d\n", nt);
+    for (int i = 0; i < nt; i++) fprintf(f, "5\n");
+    fprintf(f, "POINT_DATA %d\nSCALARS traveltime float 1\nLOOKUP_TABLE default\n", nv);
+    for (int i = 0; i < nv && i < (int)values.size(); i++) fprintf(f, "%.12f\n", static_cast<float>(values[i]));
+  }
+  fclose(f);
+}

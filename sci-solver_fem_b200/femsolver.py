@@ -56,6 +56,7 @@ def load_library():
         "fsb_resid_history": (ci, [vp, vp, ci]),
         "fsb_spmv_fine_device": (ci, [vp, vp, vp]), "fsb_precondition_device": (ci, [vp, vp, vp]),
         "fsb_time_ms": (cd, [vp, cs]), "fsb_last_launches": (cll, [vp]), "fsb_stream": (vp, [vp]),
+        "fsb_profile_report": (ci, [vp, vp, ci]),
         "fsb_tet_mass_integrals": (None, [vp]), "fsb_tri_quadrature": (None, [vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
@@ -71,7 +72,8 @@ EXPORTED_SYMBOLS = (
     "fsb_set_tri_mesh fsb_set_tet_mesh_device fsb_set_tri_mesh_device fsb_assemble fsb_matrix_rows fsb_matrix_nnz "
     "fsb_get_matrix_csr fsb_set_matrix_values fsb_set_matrix_csr fsb_setup fsb_num_levels fsb_level_rows fsb_level_nnz "
     "fsb_level_int fsb_level_val fsb_solve fsb_solve_device fsb_solve_fem fsb_resid_history fsb_spmv_fine_device "
-    "fsb_precondition_device fsb_time_ms fsb_last_launches fsb_stream fsb_tet_mass_integrals fsb_tri_quadrature").split()
+    "fsb_precondition_device fsb_time_ms fsb_last_launches fsb_stream fsb_tet_mass_integrals fsb_tri_quadrature "
+    "fsb_profile_report").split()
 
 
 def _p(a):
@@ -88,6 +90,7 @@ _FIELDS = {  # reference field -> (C-ABI parameter, default)   FEMSolver.cu:11-3
     "proOmega_": ("proOmega", 0.67), "device_": ("device", 0), "blockSize_": ("blockSize", 256),
     # additive
     "seed_": ("seed", 0), "refLevel0NoPerm_": ("refLevel0NoPerm", 0), "useGraphs_": ("useGraphs", 1), "checkEvery_": ("checkEvery", 2),
+    "profile_": ("profile", 0),
 }
 
 
@@ -283,6 +286,24 @@ class FEMSolver:
 
     def last_launches(self):
         return self._L.fsb_last_launches(self._h)
+
+    def profile_report(self):
+        """{(kernel, level): (launches, total_ms)} of the last solve run with profile_ = 1."""
+        n = self._L.fsb_profile_report(self._h, None, 0)
+        buf = C.create_string_buffer(max(n, 1))
+        self._L.fsb_profile_report(self._h, buf, n)
+        out = {}
+        for ln in buf.value.decode().splitlines():
+            name, lev, cnt, ms = ln.split()
+            out[(name, int(lev))] = (int(cnt), float(ms))
+        return out
+
+    def solve_device(self, x_ptr: int, b_ptr: int):
+        """Device-pointer variant of solve(): b and x are already resident in HBM."""
+        self._push_params()
+        it, rr = C.c_int(0), C.c_double(0)
+        self._check(self._L.fsb_solve_device(self._h, C.c_void_p(b_ptr), C.c_void_p(x_ptr), C.byref(it), C.byref(rr)))
+        self.iterations, self.relres = it.value, rr.value
 
     # raw handle for bench.py (device-pointer entry points)
     @property

@@ -268,6 +268,27 @@ def write_mat_array(path: str, arr, name: str = "x_h"):
         f.write(hdr + struct.pack("<iI", 14, len(body)) + body)
 
 
+def write_mat_sparse(path: str, nrows: int, ncols: int, jc, ir, pr, name: str = "A"):
+    """Uncompressed v5 sparse matrix (mxSPARSE_CLASS, int32 ir/jc, double pr) that
+    FEMSolver::readMatlabSparseMatrix (FEMSolver.cu:177-356) accepts."""
+    jc = np.ascontiguousarray(jc, dtype="<i4"); ir = np.ascontiguousarray(ir, dtype="<i4"); pr = np.ascontiguousarray(pr, dtype="<f8")
+    desc = b"MATLAB 5.0 MAT-file, Platform: GLNXA64, Created by SCI-Solver_FEM."
+    hdr = desc.ljust(116, b" ") + b"\0" * 8 + struct.pack("<H", 0x0100) + b"IM"
+
+    def pad8(b):
+        return b + b"\0" * ((8 - len(b) % 8) % 8)
+
+    nm = name.encode()[:4]
+    body = struct.pack("<iiII", 6, 8, 5, ir.size)
+    body += struct.pack("<iiii", 5, 8, nrows, ncols)
+    body += struct.pack("<HH", 1, len(nm)) + nm.ljust(4, b"\0")
+    body += struct.pack("<ii", 5, ir.size * 4) + pad8(ir.tobytes())
+    body += struct.pack("<ii", 5, jc.size * 4) + pad8(jc.tobytes())
+    body += struct.pack("<ii", 9, pr.size * 8) + pr.tobytes()
+    with open(path, "wb") as f:
+        f.write(hdr + struct.pack("<iI", 14, len(body)) + body)
+
+
 def csc_to_csr(nrows, ncols, jc, ir, pr):
     """CSC -> CSR with ascending columns (the reference sorts entries by (row, col), FEMSolver.cu:301)."""
     nnz = ir.size

@@ -1,0 +1,67 @@
+"""The reference's own callers against the C++ drop-in: the three gtests (src/test/sanity2D.cc,
+sanity3D.cc, tetVol.cc) and Example1, built by sci-solver_fem_b200/dropin/Makefile, run on the GPU
+with the fixtures materialised from tests/golden (the GPU box has no /root/reference)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import sci_solver_fem_b200 as fsb
+from tests.util import golden
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "sci-solver_fem_b200", "dropin", "bin")
+meshio = fsb.meshio
+
+
+@pytest.fixture(scope="module")
+def data_dir(tmp_path_factory):
+    d = str(tmp_path_factory.mktemp("test_data"))
+    for name, base, key in (("tetVol", "tetVol", "tets"), ("simple3d", "simple", "tets")):
+        g = golden(name)
+        meshio.write_node_ele(os.path.join(d, base), g["verts"], g[key])
+    g = golden("simple2d")
+    meshio.write_ply_ascii(os.path.join(d, "simple.ply"), g["verts"], g["tris"])
+    for name, A, b, ans in (("tetVol", "tetVolA", "tetVolb", "tetVolAns"), ("simple3d", "simple", "simpleb", "simpleAns"),
+                            ("simple2d", "simpleTri", "simpleTrib", "simpleTriAns")):
+        g = golden(name)
+        meshio.write_mat_sparse(os.path.join(d, A + ".mat"), int(g["A_nrows"]), int(g["A_ncols"]), g["A_jc"], g["A_ir"], g["A_pr"])
+        meshio.write_mat_array(os.path.join(d, b + ".mat"), g["b"])
+        meshio.write_mat_array(os.path.join(d, ans + ".mat"), g["ans"])
+    g = golden("CubeMesh_size256step16")
+    meshio.write_node_ele(os.path.join(d, "CubeMesh_size256step16"), g["verts"], g["tets"])
+    return d
+
+
+def run(exe, args, data_dir, cwd):
+    env = dict(os.environ, FSB_TEST_DATA_DIR=data_dir)
+    return subprocess.run([os.path.join(BIN, exe)] + args, env=env, cwd=cwd, capture_output=True, text=True, timeout=600)
+
+
+@pytest.mark.parametrize("exe", ["sanity2D", "sanity3D", "tetVol"])
+def test_reference_gtests(exe, data_dir, tmp_path):
+    if not os.path.exists(os.path.join(BIN, exe)):
+        pytest.fail("drop-in binaries missing: run __graft_entry__.build()")
+    r = run(exe, [], data_dir, str(tmp_path))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "[       OK ]" in r.stdout and "The error is" in r.stdout
+
+
+def test_example1_pcg(data_dir, tmp_path):
+    mesh = os.path.join(data_dir, "tetVol")
+    r = run("Example1", ["-i", mesh, "-A", os.path.join(data_dir, "tetVolA.mat"), "-b", os.path.join(data_dir, "tetVolb.mat"),
+                         "--pcg", "--tol", "1e-8"], data_dir, str(tmp_path))
+    assert r.returncode == 0, r.stdout + r.stderr
+    x = meshio.read_mat_array(os.path.join(str(tmp_path), "output.mat"))
+    g = golden("tetVol")
+    assert np.linalg.norm(x - g["ans"]) / np.linalg.norm(g["ans"]) < 1e-4
+    assert os.path.exists(os.path.join(str(tmp_path), "tetVol.vtk"))
+
+
+def test_example1_default_mesh_assembled_operator(data_dir, tmp_path):
+    """Example1's default input (the non-conforming CubeMesh with inverted tets), assembled K+M, b = 1."""
+    r = run("Example1", ["-i", os.path.join(data_dir, "CubeMesh_size256step16"), "--pcg", "--tol", "1e-8"], data_dir, str(tmp_path))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "rows 4913" in r.stdout
