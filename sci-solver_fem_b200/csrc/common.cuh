@@ -118,6 +118,18 @@ struct DCsr {
   DBuf val;
 };
 
+// Sliced ELL (SELL-32): 32 consecutive rows form a slice stored column-major with the slice's own
+// width, so a warp streams (col, val) with one fully coalesced 128/256-byte request per step and no
+// staging; padding entries carry val = 0 and a valid column.
+struct Sell {
+  int nrows = 0, ncols = 0, nslices = 0;
+  long long nstored = 0;
+  DevBuf<long long> sptr;  // nslices + 1 entry offsets
+  IBuf col;
+  DBuf val;
+  bool ready() const { return nslices > 0; }
+};
+
 // ---- primitives implemented in prims.cu (CUB under the hood; setup-time plumbing only) ----
 void sort_pairs_u64_u32(const uint64_t* kin, uint64_t* kout, const uint32_t* vin, uint32_t* vout, size_t n, int end_bit, cudaStream_t s);
 void sort_keys_u64(const uint64_t* kin, uint64_t* kout, size_t n, int end_bit, cudaStream_t s);

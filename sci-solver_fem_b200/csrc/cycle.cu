@@ -151,10 +151,67 @@ void spmv_dispatch(const Ctx& c, const DCsr& A, const double* x, double* y, cons
   if (n == 0) return;
   g_launch_counter++;
   ProfScope ps(c, name);
-  if (!DOT && (double)A.nnz > 32.0 * n)  // long rows: one warp per row
+  if (!DOT && ((double)A.nnz > 32.0 * n || n < 32768))  // long rows or a small operator: one warp per row
     spmv_vector_kernel<MODE><<<cdiv((long long)n * 32, 256), 256, 0, c.stream>>>(n, A.ptr, A.col, A.val, x, y, b, done);
   else
     csr_stream_kernel<MODE, DOT><<<cdiv(n, SPMV_ROWS), SPMV_ROWS, 0, c.stream>>>(n, A.ptr, A.col, A.val, x, y, b, partials, sc, done);
+  FSB_CHECK_LAUNCH();
+}
+
+// SELL-32 SpMV: thread per row, slice-major storage.  Every step of the k loop is one coalesced
+// request per warp for col and one for val; four steps are kept in flight together with their x
+// gathers.  The row sum runs in column order (same rounding sequence as a sequential CSR loop).
+template <int MODE, bool DOT>
+__global__ void __launch_bounds__(256) sell_spmv_kernel(int n, const long long* __restrict__ sptr, const int* __restrict__ col,
+                                                        const double* __restrict__ val, const double* __restrict__ x,
+                                                        double* __restrict__ y, const double* __restrict__ b,
+                                                        double* __restrict__ partials, PcgScalars* __restrict__ sc,
+                                                        const int* __restrict__ done) {
+  __shared__ double s_warp[32];
+  __shared__ int s_flag;
+  if (done && *done) return;
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  const int slice = row >> 5, lane = threadIdx.x & 31;
+  const int nslices = (n + 31) >> 5;
+  double acc = 0.0;
+  if (slice < nslices) {
+    const long long base = __ldg(sptr + slice);
+    const int K = (int)((__ldg(sptr + slice + 1) - base) >> 5);
+    const int* cp = col + base + lane;
+    const double* vp = val + base + lane;
+    int k = 0;
+    for (; k + 4 <= K; k += 4) {
+      const int c0 = __ldg(cp + k * 32), c1 = __ldg(cp + (k + 1) * 32), c2 = __ldg(cp + (k + 2) * 32), c3 = __ldg(cp + (k + 3) * 32);
+      const double v0 = __ldg(vp + k * 32), v1 = __ldg(vp + (k + 1) * 32), v2 = __ldg(vp + (k + 2) * 32), v3 = __ldg(vp + (k + 3) * 32);
+      const double x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
+      acc += v0 * x0; acc += v1 * x1; acc += v2 * x2; acc += v3 * x3;
+    }
+    for (; k < K; k++) acc += __ldg(vp + k * 32) * __ldg(x + __ldg(cp + k * 32));
+  }
+  double contrib = 0.0;
+  if (row < n) {
+    if (MODE == 0) y[row] = acc;
+    else if (MODE == 1) y[row] = b[row] - acc;
+    else if (MODE == 2) y[row] = y[row] + acc;
+    else y[row] = y[row] - acc;
+    if (DOT) contrib = x[row] * acc;
+  }
+  if (DOT) {
+    double bs = block_sum(contrib, s_warp);
+    if (publish_partial(bs, partials, &sc->ticket[0], &s_flag)) {
+      double tot = final_sum(partials, gridDim.x, s_warp);
+      if (threadIdx.x == 0) { sc->py = tot; sc->alpha = sc->rz_old / tot; }
+    }
+  }
+}
+
+template <int MODE, bool DOT>
+void sell_dispatch(const Ctx& c, const Sell& A, const double* x, double* y, const double* b, double* partials, PcgScalars* sc,
+                   const int* done, const char* name) {
+  if (A.nrows == 0) return;
+  g_launch_counter++;
+  ProfScope ps(c, name);
+  sell_spmv_kernel<MODE, DOT><<<cdiv(A.nrows, 256), 256, 0, c.stream>>>(A.nrows, A.sptr, A.col, A.val, x, y, b, partials, sc, done);
   FSB_CHECK_LAUNCH();
 }
 
@@ -337,13 +394,23 @@ __global__ void __launch_bounds__(BLOCK) smooth_cluster_kernel(int C, int G, int
   for (int t = tid; t <= mn; t += BLOCK) srp[t] = ptr[r0 + m0 + t] - e0;
   __syncthreads();
   const int lane = tid & (G - 1), grp = tid / G, RP = BLOCK / G;
-  for (int t = grp; t < mn; t += RP) {  // stage: lanes of a group read consecutive entries
-    const int qb = srp[t + 1], tl = m0 + t;
-    for (int q = srp[t] + lane; q < qb; q += G) {
-      const int cc = col[e0 + q] - r0;
-      const bool in = (unsigned)cc < (unsigned)np && cc != tl;
-      sval[q] = in ? val[e0 + q] : 0.0;
-      scol[q] = (unsigned short)(in ? cc : tl);
+  {
+    // stage the slice: flat, fully coalesced, every thread keeps several independent loads in flight;
+    // columns become partition-local (0xFFFF = inter-partition entry) ...
+    const int m = srp[mn];
+    for (int q = tid; q < m; q += BLOCK) {
+      const int cc = __ldg(col + e0 + q) - r0;
+      sval[q] = __ldg(val + e0 + q);
+      scol[q] = ((unsigned)cc < (unsigned)np) ? (unsigned short)cc : (unsigned short)0xFFFFu;
+    }
+    __syncthreads();
+    // ... then the diagonal and the inter-partition entries are neutralised to 0 * x[own row]
+    for (int t = grp; t < mn; t += RP) {
+      const int qb = srp[t + 1], tl = m0 + t;
+      for (int q = srp[t] + lane; q < qb; q += G) {
+        const unsigned short cc = scol[q];
+        if (cc == 0xFFFFu || cc == tl) { sval[q] = 0.0; scol[q] = (unsigned short)tl; }
+      }
     }
   }
   cluster.sync();  // all CTAs of the cluster are resident and initialised before remote writes start
@@ -498,6 +565,16 @@ void launch_spmv(const Ctx& c, const DCsr& A, const double* x, double* y, int mo
   else if (mode == 1) spmv_dispatch<1, false>(c, A, x, y, b, nullptr, nullptr, done, name);
   else if (mode == 2) spmv_dispatch<2, false>(c, A, x, y, b, nullptr, nullptr, done, name);
   else spmv_dispatch<3, false>(c, A, x, y, b, nullptr, nullptr, done, name);
+}
+
+void launch_spmv_sell(const Ctx& c, const Sell& A, const double* x, double* y, int mode, const double* b, const int* done, const char* name) {
+  if (mode == 0) sell_dispatch<0, false>(c, A, x, y, b, nullptr, nullptr, done, name);
+  else if (mode == 1) sell_dispatch<1, false>(c, A, x, y, b, nullptr, nullptr, done, name);
+  else if (mode == 2) sell_dispatch<2, false>(c, A, x, y, b, nullptr, nullptr, done, name);
+  else sell_dispatch<3, false>(c, A, x, y, b, nullptr, nullptr, done, name);
+}
+void launch_spmv_dot_sell(const Ctx& c, const Sell& A, const double* x, double* y, double* partials, PcgScalars* sc) {
+  sell_dispatch<0, true>(c, A, x, y, nullptr, partials, sc, &sc->done, "spmv_dot");
 }
 
 void launch_spmv_dot(const Ctx& c, const DCsr& A, const double* x, double* y, double* partials, PcgScalars* sc) {

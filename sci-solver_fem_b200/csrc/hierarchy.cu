@@ -396,7 +396,7 @@ void split_partitions(const Ctx& c, LevelData& L) {
         int chunkRows = (L.maxPartRows + C - 1) / C;
         // layout of smooth_cluster_kernel: val[cap] | 2 x double[npmax] | 3 x double[chunkmax] | int[chunkmax+1] | u16[cap]
         size_t bytes = (size_t)mx * 8 + (size_t)L.maxPartRows * 16 + (size_t)chunkRows * 24 + ((size_t)chunkRows + 1) * 4 + (size_t)mx * 2 + 32;
-        size_t limit = pass == 0 ? 100 * 1024 : 220 * 1024;
+        size_t limit = pass == 0 ? 110 * 1024 : 220 * 1024;
         if (bytes <= limit) { L.clusterC = C; L.maxChunkNnz = mx; L.maxChunkRows = chunkRows; L.smemBytes = (int)bytes; break; }
       }
     }
@@ -417,6 +417,51 @@ void split_partitions(const Ctx& c, LevelData& L) {
     L.ellcol.alloc((size_t)std::max<long long>(total, 1), s);
     fill_ell_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, L.A.ptr, L.A.col, L.A.val, rowPart, L.pstart, L.ellK, L.ellptr, L.ellval, L.ellcol);
   }
+  FSB_CHECK_LAUNCH();
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// CSR -> SELL-32 (the streaming format of the fine-level SpMV family)
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void sell_width_kernel(int n, int nslices, const int* __restrict__ ptr, long long* __restrict__ sz) {
+  int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (s >= nslices) return;
+  int r = s * 32 + lane, len = r < n ? ptr[r + 1] - ptr[r] : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+  if (lane == 0) sz[s] = 32ll * len;
+}
+__global__ void sell_fill_kernel(int n, int ncols, int nslices, const int* __restrict__ ptr, const int* __restrict__ col, const double* __restrict__ val,
+                                 const long long* __restrict__ sptr, int* __restrict__ scol, double* __restrict__ sval) {
+  int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (s >= nslices) return;
+  long long base = sptr[s];
+  int K = (int)((sptr[s + 1] - base) >> 5), r = s * 32 + lane;
+  int e0 = r < n ? ptr[r] : 0, len = r < n ? ptr[r + 1] - e0 : 0;
+  int padcol = min(r, ncols - 1);  // any valid column: the padded value is 0
+  for (int k = 0; k < K; k++) {
+    bool has = k < len;
+    scol[base + (long long)k * 32 + lane] = has ? col[e0 + k] : padcol;
+    sval[base + (long long)k * 32 + lane] = has ? val[e0 + k] : 0.0;
+  }
+}
+}  // namespace
+
+void build_sell(const Ctx& c, const DCsr& A, Sell& S) {
+  cudaStream_t s = c.stream;
+  S.nrows = A.nrows; S.ncols = A.ncols; S.nslices = (A.nrows + 31) / 32;
+  if (S.nslices == 0) return;
+  DevBuf<long long> sz((size_t)S.nslices + 1, s);
+  sz.zero();
+  sell_width_kernel<<<cdiv(S.nslices, 8), 256, 0, s>>>(A.nrows, S.nslices, A.ptr, sz);
+  S.sptr.alloc((size_t)S.nslices + 1, s);
+  exclusive_scan_i64(sz, S.sptr, (size_t)S.nslices + 1, s);
+  S.nstored = S.sptr.read(S.nslices);
+  S.col.alloc((size_t)std::max<long long>(S.nstored, 1), s);
+  S.val.alloc((size_t)std::max<long long>(S.nstored, 1), s);
+  sell_fill_kernel<<<cdiv(S.nslices, 8), 256, 0, s>>>(A.nrows, A.ncols, S.nslices, A.ptr, A.col, A.val, S.sptr, S.col, S.val);
   FSB_CHECK_LAUNCH();
 }
 

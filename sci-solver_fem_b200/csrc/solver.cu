@@ -179,6 +179,11 @@ void Solver::setup() {
     split_partitions(ctx, L);
     build_prolongator(ctx, L.A, L.diag, L.agg.aggregateIdx, L.nnout, prm.proOmega, L.P);
     transpose_csr(ctx, L.P, L.R);
+    if (N >= 32768) {  // streaming copies for the levels where bandwidth (not latency) matters
+      if (L.level_id == 0) build_sell(ctx, L.A, L.sA);
+      build_sell(ctx, L.Aout, L.sAout);
+      build_sell(ctx, L.P, L.sP);
+    }
     DCsr AP, Ac;
     spgemm(ctx, L.A, L.P, AP);
     spgemm(ctx, L.R, AP, Ac);
@@ -215,18 +220,21 @@ void Solver::vcycle(int lev, const double* b_src, const int* gather, double* x_d
   const double* b_eff = gather ? L.b.get() : b_src;
   // pre: x = w b/d, nu1 sweeps, r = b - A_in x - d x  (one kernel, matrix slab read once)
   launch_smooth(ctx, L, b_src, gather, gather ? L.b.get() : nullptr, nullptr, w, prm.preInnerIters, L.x, nullptr, nullptr, L.r, done);
-  launch_spmv(ctx, L.Aout, L.x, L.r, 3, nullptr, done, "residual_out");   // r -= A_out x   (preAout_kernel)
+  if (L.sAout.ready()) launch_spmv_sell(ctx, L.sAout, L.x, L.r, 3, nullptr, done, "residual_out");
+  else launch_spmv(ctx, L.Aout, L.x, L.r, 3, nullptr, done, "residual_out");   // r -= A_out x   (preAout_kernel)
   launch_spmv(ctx, L.R, L.r, L.bc, 0, nullptr, done, "restrict");         // bc = R r
   const bool next_is_coarsest = (lev + 1 == (int)levels.size() - 1);
   const int* ip = next_is_coarsest ? nullptr : levels[lev + 1].agg.ipermutation.get();
   vcycle(lev + 1, L.bc, ip, L.xc, ip, nullptr);
   profiler.cur_level = lev;
-  launch_spmv(ctx, L.P, L.xc, L.x, 2, nullptr, done, "prolong_add");      // x += P xc
+  if (L.sP.ready()) launch_spmv_sell(ctx, L.sP, L.xc, L.x, 2, nullptr, done, "prolong_add");
+  else launch_spmv(ctx, L.P, L.xc, L.x, 2, nullptr, done, "prolong_add");      // x += P xc
   double* xin = L.x;
   double* xtmp = L.x2;
   for (int rel = 0; rel < prm.postRelaxes; rel++) {
     bool lastpass = (rel == prm.postRelaxes - 1);
-    launch_spmv(ctx, L.Aout, xin, L.r, 1, b_eff, done, "bprime");         // b' = b - A_out x (x frozen for this pass)
+    if (L.sAout.ready()) launch_spmv_sell(ctx, L.sAout, xin, L.r, 1, b_eff, done, "bprime");
+    else launch_spmv(ctx, L.Aout, xin, L.r, 1, b_eff, done, "bprime");         // b' = b - A_out x (x frozen for this pass)
     if (lastpass) launch_smooth(ctx, L, L.r, nullptr, nullptr, xin, w, prm.postInnerIters, scatter ? nullptr : x_dst, scatter, scatter ? x_dst : nullptr, nullptr, done);
     else { launch_smooth(ctx, L, L.r, nullptr, nullptr, xin, w, prm.postInnerIters, xtmp, nullptr, nullptr, nullptr, done); std::swap(xin, xtmp); }
   }
@@ -248,7 +256,8 @@ void Solver::precondition(const double* r, double* z) {
 void Solver::enqueue_pcg_iteration() {
   const int n = levels[0].n;
   PcgScalars* sc = scal.get();
-  launch_spmv_dot(ctx, levels[0].A, cg_p, cg_y, partials, sc);               // y = A p, alpha = rz / (p.y)
+  if (levels[0].sA.ready()) launch_spmv_dot_sell(ctx, levels[0].sA, cg_p, cg_y, partials, sc);
+  else launch_spmv_dot(ctx, levels[0].A, cg_p, cg_y, partials, sc);          // y = A p, alpha = rz / (p.y)
   launch_cg_update(ctx, n, cg_x, cg_r, cg_p, cg_y, partials, sc, hist);      // x += alpha p, r -= alpha y, ||r||, test
   vcycle(0, cg_r, nullptr, cg_z, nullptr, nullptr);                          // z = M^-1 r
   launch_dot(ctx, n, cg_r, cg_z, partials, sc, 2);                           // rz_new, beta
@@ -282,7 +291,8 @@ void Solver::pcg(const double* b_user, double* x_user) {
     cg_b.from_device(b_user, n); cg_x.from_device(x_user, n);
   }
   launch_dot(ctx, n, cg_b, cg_b, partials, sc, 0);                 // bnorm
-  launch_spmv(ctx, L0.A, cg_x, cg_r, 1, cg_b, nullptr, "residual"); // r = b - A x
+  if (L0.sA.ready()) launch_spmv_sell(ctx, L0.sA, cg_x, cg_r, 1, cg_b, nullptr, "residual");
+  else launch_spmv(ctx, L0.A, cg_x, cg_r, 1, cg_b, nullptr, "residual"); // r = b - A x
   vcycle(0, cg_r, nullptr, cg_z, nullptr, nullptr);                // z = M^-1 r
   launch_cg_pdir(ctx, n, cg_p, cg_z, sc, 1);                       // p = z
   launch_dot(ctx, n, cg_r, cg_z, partials, sc, 1);                 // rz_old

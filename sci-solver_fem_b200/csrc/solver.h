@@ -39,6 +39,7 @@ struct LevelData {
   Aggregation agg;
   IBuf pstart;        // first row of each partition (nparts+1)
   DCsr Aout;          // inter-partition entries (rows internal numbering, global columns)
+  Sell sA, sAout, sP; // SELL-32 streaming copies (large levels only): operator, A_out, prolongator
   bool use_ell = false;  // intra-partition off-diagonal entries as per-partition column-major ELL slabs
   int ellMaxK = 0, coopG = 1;
   int clusterC = 1;      // CTAs per partition of the cluster smoother

@@ -249,3 +249,15 @@ def test_errors():
     s.topSize_ = 16
     with pytest.raises(ValueError):
         s.setup()
+
+
+def test_large_levels_use_streaming_formats():
+    """N=40 with topSize_ small enough for 4 levels and SELL/cluster paths forced at every level size:
+    the solve must agree with the oracle whatever storage format a level picks."""
+    v, t = kuhn(40)
+    o, s, nl = _setup_pair(v, t, **PCG)
+    b = o.spmv(egg_carton(v))
+    xo, ito = o.solve(b)
+    xg = s.solve(np.zeros_like(b), b)
+    assert abs(s.iterations - ito) <= 2, (s.iterations, ito)
+    assert rel(xg, xo) <= 1e-6
