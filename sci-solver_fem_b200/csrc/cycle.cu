@@ -222,29 +222,30 @@ void sell_dispatch(const Ctx& c, const Sell& A, const double* x, double* y, cons
 // coalesced and go straight into registers; the nu sweeps + the residual pass then touch HBM no
 // more: x lives double-buffered in shared memory.  Threads beyond the partition's rows exit.
 template <int MAXK, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, (BLOCK <= 512 && MAXK <= 16) ? 2 : 1)
-smooth_ell_kernel(const int* __restrict__ pstart, const long long* __restrict__ ellptr, const int* __restrict__ ellK,
-                  const double* __restrict__ ellval, const unsigned short* __restrict__ ellcol, const double* __restrict__ diag,
-                  const double* __restrict__ b_src, const int* __restrict__ gather, double* __restrict__ b_int,
-                  const double* __restrict__ x_in, double w, int nsweeps, double* __restrict__ x_out,
+__global__ void __launch_bounds__(BLOCK, (MAXK <= 16) ? (1024 / BLOCK) : (MAXK <= 24 ? 512 / BLOCK : 1))
+smooth_ell_kernel(const int* __restrict__ plist, const int* __restrict__ pstart, const long long* __restrict__ ellptr,
+                  const int* __restrict__ ellK, const double* __restrict__ ellval, const unsigned short* __restrict__ ellcol,
+                  const double* __restrict__ diag, const double* __restrict__ b_src, const int* __restrict__ gather,
+                  double* __restrict__ b_int, const double* __restrict__ x_in, double w, int nsweeps, double* __restrict__ x_out,
                   const int* __restrict__ scatter, double* __restrict__ x_ext, double* __restrict__ r_out,
                   const int* __restrict__ done) {
   __shared__ double sx[2][BLOCK];
   if (done && *done) return;
-  const int r0 = pstart[blockIdx.x], np = pstart[blockIdx.x + 1] - r0, t = threadIdx.x, row = r0 + t;
+  const int p = plist ? plist[blockIdx.x] : blockIdx.x;
+  const int r0 = pstart[p], np = pstart[p + 1] - r0, t = threadIdx.x, row = r0 + t;
   if (t >= np) return;  // exited threads do not take part in the barriers below
-  const int K = ellK[blockIdx.x];
-  const double* ev = ellval + ellptr[blockIdx.x] + t;
-  const unsigned short* ec = ellcol + ellptr[blockIdx.x] + t;
+  const int K = ellK[p];
+  const double* ev = ellval + ellptr[p] + t;
+  const unsigned short* ec = ellcol + ellptr[p] + t;
   double v[MAXK];
-  unsigned cpk[MAXK / 2];  // two 16-bit local columns per register
+  unsigned cpk[MAXK / 2];  // two 16-bit byte offsets into the x tile per register
 #pragma unroll
   for (int k = 0; k < MAXK; k += 2) {
     unsigned c0 = t, c1 = t;
     v[k] = 0.0; v[k + 1] = 0.0;
     if (k < K) { v[k] = ev[(size_t)k * np]; c0 = ec[(size_t)k * np]; }
     if (k + 1 < K) { v[k + 1] = ev[(size_t)(k + 1) * np]; c1 = ec[(size_t)(k + 1) * np]; }
-    cpk[k >> 1] = (c0 << 3) | (c1 << 19);  // byte offsets into the x tile
+    cpk[k >> 1] = (c0 << 3) | (c1 << 19);
   }
   const double b = b_src[gather ? gather[row] : row];
   const double d = diag[row];
@@ -255,37 +256,28 @@ smooth_ell_kernel(const int* __restrict__ pstart, const long long* __restrict__ 
   const int nbar = (np + 31) & ~31;
   asm volatile("bar.sync 1, %0;" ::"r"(nbar));
   int cur = 0;
-  for (int it = 0; it < nsweeps; it++) {
+  const int npasses = nsweeps + (r_out ? 1 : 0);
+  for (int it = 0; it < npasses; it++) {
     const char* xs = reinterpret_cast<const char*>(sx[cur]);
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;  // four independent FMA chains (fixed order)
+    double s0 = 0.0, s1 = 0.0;  // two independent FMA chains (fixed order)
 #pragma unroll
-    for (int k = 0; k < MAXK; k += 4) {
+    for (int k = 0; k < MAXK; k += 2) {
       s0 += v[k] * *reinterpret_cast<const double*>(xs + (cpk[k >> 1] & 0xffffu));
       s1 += v[k + 1] * *reinterpret_cast<const double*>(xs + (cpk[k >> 1] >> 16));
-      s2 += v[k + 2] * *reinterpret_cast<const double*>(xs + (cpk[(k >> 1) + 1] & 0xffffu));
-      s3 += v[k + 3] * *reinterpret_cast<const double*>(xs + (cpk[(k >> 1) + 1] >> 16));
     }
-    const double s = (s0 + s1) + (s2 + s3);
+    const double s = s0 + s1;
     const double xv = sx[cur][t];
-    sx[cur ^ 1][t] = xv + wd * (b - s - d * xv);
-    asm volatile("bar.sync 1, %0;" ::"r"(nbar));
-    cur ^= 1;
+    if (it < nsweeps) {
+      sx[cur ^ 1][t] = xv + wd * (b - s - d * xv);
+      asm volatile("bar.sync 1, %0;" ::"r"(nbar));
+      cur ^= 1;
+    } else {
+      r_out[row] = b - s - d * xv;  // in-partition residual b - A_in x - d x (gauss_seidel.cu:1352-1375)
+    }
   }
   const double xv = sx[cur][t];
   if (x_out) x_out[row] = xv;
   if (scatter) x_ext[scatter[row]] = xv;
-  if (r_out) {  // in-partition residual b - A_in x - d x (gauss_seidel.cu:1352-1375)
-    const char* xs = reinterpret_cast<const char*>(sx[cur]);
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-    for (int k = 0; k < MAXK; k += 4) {
-      s0 += v[k] * *reinterpret_cast<const double*>(xs + (cpk[k >> 1] & 0xffffu));
-      s1 += v[k + 1] * *reinterpret_cast<const double*>(xs + (cpk[k >> 1] >> 16));
-      s2 += v[k + 2] * *reinterpret_cast<const double*>(xs + (cpk[(k >> 1) + 1] & 0xffffu));
-      s3 += v[k + 3] * *reinterpret_cast<const double*>(xs + (cpk[(k >> 1) + 1] >> 16));
-    }
-    r_out[row] = b - ((s0 + s1) + (s2 + s3)) - d * xv;
-  }
 }
 
 // (b) cooperative CSR kernel (coarse levels: long rows, few partitions).  G lanes share a row,
@@ -422,7 +414,14 @@ __global__ void __launch_bounds__(BLOCK) smooth_cluster_kernel(int C, int G, int
       double s = 0.0;
       if (t < mn) {
         const int qb = srp[t + 1];
-        for (int q = srp[t] + lane; q < qb; q += G) s += sval[q] * xc[scol[q]];
+        int q = srp[t] + lane;
+        double s1 = 0.0;
+        for (; q + G < qb; q += 2 * G) {  // two independent chains per lane
+          s += sval[q] * xc[scol[q]];
+          s1 += sval[q + G] * xc[scol[q + G]];
+        }
+        if (q < qb) s += sval[q] * xc[scol[q]];
+        s += s1;
       }
       for (int o = G >> 1; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, G);
       if (t < mn && lane == 0) {
@@ -440,7 +439,14 @@ __global__ void __launch_bounds__(BLOCK) smooth_cluster_kernel(int C, int G, int
       double s = 0.0;
       if (t < mn) {
         const int qb = srp[t + 1];
-        for (int q = srp[t] + lane; q < qb; q += G) s += sval[q] * xc[scol[q]];
+        int q = srp[t] + lane;
+        double s1 = 0.0;
+        for (; q + G < qb; q += 2 * G) {  // two independent chains per lane
+          s += sval[q] * xc[scol[q]];
+          s1 += sval[q + G] * xc[scol[q + G]];
+        }
+        if (q < qb) s += sval[q] * xc[scol[q]];
+        s += s1;
       }
       for (int o = G >> 1; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, G);
       if (t < mn && lane == 0) r_out[r0 + m0 + t] = sb[t] - s - sd[t] * xc[m0 + t];
@@ -586,11 +592,20 @@ void launch_smooth(const Ctx& c, const LevelData& L, const double* b_src, const 
   g_launch_counter++;
   ProfScope ps(c, x_in ? "post_smooth" : "pre_smooth");
   cudaStream_t s = c.stream;
-  const int threads = std::max(32, (L.maxPartRows + 31) & ~31);
-#define FSB_ELL_ARGS L.pstart, L.ellptr, L.ellK, L.ellval, L.ellcol, L.diag, b_src, gather, b_int, x_in, w, nsweeps, x_out, scatter, x_ext, r_out, done
-  if (L.use_ell && L.ellMaxK <= 16 && L.maxPartRows <= 512) smooth_ell_kernel<16, 512><<<L.nparts, threads, 0, s>>>(FSB_ELL_ARGS);
-  else if (L.use_ell && L.ellMaxK <= 16) smooth_ell_kernel<16, 1024><<<L.nparts, threads, 0, s>>>(FSB_ELL_ARGS);
-  else if (L.use_ell && L.ellMaxK <= 32 && L.maxPartRows <= 512) smooth_ell_kernel<32, 512><<<L.nparts, threads, 0, s>>>(FSB_ELL_ARGS);
+#define FSB_ELL_ARGS(pl) pl, L.pstart, L.ellptr, L.ellK, L.ellval, L.ellcol, L.diag, b_src, gather, b_int, x_in, w, nsweeps, x_out, scatter, x_ext, r_out, done
+#define FSB_ELL_LAUNCH(MK)                                                                                                  \
+  do {                                                                                                                     \
+    if (L.nSmall > 0) smooth_ell_kernel<MK, 256><<<L.nSmall, 256, 0, s>>>(FSB_ELL_ARGS(L.plistSmall.get()));               \
+    if (L.nBig > 0 && L.maxPartRows <= 512) smooth_ell_kernel<MK, 512><<<L.nBig, 512, 0, s>>>(FSB_ELL_ARGS(L.plistBig.get())); \
+    else if (L.nBig > 0) smooth_ell_kernel<MK, 1024><<<L.nBig, (L.maxPartRows + 31) & ~31, 0, s>>>(FSB_ELL_ARGS(L.plistBig.get())); \
+    if (L.nSmall > 0 && L.nBig > 0) g_launch_counter++;                                                                    \
+  } while (0)
+  if (L.use_ell && L.ellMaxK <= 8) FSB_ELL_LAUNCH(8);
+  else if (L.use_ell && L.ellMaxK <= 16) FSB_ELL_LAUNCH(16);
+  else if (L.use_ell && L.ellMaxK <= 24 && L.maxPartRows <= 512) FSB_ELL_LAUNCH(24);
+  else if (L.use_ell && L.ellMaxK <= 32 && L.maxPartRows <= 512) FSB_ELL_LAUNCH(32);
+#undef FSB_ELL_LAUNCH
+#undef FSB_ELL_ARGS
   else if (L.smemBytes > 0) {
     static bool attr_set = false;
     if (!attr_set) {

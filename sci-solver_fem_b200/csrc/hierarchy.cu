@@ -382,8 +382,9 @@ void split_partitions(const Ctx& c, LevelData& L) {
   fill_out_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, L.A.ptr, L.A.col, L.A.val, rowPart, L.pstart, L.Aout.ptr, L.Aout.col, L.Aout.val);
   L.ellMaxK = reduce_max_i32(partK, np, s);
   double avg = (double)L.A.nnz / std::max(1, n);
-  L.coopG = avg > 48 ? 32 : avg > 24 ? 16 : avg > 12 ? 8 : avg > 6 ? 4 : 2;
+  L.coopG = avg > 192 ? 32 : avg > 96 ? 16 : avg > 48 ? 8 : avg > 16 ? 4 : 2;
   L.use_ell = (L.ellMaxK <= 16) || (L.ellMaxK <= 32 && L.maxPartRows <= 512);
+  L.nSmall = L.nBig = 0;
   L.smemBytes = 0;
   if (!L.use_ell) {
     // smallest cluster size whose per-CTA slice fits comfortably (two CTAs per SM), else the
@@ -416,6 +417,14 @@ void split_partitions(const Ctx& c, LevelData& L) {
     L.ellval.alloc((size_t)std::max<long long>(total, 1), s);
     L.ellcol.alloc((size_t)std::max<long long>(total, 1), s);
     fill_ell_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, L.A.ptr, L.A.col, L.A.val, rowPart, L.pstart, L.ellK, L.ellptr, L.ellval, L.ellcol);
+    // partition lists by size class (host side: nparts is a few thousand)
+    std::vector<int> ps = L.pstart.to_vector(), small, big;
+    for (int p = 0; p < np; p++) ((ps[p + 1] - ps[p] <= 256) ? small : big).push_back(p);
+    L.nSmall = (int)small.size(); L.nBig = (int)big.size();
+    L.plistSmall.alloc(std::max<size_t>(1, small.size()), s); L.plistBig.alloc(std::max<size_t>(1, big.size()), s);
+    if (!small.empty()) L.plistSmall.from_host(small.data(), small.size());
+    if (!big.empty()) L.plistBig.from_host(big.data(), big.size());
+    FSB_CUDA(cudaStreamSynchronize(s));
   }
   FSB_CHECK_LAUNCH();
 }

@@ -303,19 +303,16 @@ void Solver::pcg(const double* b_user, double* x_user) {
   if (!graphs) destroy_graph();
   if (graphs && !iter_graph_) {
     cudaGraph_t g;
+    long long before = g_launch_counter;
     FSB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
     enqueue_pcg_iteration();
     FSB_CUDA(cudaStreamEndCapture(s, &g));
     FSB_CUDA(cudaGraphInstantiate(&iter_graph_, g, 0));
     FSB_CUDA(cudaGraphDestroy(g));
+    iter_launches_ = g_launch_counter - before;  // kernels of one iteration (counted while capturing)
+    g_launch_counter = before;
   }
-  long long per_iter = 0;
-  {
-    long long before = g_launch_counter;
-    // count the kernels of one iteration without launching: known structure
-    per_iter = 4 + 1 + (long long)(levels.size() - 1) * (4 + 2 * std::max(prm.postRelaxes, 1));
-    (void)before;
-  }
+  const long long per_iter = iter_launches_;
   PcgScalars h;
   int enq = 0;
   const int chunk = std::max(1, prm.checkEvery);

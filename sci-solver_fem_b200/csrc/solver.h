@@ -46,6 +46,8 @@ struct LevelData {
   int maxChunkNnz = 0;   // largest number of CSR entries of one CTA's row chunk
   int maxChunkRows = 0;
   int smemBytes = 0;     // > 0: the cluster smoother is usable (chunk fits in shared memory)
+  IBuf plistSmall, plistBig;  // partitions with <= 256 rows / more: two CTA sizes keep occupancy up
+  int nSmall = 0, nBig = 0;
   DevBuf<long long> ellptr;  // nparts+1 slab offsets (entries)
   IBuf ellK;                 // slab width of each partition
   DBuf ellval;
@@ -110,6 +112,7 @@ class Solver {
   struct GraphKey { void* p[9]; int pre, post, relaxes; double w; };
   GraphKey graph_key_ = {};
   bool cg_active_ = false;
+  long long iter_launches_ = 0;
   void destroy_graph();
 };
 
