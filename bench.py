@@ -18,8 +18,9 @@ tolerance_=1e-8, maxIters_=200.  One STEP = one complete PCG solve from the init
                 on this box's host cores, same workload, one full solve
 
 `--impl reference` times that CPU oracle alone (all host threads) and prints the same line shape.
-Under torchrun (N > 1) every rank solves its own cube (replicas; the sharded solve is DESIGN.md's
-next row) and the line reports the aggregate.
+Under torchrun (N > 1) the SAME cube is solved by all N GPUs together (strong scaling): setup is
+replicated on every GPU, the fine level of the solve is sharded in contiguous partition ranges, halo
+values and dot products travel over NVLink peer memory.
 """
 from __future__ import annotations
 
@@ -165,7 +166,7 @@ def reference_arm(args):
     value = r["n"] / r["t_solve"]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": r["t_solve"] * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": r["t_solve"] * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(N), "iterations": r["iters"], "relres": r["relres"], "rel_l2_err_vs_exact": r["err"],
                    "setup_s": r["t_setup"], "assemble_s": r["t_assemble"], "pattern_s": r["t_pattern"]},
@@ -206,17 +207,21 @@ def ours(args):
     levels = [(s.level_rows(l), s.level_nnz(l)) for l in range(s.num_levels())]
     log(f"[rank {rank}] n={n} nnz={nnz} levels={levels} pattern {t_pattern:.1f} ms assemble {t_assemble:.1f} ms setup {t_setup:.1f} ms")
 
-    # b = A x* on the host (outside every timed region)
-    import scipy.sparse as sp
-    ptr, col, val = s.matrix_csr()
-    A = sp.csr_matrix((val, col, ptr), shape=(n, n))
-    b_host = torch.from_numpy(A @ xstar).pin_memory()
+    # b = A x* on the device (outside every timed region)
+    xs_dev = torch.from_numpy(xstar).cuda()
+    b_dev = torch.empty(n, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    s.apply_matrix_device(xs_dev.data_ptr(), b_dev.data_ptr())
+    b_host = b_dev.cpu().pin_memory()
     x_host = torch.zeros(n, dtype=torch.float64).pin_memory()
-    del A, ptr, col, val
-    b_dev = b_host.cuda()
     x_dev = torch.zeros(n, dtype=torch.float64, device="cuda")
     stream = torch.cuda.ExternalStream(s._L.fsb_stream(s.handle))
     torch.cuda.synchronize()
+    if world > 1:
+        s.dist_connect(rank, world, fsb.exchange_handles_torch)
+        pb, rb, ab = s.dist_ranges()
+        log(f"[rank {rank}] owns partitions [{pb[rank]},{pb[rank+1]}) rows [{rb[rank]},{rb[rank+1]})")
+        dist.barrier()
 
     def barrier():
         if world > 1:
@@ -261,8 +266,11 @@ def ours(args):
     xg = x_dev.cpu().numpy()
     err = float(np.linalg.norm(xg - xstar) / np.linalg.norm(xstar))
     ms_e2e, wall_e2e = timed(solve_host, max(1, args.steps), min(args.warmup, 3))
-    # solveFEM-equivalent (hierarchy rebuilt + solve, host buffers), for the record
-    t0 = time.perf_counter(); x_host.zero_(); s.solveFEM(x_host.numpy(), b_host.numpy()); t_solvefem = time.perf_counter() - t0
+    # solveFEM-equivalent (hierarchy rebuilt + solve, host buffers), for the record (single GPU only:
+    # a rebuild ends the sharded mode)
+    t_solvefem = float("nan")
+    if world == 1:
+        t0 = time.perf_counter(); x_host.zero_(); s.solveFEM(x_host.numpy(), b_host.numpy()); t_solvefem = time.perf_counter() - t0
 
     # roofline pass: one profiled solve (CUDA events around every kernel; graphs off)
     s.profile_ = 1
@@ -291,7 +299,7 @@ def ours(args):
             fine[k] = {"us": round(ms / c * 1e3, 2), "GBps": round(gbs, 1), "frac_of_peak": round(gbs / peak, 4)}
 
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             r = run_oracle(N, 1, 0)
             cpu = {"value": r["n"] / r["t_solve"], "unit": UNIT, "cores": r["threads"], "kind": "port",
@@ -303,14 +311,14 @@ def ours(args):
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": world * n / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(N), "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one cube per GPU)",
+            "metric": METRIC, "value": n / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(N), "parallelism": "single GPU" if world == 1 else f"{world} GPUs: replicated setup, fine level sharded in contiguous partition ranges, NVLink peer-memory halo pushes + in-kernel all-reduce",
                        "l2_policy": "inputs larger than L2 (hierarchy + vectors ~%.0f MB per solve pass)" % ((12 * nnz + 40 * n) / 1e6),
                        "iterations": iters, "relres": relres, "rel_l2_err_vs_exact": err, "levels": levels,
-                       "pattern_ms": t_pattern, "assemble_ms": t_assemble, "setup_ms": t_setup, "solveFEM_host_ms": t_solvefem * 1e3,
+                       "pattern_ms": t_pattern, "assemble_ms": t_assemble, "setup_ms": t_setup, "solveFEM_host_ms": None if t_solvefem != t_solvefem else t_solvefem * 1e3,
                        "wall_ms_per_step": wall_dev},
-            "e2e": {"value": world * n / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 8 * n,
+            "e2e": {"value": n / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 8 * n,
                     "ms_per_step": ms_e2e, "call": "fsb_solve (host b/x0 in pinned memory -> x)"},
             "gpu_launches": int(launches) * args.steps,
             "roofline": {"bound": "hbm", "kernel": f"{kname}@level{klev}", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -88,7 +88,28 @@ int fsb_resid_history(const fsb_solver* s, double* buf, int cap);
 /* kernel-level hooks (device pointers, level-0 partition-contiguous numbering) for parity tests and
  * micro-benchmarks: y = A x on the permuted fine operator; z = one V-cycle applied to r. */
 int fsb_spmv_fine_device(fsb_solver* s, const double* x_dev, double* y_dev);
+/* y = A x with the assembled (user-ordered) matrix, device pointers: builds right-hand sides without
+ * moving the matrix to the host */
+int fsb_apply_matrix_device(fsb_solver* s, const double* x_dev, double* y_dev);
 int fsb_precondition_device(fsb_solver* s, const double* r_dev, double* z_dev);
+
+/* stage 4 — sharded solve over the GPUs of one box (absent upstream; one process per GPU).
+ * Every process builds the same mesh and calls fsb_setup (replicated, deterministic); then
+ *   fsb_dist_prepare(rank, nranks)  splits the fine level into contiguous nnz-balanced partition ranges,
+ *                                   builds the halo send lists and allocates the exchange arena;
+ *   fsb_dist_handle                 returns the 64-byte CUDA IPC handle of that arena (all-gather it, e.g.
+ *                                   with torch.distributed / MPI);
+ *   fsb_dist_connect(handles)       maps the peers' arenas (nranks x 64 bytes, rank order).
+ * After that fsb_solve / fsb_solve_device with solverType = 1 run sharded; all processes must call them
+ * together.  fsb_setup or fsb_dist_disconnect ends the sharded mode. */
+int fsb_dist_prepare(fsb_solver* s, int rank, int nranks);
+int fsb_dist_handle(fsb_solver* s, void* handle64, long long* arena_bytes);
+int fsb_dist_connect(fsb_solver* s, const void* handles);
+int fsb_dist_disconnect(fsb_solver* s);
+/* first partition / first fine row / first coarse row of every rank (nranks+1 entries each); returns nranks */
+int fsb_dist_ranges(const fsb_solver* s, int* part_begin, int* row_begin, int* coarse_begin);
+/* host-only helper: contiguous split of weighted partitions over nranks (out_begin has nranks+1 entries) */
+void fsb_split_by_weight(int nparts, const long long* weights, int nranks, int* out_begin);
 
 /* measurements of the last calls, milliseconds, CUDA events on the solver's stream:
  * "pattern", "assemble", "setup", "solve" */

@@ -9,4 +9,5 @@ Contents: `femsolver` (FEMSolver mirror over the C-ABI of libfemsolver_b200.so),
 path: there is no CPU fallback and nothing here imports oracle/.
 """
 from . import meshio  # noqa: F401
-from .femsolver import EXPORTED_SYMBOLS, FEMSolver, FEMSolverError, load_library  # noqa: F401
+from .femsolver import (EXPORTED_SYMBOLS, FEMSolver, FEMSolverError, exchange_handles_torch, load_library,  # noqa: F401
+                        split_by_weight)

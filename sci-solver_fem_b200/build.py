@@ -28,8 +28,8 @@ SOURCES = {
     "hierarchy.cu": ["-fmad=false"],
     "cycle.cu": [],
     "solver.cu": [],
+    "dist.cu": [],
     "capi.cu": [],
-    "FEMSolver.cpp": [],
 }
 
 

@@ -5,6 +5,8 @@
 #include "../../include/femsolver_b200.h"
 #include "solver.h"
 
+namespace fsb { void split_by_weight(int nparts, const long long* w, int nranks, int* out); }
+
 struct fsb_solver {
   fsb::Solver* impl = nullptr;
 };
@@ -218,6 +220,9 @@ int fsb_resid_history(const fsb_solver* s, double* buf, int cap) {
   return n;
 }
 
+int fsb_apply_matrix_device(fsb_solver* s, const double* x, double* y) {
+  return guarded(s, [&](fsb::Solver& S) { S.apply_matrix(x, y); });
+}
 int fsb_spmv_fine_device(fsb_solver* s, const double* x, double* y) {
   return guarded(s, [&](fsb::Solver& S) { if (!S.has_setup) throw std::runtime_error("setup first"); S.spmv_fine(x, y); });
 }
@@ -240,6 +245,23 @@ int fsb_profile_report(fsb_solver* s, char* buf, int cap) {
   memcpy(buf, r.c_str(), r.size() + 1);
   return (int)r.size() + 1;
 }
+int fsb_dist_prepare(fsb_solver* s, int rank, int nranks) { return guarded(s, [&](fsb::Solver& S) { S.dist_prepare(rank, nranks); }); }
+int fsb_dist_handle(fsb_solver* s, void* handle64, long long* arena_bytes) {
+  return guarded(s, [&](fsb::Solver& S) { S.dist_get_handle(handle64, arena_bytes); });
+}
+int fsb_dist_connect(fsb_solver* s, const void* handles) { return guarded(s, [&](fsb::Solver& S) { S.dist_connect(handles); }); }
+int fsb_dist_disconnect(fsb_solver* s) { return guarded(s, [&](fsb::Solver& S) { S.dist_disconnect(); }); }
+int fsb_dist_ranges(const fsb_solver* s, int* part_begin, int* row_begin, int* coarse_begin) {
+  if (!s || !s->impl) return FSB_ERR_INVALID;
+  const auto& d = s->impl->dist;
+  for (int r = 0; r <= d.nranks; r++) {
+    if (part_begin) part_begin[r] = d.pbeg[r];
+    if (row_begin) row_begin[r] = d.rbeg[r];
+    if (coarse_begin) coarse_begin[r] = d.abeg[r];
+  }
+  return d.nranks;
+}
+void fsb_split_by_weight(int nparts, const long long* weights, int nranks, int* out_begin) { fsb::split_by_weight(nparts, weights, nranks, out_begin); }
 void* fsb_stream(const fsb_solver* s) { return (s && s->impl) ? (void*)s->impl->ctx.stream : nullptr; }
 
 void fsb_tet_mass_integrals(double out10[10]) { fsb::tet_mass_integrals_host(out10); }

@@ -29,6 +29,19 @@ struct CudaError : public std::runtime_error {
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Device-visible description of the GPU group of a sharded solve (one process per GPU; peers'
+// arenas are mapped through CUDA IPC and reached over NVLink).  nranks == 1: everything is local.
+constexpr int kMaxRanks = 8;
+struct DistDev {
+  int rank = 0, nranks = 1;
+  unsigned long long* my_flags = nullptr;             // [kMaxRanks] written by the peers
+  unsigned long long* peer_flags[kMaxRanks] = {};     // the same array in every peer's arena
+  double* my_red = nullptr;                           // [2][kMaxRanks] all-reduce slots (parity double-buffered)
+  double* peer_red[kMaxRanks] = {};
+  unsigned long long* epoch = nullptr;                // local exchange counter
+  int* error = nullptr;                               // set when a peer wait times out
+};
+
 // Optional per-launch timing (CUDA events around every solve-phase kernel; used by bench.py's
 // roofline pass, never inside a timed region).
 struct Profiler {
@@ -51,7 +64,12 @@ struct Ctx {
   int device = 0;
   int num_sms = 148;
   Profiler* prof = nullptr;
+  DistDev dist;                        // nranks == 1 unless a sharded solve is connected
+  unsigned int* dist_ticket = nullptr; // last-CTA ticket of the push kernels
 };
+
+struct RowRange { int begin = 0, end = -1; };  // end < 0: all rows
+struct PeerPtrs { double* p[kMaxRanks]; };
 
 struct ProfScope {
   Profiler* p; size_t idx; cudaStream_t s;
@@ -85,10 +103,12 @@ class DevBuf {
     if (n) FSB_CUDA(cudaMallocAsync((void**)&p_, n * sizeof(T), s));
   }
   void release() {
-    if (p_) cudaFreeAsync(p_, s_);
-    p_ = nullptr; n_ = 0;
+    if (p_ && !view_) cudaFreeAsync(p_, s_);
+    p_ = nullptr; n_ = 0; view_ = false;
   }
-  void swap(DevBuf& o) { std::swap(p_, o.p_); std::swap(n_, o.n_); std::swap(s_, o.s_); }
+  // non-owning view (multi-GPU: vectors that peers write live in one IPC-shared arena)
+  void view(T* p, size_t n, cudaStream_t s) { release(); p_ = p; n_ = n; s_ = s; view_ = true; }
+  void swap(DevBuf& o) { std::swap(p_, o.p_); std::swap(n_, o.n_); std::swap(s_, o.s_); std::swap(view_, o.view_); }
   T* get() const { return p_; }
   operator T*() const { return p_; }
   size_t size() const { return n_; }
@@ -107,6 +127,7 @@ class DevBuf {
   T* p_ = nullptr;
   size_t n_ = 0;
   cudaStream_t s_ = nullptr;
+  bool view_ = false;
 };
 
 typedef DevBuf<int> IBuf;

@@ -62,6 +62,89 @@ __device__ __forceinline__ double final_sum(const double* partials, int n, doubl
   return block_sum(v, s_warp);
 }
 
+// ------------------------------------------------------------------ cross-GPU exchange (NVLink peer memory)
+// One CTA per GPU meets its peers: thread q publishes to peer q (value first, system fence, then the
+// epoch flag) and waits for peer q's flag.  Epochs increase monotonically and every GPU executes the
+// same sequence of exchanges, so no reset is ever needed; a wait that exceeds ~30 s raises the error
+// flag instead of hanging the GPU.
+__device__ __forceinline__ void cross_signal_wait(const DistDev& d, unsigned long long ep) {
+  const int t = threadIdx.x;
+  if (t < d.nranks) {
+    __threadfence_system();
+    *(reinterpret_cast<volatile unsigned long long*>(d.peer_flags[t]) + d.rank) = ep;
+    volatile unsigned long long* f = reinterpret_cast<volatile unsigned long long*>(d.my_flags) + t;
+    const long long t0 = clock64();
+    while (*f < ep) {
+      if (clock64() - t0 > 60000000000ll) { *d.error = 1; break; }  // ~30 s: never hang the GPU
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+}
+
+// all-reduce(sum) of one double per GPU, executed by the last CTA of a reduction kernel: every GPU
+// adds the contributions in rank order, so the result is bit-identical everywhere.
+__device__ __forceinline__ double cross_sum(const DistDev& d, double local) {
+  if (d.nranks == 1) return local;  // uniform
+  __shared__ double s_val;
+  __shared__ unsigned long long s_ep;
+  if (threadIdx.x == 0) { s_val = local; s_ep = ++(*d.epoch); }
+  __syncthreads();
+  const unsigned long long ep = s_ep;
+  const int par = (int)(ep & 1ull) * kMaxRanks;
+  if (threadIdx.x < d.nranks) *(reinterpret_cast<volatile double*>(d.peer_red[threadIdx.x]) + par + d.rank) = s_val;
+  cross_signal_wait(d, ep);
+  double tot = 0.0;
+  if (threadIdx.x == 0) for (int q = 0; q < d.nranks; q++) tot += *(reinterpret_cast<volatile double*>(d.my_red) + par + q);
+  return tot;
+}
+
+// pushes owned boundary values into the peers' copies of a vector: entry k of `list` goes to the peer
+// whose segment of list_ptr contains k.  The last CTA closes the exchange with a cross-GPU barrier.
+__global__ void __launch_bounds__(256) halo_push_kernel(DistDev d, int total, const int* __restrict__ list, const int* __restrict__ list_ptr,
+                                                        const double* __restrict__ src, PeerPtrs dst, unsigned int* ticket,
+                                                        const int* __restrict__ done) {
+  __shared__ int s_last;
+  if (done && *done) return;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
+    int q = 0;
+    while (k >= list_ptr[q + 1]) q++;
+    const int j = list[k];
+    dst.p[q][j] = src[j];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {
+    __shared__ unsigned long long s_ep;
+    if (threadIdx.x == 0) s_ep = ++(*d.epoch);
+    __syncthreads();
+    cross_signal_wait(d, s_ep);
+  }
+}
+
+// all-gather by peer stores: the owned slice [begin, end) of a vector is written into every peer's copy
+__global__ void __launch_bounds__(256) push_all_kernel(DistDev d, int begin, int end, const double* __restrict__ src, PeerPtrs dst,
+                                                       unsigned int* ticket, const int* __restrict__ done) {
+  __shared__ int s_last;
+  if (done && *done) return;
+  for (int j = begin + blockIdx.x * blockDim.x + threadIdx.x; j < end; j += gridDim.x * blockDim.x) {
+    const double v = src[j];
+    for (int q = 0; q < d.nranks; q++) if (q != d.rank) dst.p[q][j] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {
+    __shared__ unsigned long long s_ep;
+    if (threadIdx.x == 0) s_ep = ++(*d.epoch);
+    __syncthreads();
+    cross_signal_wait(d, s_ep);
+  }
+}
+
 // ------------------------------------------------------------------ SpMV family (CSR-stream)
 // A CTA owns SPMV_ROWS consecutive rows.  Their entries are contiguous in CSR, so the CTA streams
 // them with fully coalesced, deeply unrolled loads (every thread keeps several independent
@@ -140,20 +223,23 @@ __global__ void __launch_bounds__(SPMV_ROWS) csr_stream_kernel(int n, const int*
 }
 
 template <int MODE>
-__global__ void spmv_vector_kernel(int n, const int* __restrict__ ptr, const int* __restrict__ col, const double* __restrict__ val,
+__global__ void spmv_vector_kernel(int row_begin, int n, const int* __restrict__ ptr, const int* __restrict__ col, const double* __restrict__ val,
                                    const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ b,
                                    const int* __restrict__ done);
 
 template <int MODE, bool DOT>
 void spmv_dispatch(const Ctx& c, const DCsr& A, const double* x, double* y, const double* b, double* partials, PcgScalars* sc,
-                   const int* done, const char* name) {
+                   const int* done, const char* name, RowRange rr = RowRange()) {
   int n = A.nrows;
   if (n == 0) return;
   g_launch_counter++;
   ProfScope ps(c, name);
-  if (!DOT && ((double)A.nnz > 32.0 * n || n < 32768))  // long rows or a small operator: one warp per row
-    spmv_vector_kernel<MODE><<<cdiv((long long)n * 32, 256), 256, 0, c.stream>>>(n, A.ptr, A.col, A.val, x, y, b, done);
-  else
+  const bool ranged = rr.end >= 0;
+  if (ranged && DOT) throw std::runtime_error("row-ranged CSR dot is not implemented (use the SELL copy)");
+  if (!DOT && (ranged || (double)A.nnz > 32.0 * n || n < 32768)) {  // long rows, a small operator or a row range: one warp per row
+    const int r0 = ranged ? rr.begin : 0, r1 = ranged ? rr.end : n;
+    if (r1 > r0) spmv_vector_kernel<MODE><<<cdiv((long long)(r1 - r0) * 32, 256), 256, 0, c.stream>>>(r0, r1, A.ptr, A.col, A.val, x, y, b, done);
+  } else
     csr_stream_kernel<MODE, DOT><<<cdiv(n, SPMV_ROWS), SPMV_ROWS, 0, c.stream>>>(n, A.ptr, A.col, A.val, x, y, b, partials, sc, done);
   FSB_CHECK_LAUNCH();
 }
@@ -162,15 +248,15 @@ void spmv_dispatch(const Ctx& c, const DCsr& A, const double* x, double* y, cons
 // request per warp for col and one for val; four steps are kept in flight together with their x
 // gathers.  The row sum runs in column order (same rounding sequence as a sequential CSR loop).
 template <int MODE, bool DOT>
-__global__ void __launch_bounds__(256) sell_spmv_kernel(int n, const long long* __restrict__ sptr, const int* __restrict__ col,
-                                                        const double* __restrict__ val, const double* __restrict__ x,
-                                                        double* __restrict__ y, const double* __restrict__ b,
+__global__ void __launch_bounds__(256) sell_spmv_kernel(DistDev dist, int row_begin, int row_end, int n, const long long* __restrict__ sptr,
+                                                        const int* __restrict__ col, const double* __restrict__ val,
+                                                        const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ b,
                                                         double* __restrict__ partials, PcgScalars* __restrict__ sc,
                                                         const int* __restrict__ done) {
   __shared__ double s_warp[32];
   __shared__ int s_flag;
   if (done && *done) return;
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = (row_begin & ~31) + blockIdx.x * blockDim.x + threadIdx.x;  // owned rows [row_begin, row_end)
   const int slice = row >> 5, lane = threadIdx.x & 31;
   const int nslices = (n + 31) >> 5;
   double acc = 0.0;
@@ -189,7 +275,7 @@ __global__ void __launch_bounds__(256) sell_spmv_kernel(int n, const long long* 
     for (; k < K; k++) acc += __ldg(vp + k * 32) * __ldg(x + __ldg(cp + k * 32));
   }
   double contrib = 0.0;
-  if (row < n) {
+  if (row >= row_begin && row < row_end) {
     if (MODE == 0) y[row] = acc;
     else if (MODE == 1) y[row] = b[row] - acc;
     else if (MODE == 2) y[row] = y[row] + acc;
@@ -200,6 +286,7 @@ __global__ void __launch_bounds__(256) sell_spmv_kernel(int n, const long long* 
     double bs = block_sum(contrib, s_warp);
     if (publish_partial(bs, partials, &sc->ticket[0], &s_flag)) {
       double tot = final_sum(partials, gridDim.x, s_warp);
+      tot = cross_sum(dist, tot);  // all-reduce over the GPUs of a sharded solve (no-op on one GPU)
       if (threadIdx.x == 0) { sc->py = tot; sc->alpha = sc->rz_old / tot; }
     }
   }
@@ -207,11 +294,14 @@ __global__ void __launch_bounds__(256) sell_spmv_kernel(int n, const long long* 
 
 template <int MODE, bool DOT>
 void sell_dispatch(const Ctx& c, const Sell& A, const double* x, double* y, const double* b, double* partials, PcgScalars* sc,
-                   const int* done, const char* name) {
+                   const int* done, const char* name, RowRange rr = RowRange()) {
   if (A.nrows == 0) return;
+  const int r0 = rr.end >= 0 ? rr.begin : 0, r1 = rr.end >= 0 ? rr.end : A.nrows;
   g_launch_counter++;
   ProfScope ps(c, name);
-  sell_spmv_kernel<MODE, DOT><<<cdiv(A.nrows, 256), 256, 0, c.stream>>>(A.nrows, A.sptr, A.col, A.val, x, y, b, partials, sc, done);
+  const int span = r1 - (r0 & ~31);
+  if (span <= 0) return;
+  sell_spmv_kernel<MODE, DOT><<<cdiv(span, 256), 256, 0, c.stream>>>(c.dist, r0, r1, A.nrows, A.sptr, A.col, A.val, x, y, b, partials, sc, done);
   FSB_CHECK_LAUNCH();
 }
 
@@ -461,11 +551,11 @@ __global__ void __launch_bounds__(BLOCK) smooth_cluster_kernel(int C, int G, int
 
 // warp-per-row SpMV for long rows (restriction operators, coarse operators)
 template <int MODE>
-__global__ void __launch_bounds__(256) spmv_vector_kernel(int n, const int* __restrict__ ptr, const int* __restrict__ col,
+__global__ void __launch_bounds__(256) spmv_vector_kernel(int row_begin, int n, const int* __restrict__ ptr, const int* __restrict__ col,
                                                           const double* __restrict__ val, const double* __restrict__ x,
                                                           double* __restrict__ y, const double* __restrict__ b, const int* __restrict__ done) {
   if (done && *done) return;
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int row = row_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (row >= n) return;
   double s = 0.0;
   const int e1 = ptr[row + 1];
@@ -499,7 +589,7 @@ __global__ void cg_init_kernel(PcgScalars* sc, double tol, int maxit) {
 }
 
 template <int WHICH>
-__global__ void __launch_bounds__(256) dot_kernel(int n, const double* __restrict__ a, const double* __restrict__ b,
+__global__ void __launch_bounds__(256) dot_kernel(DistDev dist, int n, const double* __restrict__ a, const double* __restrict__ b,
                                                   double* __restrict__ partials, PcgScalars* __restrict__ sc) {
   __shared__ double s_warp[32];
   __shared__ int s_flag;
@@ -509,6 +599,7 @@ __global__ void __launch_bounds__(256) dot_kernel(int n, const double* __restric
   double bs = block_sum(v, s_warp);
   if (publish_partial(bs, partials, &sc->ticket[1], &s_flag)) {
     double tot = final_sum(partials, gridDim.x, s_warp);
+    if (WHICH != 0) tot = cross_sum(dist, tot);  // bnorm is computed from the full (replicated) b on every GPU
     if (threadIdx.x == 0) {
       if (WHICH == 0) sc->bnorm = sqrt(tot);
       else if (WHICH == 1) sc->rz_old = tot;
@@ -518,7 +609,7 @@ __global__ void __launch_bounds__(256) dot_kernel(int n, const double* __restric
 }
 
 // x += alpha p ; r -= alpha y ; ||r||^2 ; convergence test and iteration count by the last CTA
-__global__ void __launch_bounds__(256) cg_update_kernel(int n, double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
+__global__ void __launch_bounds__(256) cg_update_kernel(DistDev dist, int n, double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
                                                         const double* __restrict__ y, double* __restrict__ partials,
                                                         PcgScalars* __restrict__ sc, double* __restrict__ hist) {
   __shared__ double s_warp[32];
@@ -535,6 +626,7 @@ __global__ void __launch_bounds__(256) cg_update_kernel(int n, double* __restric
   double bs = block_sum(v, s_warp);
   if (publish_partial(bs, partials, &sc->ticket[2], &s_flag)) {
     double tot = final_sum(partials, gridDim.x, s_warp);
+    tot = cross_sum(dist, tot);
     if (threadIdx.x == 0) {
       sc->rr = tot;
       double rel = sqrt(tot) / sc->bnorm;
@@ -566,21 +658,36 @@ inline int vec_blocks(const Ctx& c, int n) { return std::max(1, std::min(cdiv(n,
 
 }  // namespace
 
-void launch_spmv(const Ctx& c, const DCsr& A, const double* x, double* y, int mode, const double* b, const int* done, const char* name) {
-  if (mode == 0) spmv_dispatch<0, false>(c, A, x, y, b, nullptr, nullptr, done, name);
-  else if (mode == 1) spmv_dispatch<1, false>(c, A, x, y, b, nullptr, nullptr, done, name);
-  else if (mode == 2) spmv_dispatch<2, false>(c, A, x, y, b, nullptr, nullptr, done, name);
-  else spmv_dispatch<3, false>(c, A, x, y, b, nullptr, nullptr, done, name);
+void launch_spmv(const Ctx& c, const DCsr& A, const double* x, double* y, int mode, const double* b, const int* done, const char* name, RowRange rr) {
+  if (mode == 0) spmv_dispatch<0, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr);
+  else if (mode == 1) spmv_dispatch<1, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr);
+  else if (mode == 2) spmv_dispatch<2, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr);
+  else spmv_dispatch<3, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr);
 }
 
-void launch_spmv_sell(const Ctx& c, const Sell& A, const double* x, double* y, int mode, const double* b, const int* done, const char* name) {
-  if (mode == 0) sell_dispatch<0, false>(c, A, x, y, b, nullptr, nullptr, done, name);
-  else if (mode == 1) sell_dispatch<1, false>(c, A, x, y, b, nullptr, nullptr, done, name);
-  else if (mode == 2) sell_dispatch<2, false>(c, A, x, y, b, nullptr, nullptr, done, name);
-  else sell_dispatch<3, false>(c, A, x, y, b, nullptr, nullptr, done, name);
+void launch_spmv_sell(const Ctx& c, const Sell& A, const double* x, double* y, int mode, const double* b, const int* done, const char* name, RowRange rr) {
+  if (mode == 0) sell_dispatch<0, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr);
+  else if (mode == 1) sell_dispatch<1, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr);
+  else if (mode == 2) sell_dispatch<2, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr);
+  else sell_dispatch<3, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr);
 }
-void launch_spmv_dot_sell(const Ctx& c, const Sell& A, const double* x, double* y, double* partials, PcgScalars* sc) {
-  sell_dispatch<0, true>(c, A, x, y, nullptr, partials, sc, &sc->done, "spmv_dot");
+void launch_spmv_dot_sell(const Ctx& c, const Sell& A, const double* x, double* y, double* partials, PcgScalars* sc, RowRange rr) {
+  sell_dispatch<0, true>(c, A, x, y, nullptr, partials, sc, &sc->done, "spmv_dot", rr);
+}
+
+void launch_halo_push(const Ctx& c, int total, const int* list, const int* list_ptr, const double* src, const PeerPtrs& dst, const int* done) {
+  g_launch_counter++;
+  ProfScope ps(c, "halo_push");
+  int blocks = std::max(1, std::min(cdiv(total, 256), c.num_sms * 4));
+  halo_push_kernel<<<blocks, 256, 0, c.stream>>>(c.dist, total, list, list_ptr, src, dst, c.dist_ticket, done);
+  FSB_CHECK_LAUNCH();
+}
+void launch_push_all(const Ctx& c, int begin, int end, const double* src, const PeerPtrs& dst, const int* done) {
+  g_launch_counter++;
+  ProfScope ps(c, "push_all");
+  int blocks = std::max(1, std::min(cdiv(end - begin, 256), c.num_sms * 4));
+  push_all_kernel<<<blocks, 256, 0, c.stream>>>(c.dist, begin, end, src, dst, c.dist_ticket, done);
+  FSB_CHECK_LAUNCH();
 }
 
 void launch_spmv_dot(const Ctx& c, const DCsr& A, const double* x, double* y, double* partials, PcgScalars* sc) {
@@ -588,17 +695,21 @@ void launch_spmv_dot(const Ctx& c, const DCsr& A, const double* x, double* y, do
 }
 
 void launch_smooth(const Ctx& c, const LevelData& L, const double* b_src, const int* gather, double* b_int, const double* x_in,
-                   double w, int nsweeps, double* x_out, const int* scatter, double* x_ext, double* r_out, const int* done) {
+                   double w, int nsweeps, double* x_out, const int* scatter, double* x_ext, double* r_out, const int* done, bool owned_only) {
   g_launch_counter++;
   ProfScope ps(c, x_in ? "post_smooth" : "pre_smooth");
   cudaStream_t s = c.stream;
+  if (owned_only && !L.use_ell) throw std::runtime_error("sharded smoothing needs the ELL path on the sharded level");
+  const int nSmall = owned_only ? L.nSmallOwn : L.nSmall, nBig = owned_only ? L.nBigOwn : L.nBig;
+  const int* plS = owned_only ? L.plistSmallOwn.get() : L.plistSmall.get();
+  const int* plB = owned_only ? L.plistBigOwn.get() : L.plistBig.get();
 #define FSB_ELL_ARGS(pl) pl, L.pstart, L.ellptr, L.ellK, L.ellval, L.ellcol, L.diag, b_src, gather, b_int, x_in, w, nsweeps, x_out, scatter, x_ext, r_out, done
 #define FSB_ELL_LAUNCH(MK)                                                                                                  \
   do {                                                                                                                     \
-    if (L.nSmall > 0) smooth_ell_kernel<MK, 256><<<L.nSmall, 256, 0, s>>>(FSB_ELL_ARGS(L.plistSmall.get()));               \
-    if (L.nBig > 0 && L.maxPartRows <= 512) smooth_ell_kernel<MK, 512><<<L.nBig, 512, 0, s>>>(FSB_ELL_ARGS(L.plistBig.get())); \
-    else if (L.nBig > 0) smooth_ell_kernel<MK, 1024><<<L.nBig, (L.maxPartRows + 31) & ~31, 0, s>>>(FSB_ELL_ARGS(L.plistBig.get())); \
-    if (L.nSmall > 0 && L.nBig > 0) g_launch_counter++;                                                                    \
+    if (nSmall > 0) smooth_ell_kernel<MK, 256><<<nSmall, 256, 0, s>>>(FSB_ELL_ARGS(plS));                                   \
+    if (nBig > 0 && L.maxPartRows <= 512) smooth_ell_kernel<MK, 512><<<nBig, 512, 0, s>>>(FSB_ELL_ARGS(plB));               \
+    else if (nBig > 0) smooth_ell_kernel<MK, 1024><<<nBig, (L.maxPartRows + 31) & ~31, 0, s>>>(FSB_ELL_ARGS(plB));          \
+    if (nSmall > 0 && nBig > 0) g_launch_counter++;                                                                        \
   } while (0)
   if (L.use_ell && L.ellMaxK <= 8) FSB_ELL_LAUNCH(8);
   else if (L.use_ell && L.ellMaxK <= 16) FSB_ELL_LAUNCH(16);
@@ -644,16 +755,16 @@ void launch_dot(const Ctx& c, int n, const double* a, const double* b, double* p
   g_launch_counter++;
   ProfScope ps(c, "dot");
   int blocks = vec_blocks(c, n);
-  if (which == 0) dot_kernel<0><<<blocks, 256, 0, c.stream>>>(n, a, b, partials, sc);
-  else if (which == 1) dot_kernel<1><<<blocks, 256, 0, c.stream>>>(n, a, b, partials, sc);
-  else dot_kernel<2><<<blocks, 256, 0, c.stream>>>(n, a, b, partials, sc);
+  if (which == 0) dot_kernel<0><<<blocks, 256, 0, c.stream>>>(c.dist, n, a, b, partials, sc);
+  else if (which == 1) dot_kernel<1><<<blocks, 256, 0, c.stream>>>(c.dist, n, a, b, partials, sc);
+  else dot_kernel<2><<<blocks, 256, 0, c.stream>>>(c.dist, n, a, b, partials, sc);
   FSB_CHECK_LAUNCH();
 }
 
 void launch_cg_update(const Ctx& c, int n, double* x, double* r, const double* p, const double* y, double* partials, PcgScalars* sc, double* hist) {
   g_launch_counter++;
   ProfScope ps(c, "cg_update");
-  cg_update_kernel<<<vec_blocks(c, n), 256, 0, c.stream>>>(n, x, r, p, y, partials, sc, hist);
+  cg_update_kernel<<<vec_blocks(c, n), 256, 0, c.stream>>>(c.dist, n, x, r, p, y, partials, sc, hist);
   FSB_CHECK_LAUNCH();
 }
 

@@ -5,10 +5,15 @@
 namespace fsb {
 
 // y = A x (mode 0), y = b - A x (1), y += A x (2), y -= A x (3); CSR-stream kernel. `name` tags the profile.
-void launch_spmv(const Ctx& c, const DCsr& A, const double* x, double* y, int mode, const double* b, const int* done, const char* name);
+void launch_spmv(const Ctx& c, const DCsr& A, const double* x, double* y, int mode, const double* b, const int* done, const char* name,
+                 RowRange rr = RowRange());
 // same operation on the SELL-32 copy of an operator (thread per row, coalesced, no staging)
-void launch_spmv_sell(const Ctx& c, const Sell& A, const double* x, double* y, int mode, const double* b, const int* done, const char* name);
-void launch_spmv_dot_sell(const Ctx& c, const Sell& A, const double* x, double* y, double* partials, PcgScalars* sc);
+void launch_spmv_sell(const Ctx& c, const Sell& A, const double* x, double* y, int mode, const double* b, const int* done, const char* name,
+                      RowRange rr = RowRange());
+void launch_spmv_dot_sell(const Ctx& c, const Sell& A, const double* x, double* y, double* partials, PcgScalars* sc, RowRange rr = RowRange());
+// multi-GPU exchanges over NVLink peer memory (each ends with a cross-GPU barrier in its last CTA)
+void launch_halo_push(const Ctx& c, int total, const int* list, const int* list_ptr, const double* src, const PeerPtrs& dst, const int* done);
+void launch_push_all(const Ctx& c, int begin, int end, const double* src, const PeerPtrs& dst, const int* done);
 // y = A x and the dot product x.y folded into the same pass; the last CTA finishes
 // py and alpha = rz_old / py in device memory.
 void launch_spmv_dot(const Ctx& c, const DCsr& A, const double* x, double* y, double* partials, PcgScalars* sc);
@@ -19,7 +24,8 @@ void launch_spmv_dot(const Ctx& c, const DCsr& A, const double* x, double* y, do
 // b_src is read through `gather` (level > 0: external -> internal numbering) and saved to b_int when
 // non-null; the result goes to x_out (internal) and/or is scattered to x_ext through `scatter`.
 void launch_smooth(const Ctx& c, const LevelData& L, const double* b_src, const int* gather, double* b_int, const double* x_in,
-                   double w, int nsweeps, double* x_out, const int* scatter, double* x_ext, double* r_out, const int* done);
+                   double w, int nsweeps, double* x_out, const int* scatter, double* x_ext, double* r_out, const int* done,
+                   bool owned_only = false);
 void launch_coarse_solve(const Ctx& c, int n, const double* Ainv, const double* b, double* x, const int* done);
 
 // PCG vector kernels (device-resident scalars)

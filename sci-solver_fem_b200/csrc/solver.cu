@@ -33,6 +33,7 @@ Solver::Solver(int device) {
 }
 
 Solver::~Solver() {
+  try { dist_disconnect(); } catch (...) {}
   destroy_graph();
   levels.clear();
   if (ev0_) cudaEventDestroy(ev0_);
@@ -136,6 +137,7 @@ void Solver::setup() {
   if (prm.partitionMaxSize > 1024) throw std::invalid_argument("partitionMaxSize_ must be <= 1024");
   FSB_CUDA(cudaSetDevice(ctx.device));
   cudaStream_t s = ctx.stream;
+  dist_disconnect();
   destroy_graph();
   levels.clear();
   tic("setup");
@@ -218,30 +220,54 @@ void Solver::vcycle(int lev, const double* b_src, const int* gather, double* x_d
   }
   const double w = prm.smootherWeight;
   const double* b_eff = gather ? L.b.get() : b_src;
+  // sharded solve: this GPU owns a contiguous range of level-0 partitions (dist.cu); levels >= 1 are replicated
+  const bool D = dist.connected && dist.nranks > 1 && cg_active_ && lev == 0;
+  RowRange rr, rrc;
+  PeerPtrs px = {}, pr = {}, pbc = {};
+  if (D) {
+    if (prm.postRelaxes != 1) throw std::invalid_argument("the sharded solve supports postRelaxes_ == 1");
+    rr.begin = dist.rbeg[dist.rank]; rr.end = dist.rbeg[dist.rank + 1];
+    rrc.begin = dist.abeg[dist.rank]; rrc.end = dist.abeg[dist.rank + 1];
+    for (int q = 0; q < dist.nranks; q++) {
+      px.p[q] = reinterpret_cast<double*>(dist.peer[q] + dist.off_x);
+      pr.p[q] = reinterpret_cast<double*>(dist.peer[q] + dist.off_r);
+      pbc.p[q] = reinterpret_cast<double*>(dist.peer[q] + dist.off_bc);
+    }
+  }
   // pre: x = w b/d, nu1 sweeps, r = b - A_in x - d x  (one kernel, matrix slab read once)
-  launch_smooth(ctx, L, b_src, gather, gather ? L.b.get() : nullptr, nullptr, w, prm.preInnerIters, L.x, nullptr, nullptr, L.r, done);
-  if (L.sAout.ready()) launch_spmv_sell(ctx, L.sAout, L.x, L.r, 3, nullptr, done, "residual_out");
-  else launch_spmv(ctx, L.Aout, L.x, L.r, 3, nullptr, done, "residual_out");   // r -= A_out x   (preAout_kernel)
-  launch_spmv(ctx, L.R, L.r, L.bc, 0, nullptr, done, "restrict");         // bc = R r
+  launch_smooth(ctx, L, b_src, gather, gather ? L.b.get() : nullptr, nullptr, w, prm.preInnerIters, L.x, nullptr, nullptr, L.r, done, D);
+  if (D) launch_halo_push(ctx, dist.nSendA, dist.sendA, dist.sendA_ptr, L.x, px, done);           // x across the cut
+  if (L.sAout.ready()) launch_spmv_sell(ctx, L.sAout, L.x, L.r, 3, nullptr, done, "residual_out", rr);
+  else launch_spmv(ctx, L.Aout, L.x, L.r, 3, nullptr, done, "residual_out", rr);   // r -= A_out x   (preAout_kernel)
+  if (D) launch_halo_push(ctx, dist.nSendR, dist.sendR, dist.sendR_ptr, L.r, pr, done);           // r rows the peers restrict
+  launch_spmv(ctx, L.R, L.r, L.bc, 0, nullptr, done, "restrict", rrc);            // bc = R r
+  if (D) launch_push_all(ctx, rrc.begin, rrc.end, L.bc, pbc, done);                               // all-gather of bc
   const bool next_is_coarsest = (lev + 1 == (int)levels.size() - 1);
   const int* ip = next_is_coarsest ? nullptr : levels[lev + 1].agg.ipermutation.get();
   vcycle(lev + 1, L.bc, ip, L.xc, ip, nullptr);
   profiler.cur_level = lev;
-  if (L.sP.ready()) launch_spmv_sell(ctx, L.sP, L.xc, L.x, 2, nullptr, done, "prolong_add");
-  else launch_spmv(ctx, L.P, L.xc, L.x, 2, nullptr, done, "prolong_add");      // x += P xc
+  if (L.sP.ready()) launch_spmv_sell(ctx, L.sP, L.xc, L.x, 2, nullptr, done, "prolong_add", rr);
+  else launch_spmv(ctx, L.P, L.xc, L.x, 2, nullptr, done, "prolong_add", rr);      // x += P xc
   double* xin = L.x;
   double* xtmp = L.x2;
   for (int rel = 0; rel < prm.postRelaxes; rel++) {
     bool lastpass = (rel == prm.postRelaxes - 1);
-    if (L.sAout.ready()) launch_spmv_sell(ctx, L.sAout, xin, L.r, 1, b_eff, done, "bprime");
-    else launch_spmv(ctx, L.Aout, xin, L.r, 1, b_eff, done, "bprime");         // b' = b - A_out x (x frozen for this pass)
-    if (lastpass) launch_smooth(ctx, L, L.r, nullptr, nullptr, xin, w, prm.postInnerIters, scatter ? nullptr : x_dst, scatter, scatter ? x_dst : nullptr, nullptr, done);
-    else { launch_smooth(ctx, L, L.r, nullptr, nullptr, xin, w, prm.postInnerIters, xtmp, nullptr, nullptr, nullptr, done); std::swap(xin, xtmp); }
+    if (D) launch_halo_push(ctx, dist.nSendA, dist.sendA, dist.sendA_ptr, xin, px, done);
+    if (L.sAout.ready()) launch_spmv_sell(ctx, L.sAout, xin, L.r, 1, b_eff, done, "bprime", rr);
+    else launch_spmv(ctx, L.Aout, xin, L.r, 1, b_eff, done, "bprime", rr);         // b' = b - A_out x (x frozen for this pass)
+    if (lastpass) launch_smooth(ctx, L, L.r, nullptr, nullptr, xin, w, prm.postInnerIters, scatter ? nullptr : x_dst, scatter, scatter ? x_dst : nullptr, nullptr, done, D);
+    else { launch_smooth(ctx, L, L.r, nullptr, nullptr, xin, w, prm.postInnerIters, xtmp, nullptr, nullptr, nullptr, done, D); std::swap(xin, xtmp); }
   }
   if (prm.postRelaxes <= 0) {  // degenerate configuration: no post-relaxation pass
     if (scatter) launch_scatter(ctx, L.n, scatter, xin, x_dst);
     else FSB_CUDA(cudaMemcpyAsync(x_dst, xin, sizeof(double) * L.n, cudaMemcpyDeviceToDevice, ctx.stream));
   }
+}
+
+void Solver::apply_matrix(const double* x, double* y) {
+  if (A0.nrows == 0) throw std::invalid_argument("Error no matrix specified");
+  launch_spmv(ctx, A0, x, y, 0, nullptr, nullptr, "apply_matrix");
+  FSB_CUDA(cudaStreamSynchronize(ctx.stream));
 }
 
 void Solver::spmv_fine(const double* x, double* y) { launch_spmv(ctx, levels.at(0).A, x, y, 0, nullptr, nullptr, "spmv"); FSB_CUDA(cudaStreamSynchronize(ctx.stream)); }
@@ -256,12 +282,21 @@ void Solver::precondition(const double* r, double* z) {
 void Solver::enqueue_pcg_iteration() {
   const int n = levels[0].n;
   PcgScalars* sc = scal.get();
-  if (levels[0].sA.ready()) launch_spmv_dot_sell(ctx, levels[0].sA, cg_p, cg_y, partials, sc);
+  const bool D = dist.connected && dist.nranks > 1;
+  const int rb = D ? dist.rbeg[dist.rank] : 0, re = D ? dist.rbeg[dist.rank + 1] : n, nown = re - rb;
+  RowRange rr;
+  if (D) { rr.begin = rb; rr.end = re; }
+  if (levels[0].sA.ready()) launch_spmv_dot_sell(ctx, levels[0].sA, cg_p, cg_y, partials, sc, rr);
   else launch_spmv_dot(ctx, levels[0].A, cg_p, cg_y, partials, sc);          // y = A p, alpha = rz / (p.y)
-  launch_cg_update(ctx, n, cg_x, cg_r, cg_p, cg_y, partials, sc, hist);      // x += alpha p, r -= alpha y, ||r||, test
+  launch_cg_update(ctx, nown, cg_x.get() + rb, cg_r.get() + rb, cg_p.get() + rb, cg_y.get() + rb, partials, sc, hist);  // x += alpha p, r -= alpha y, ||r||, test
   vcycle(0, cg_r, nullptr, cg_z, nullptr, nullptr);                          // z = M^-1 r
-  launch_dot(ctx, n, cg_r, cg_z, partials, sc, 2);                           // rz_new, beta
-  launch_cg_pdir(ctx, n, cg_p, cg_z, sc, 0);                                 // p = z + beta p
+  launch_dot(ctx, nown, cg_r.get() + rb, cg_z.get() + rb, partials, sc, 2);  // rz_new, beta
+  launch_cg_pdir(ctx, nown, cg_p.get() + rb, cg_z.get() + rb, sc, 0);        // p = z + beta p
+  if (D) {
+    PeerPtrs pp = {};
+    for (int q = 0; q < dist.nranks; q++) pp.p[q] = reinterpret_cast<double*>(dist.peer[q] + dist.off_p);
+    launch_halo_push(ctx, dist.nSendA, dist.sendA, dist.sendA_ptr, cg_p, pp, &sc->done);  // p across the cut for the next SpMV
+  }
 }
 
 void Solver::pcg(const double* b_user, double* x_user) {
@@ -290,12 +325,24 @@ void Solver::pcg(const double* b_user, double* x_user) {
   } else {
     cg_b.from_device(b_user, n); cg_x.from_device(x_user, n);
   }
-  launch_dot(ctx, n, cg_b, cg_b, partials, sc, 0);                 // bnorm
-  if (L0.sA.ready()) launch_spmv_sell(ctx, L0.sA, cg_x, cg_r, 1, cg_b, nullptr, "residual");
+  const bool D = dist.connected && dist.nranks > 1;
+  const int rb = D ? dist.rbeg[dist.rank] : 0, re = D ? dist.rbeg[dist.rank + 1] : n, nown = re - rb;
+  RowRange rr;
+  PeerPtrs pp = {}, pcx = {};
+  if (D) {
+    rr.begin = rb; rr.end = re;
+    for (int q = 0; q < dist.nranks; q++) {
+      pp.p[q] = reinterpret_cast<double*>(dist.peer[q] + dist.off_p);
+      pcx.p[q] = reinterpret_cast<double*>(dist.peer[q] + dist.off_cgx);
+    }
+  }
+  launch_dot(ctx, n, cg_b, cg_b, partials, sc, 0);                 // bnorm (full b on every GPU)
+  if (L0.sA.ready()) launch_spmv_sell(ctx, L0.sA, cg_x, cg_r, 1, cg_b, nullptr, "residual", rr);
   else launch_spmv(ctx, L0.A, cg_x, cg_r, 1, cg_b, nullptr, "residual"); // r = b - A x
   vcycle(0, cg_r, nullptr, cg_z, nullptr, nullptr);                // z = M^-1 r
-  launch_cg_pdir(ctx, n, cg_p, cg_z, sc, 1);                       // p = z
-  launch_dot(ctx, n, cg_r, cg_z, partials, sc, 1);                 // rz_old
+  launch_cg_pdir(ctx, nown, cg_p.get() + rb, cg_z.get() + rb, sc, 1);  // p = z
+  if (D) launch_halo_push(ctx, dist.nSendA, dist.sendA, dist.sendA_ptr, cg_p, pp, nullptr);
+  launch_dot(ctx, nown, cg_r.get() + rb, cg_z.get() + rb, partials, sc, 1);  // rz_old
   FSB_CUDA(cudaStreamSynchronize(s));
 
   profiler.cur_level = 0;
@@ -330,6 +377,11 @@ void Solver::pcg(const double* b_user, double* x_user) {
   resid_history.resize(h.hist_len);
   if (h.hist_len) hist.to_host(resid_history.data(), h.hist_len);
   final_relres = h.hist_len ? resid_history.back() : -1;
+  if (D) {
+    launch_push_all(ctx, rb, re, cg_x, pcx, nullptr);              // every GPU ends up with the full solution
+    int err = dist.error.read(0);
+    if (err) throw std::runtime_error("sharded solve: a peer did not arrive at an exchange (timeout)");
+  }
   if (permute) launch_scatter(ctx, n, L0.agg.ipermutation, cg_x, x_user);
   else FSB_CUDA(cudaMemcpyAsync(x_user, cg_x.get(), sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
   FSB_CUDA(cudaStreamSynchronize(s));

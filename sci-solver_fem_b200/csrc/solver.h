@@ -48,6 +48,8 @@ struct LevelData {
   int smemBytes = 0;     // > 0: the cluster smoother is usable (chunk fits in shared memory)
   IBuf plistSmall, plistBig;  // partitions with <= 256 rows / more: two CTA sizes keep occupancy up
   int nSmall = 0, nBig = 0;
+  IBuf plistSmallOwn, plistBigOwn;  // the same lists restricted to this GPU's partitions (sharded solve)
+  int nSmallOwn = 0, nBigOwn = 0;
   DevBuf<long long> ellptr;  // nparts+1 slab offsets (entries)
   IBuf ellK;                 // slab width of each partition
   DBuf ellval;
@@ -84,8 +86,32 @@ class Solver {
   std::map<std::string, double> times_ms;
   // kernel-level entry points for tests / microbenchmarks (device pointers, level-0 internal numbering)
   void spmv_fine(const double* x, double* y);
+  void apply_matrix(const double* x, double* y);   // y = A x with the user-order matrix (device pointers)
   void precondition(const double* r, double* z);   // one V-cycle, z = M^-1 r
   long long launches = 0;              // kernels launched by the last solve()
+  // ---- stage 4: sharded solve over the GPUs of one box (one process per GPU, replicated setup) ----
+  // dist_prepare(): after setup(); splits level-0 partitions over the ranks, builds the halo send lists and
+  // allocates the IPC arena.  dist_connect(): maps the peers' arenas.  Then solve() (PCG) runs sharded.
+  void dist_prepare(int rank, int nranks);
+  void dist_get_handle(void* handle64, long long* bytes);
+  void dist_connect(const void* handles /* nranks x 64 bytes */);
+  void dist_disconnect();
+  struct DistHost {
+    int rank = 0, nranks = 1;
+    bool connected = false;
+    int pbeg[kMaxRanks + 1] = {};  // level-0 partition ranges
+    int rbeg[kMaxRanks + 1] = {};  // level-0 row ranges
+    int abeg[kMaxRanks + 1] = {};  // level-1 (external) row ranges = aggregates of the owned partitions
+    char* arena = nullptr;
+    size_t arena_bytes = 0;
+    size_t off_flags = 0, off_red = 0, off_p = 0, off_x = 0, off_r = 0, off_bc = 0, off_cgx = 0;
+    char* peer[kMaxRanks] = {};
+    IBuf sendA, sendA_ptr, sendR, sendR_ptr;  // boundary rows each peer needs (operator columns / restriction rows)
+    int nSendA = 0, nSendR = 0;
+    DevBuf<unsigned long long> epoch;
+    IBuf error;
+    DevBuf<unsigned int> ticket;
+  } dist;
   std::string profile_report();        // "name level launches total_ms" lines of the last profiled solve
   Profiler profiler;
 

@@ -54,9 +54,12 @@ def load_library():
         "fsb_solve_device": (ci, [vp, vp, vp, C.POINTER(ci), C.POINTER(cd)]),
         "fsb_solve_fem": (ci, [vp, vp, vp, C.POINTER(ci), C.POINTER(cd)]),
         "fsb_resid_history": (ci, [vp, vp, ci]),
-        "fsb_spmv_fine_device": (ci, [vp, vp, vp]), "fsb_precondition_device": (ci, [vp, vp, vp]),
+        "fsb_spmv_fine_device": (ci, [vp, vp, vp]), "fsb_apply_matrix_device": (ci, [vp, vp, vp]), "fsb_precondition_device": (ci, [vp, vp, vp]),
         "fsb_time_ms": (cd, [vp, cs]), "fsb_last_launches": (cll, [vp]), "fsb_stream": (vp, [vp]),
         "fsb_profile_report": (ci, [vp, vp, ci]),
+        "fsb_dist_prepare": (ci, [vp, ci, ci]), "fsb_dist_handle": (ci, [vp, vp, C.POINTER(cll)]),
+        "fsb_dist_connect": (ci, [vp, vp]), "fsb_dist_disconnect": (ci, [vp]), "fsb_dist_ranges": (ci, [vp, vp, vp, vp]),
+        "fsb_split_by_weight": (None, [ci, vp, ci, vp]),
         "fsb_tet_mass_integrals": (None, [vp]), "fsb_tri_quadrature": (None, [vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
@@ -73,11 +76,32 @@ EXPORTED_SYMBOLS = (
     "fsb_get_matrix_csr fsb_set_matrix_values fsb_set_matrix_csr fsb_setup fsb_num_levels fsb_level_rows fsb_level_nnz "
     "fsb_level_int fsb_level_val fsb_solve fsb_solve_device fsb_solve_fem fsb_resid_history fsb_spmv_fine_device "
     "fsb_precondition_device fsb_time_ms fsb_last_launches fsb_stream fsb_tet_mass_integrals fsb_tri_quadrature "
-    "fsb_profile_report").split()
+    "fsb_profile_report fsb_dist_prepare fsb_dist_handle fsb_dist_connect fsb_dist_disconnect fsb_dist_ranges "
+    "fsb_split_by_weight fsb_apply_matrix_device").split()
 
 
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def split_by_weight(weights, nranks):
+    """Contiguous, weight-balanced split (host helper of the sharded solve): first item of every rank."""
+    w = np.ascontiguousarray(weights, dtype=np.int64)
+    out = np.zeros(nranks + 1, dtype=np.int32)
+    load_library().fsb_split_by_weight(w.size, _p(w), int(nranks), _p(out))
+    return out
+
+
+def exchange_handles_torch(payload: bytes, group=None):
+    """All-gathers one fixed-size byte string per rank with torch.distributed (any backend)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    mine = torch.tensor(list(payload), dtype=torch.uint8, device=dev)
+    outs = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(outs, mine, group=group)
+    return [bytes(o.cpu().tolist()) for o in outs]
 
 
 _FIELDS = {  # reference field -> (C-ABI parameter, default)   FEMSolver.cu:11-34
@@ -297,6 +321,33 @@ class FEMSolver:
             name, lev, cnt, ms = ln.split()
             out[(name, int(lev))] = (int(cnt), float(ms))
         return out
+
+    # ------------------------------------------------------------------ stage 4: sharded solve
+    def dist_connect(self, rank: int, world: int, allgather):
+        """Switches the PCG solve to the sharded mode.  `allgather(bytes) -> list[bytes]` exchanges the
+        64-byte IPC handles in rank order (see exchange_handles_torch)."""
+        self._check(self._L.fsb_dist_prepare(self._h, int(rank), int(world)))
+        if world == 1:
+            return
+        buf = C.create_string_buffer(64)
+        nbytes = C.c_longlong(0)
+        self._check(self._L.fsb_dist_handle(self._h, buf, C.byref(nbytes)))
+        handles = allgather(buf.raw)
+        assert len(handles) == world and all(len(h) == 64 for h in handles)
+        assert handles[rank] == buf.raw, "all-gather returned the handles in the wrong order"
+        self._check(self._L.fsb_dist_connect(self._h, C.create_string_buffer(b"".join(handles), 64 * world)))
+
+    def dist_disconnect(self):
+        self._check(self._L.fsb_dist_disconnect(self._h))
+
+    def dist_ranges(self):
+        pb, rb, ab = (np.zeros(9, dtype=np.int32) for _ in range(3))
+        n = self._L.fsb_dist_ranges(self._h, _p(pb), _p(rb), _p(ab))
+        return pb[: n + 1].copy(), rb[: n + 1].copy(), ab[: n + 1].copy()
+
+    def apply_matrix_device(self, x_ptr: int, y_ptr: int):
+        """y = A x on the device (user ordering)."""
+        self._check(self._L.fsb_apply_matrix_device(self._h, C.c_void_p(x_ptr), C.c_void_p(y_ptr)))
 
     def solve_device(self, x_ptr: int, b_ptr: int):
         """Device-pointer variant of solve(): b and x are already resident in HBM."""

@@ -1,0 +1,51 @@
+"""Multi-process tests of stage 4 (sharded solve): host plumbing on CPU with gloo (world_size 2), and —
+when the box has >= 2 GPUs — the sharded PCG solve against the single-GPU solve."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+WORKER = os.path.join(ROOT, "tests", "dist_worker.py")
+
+
+def free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def launch(nproc, args, timeout):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
+           "--master-port", str(free_port()), WORKER] + args
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+
+
+def test_host_plumbing_gloo_world2():
+    r = launch(2, ["cpu"], 300)
+    assert r.returncode == 0 and "CPU_DIST_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_split_by_weight_properties():
+    import numpy as np
+    import sci_solver_fem_b200 as fsb
+    w = np.full(100, 10)
+    assert list(fsb.split_by_weight(w, 4)) == [0, 25, 50, 75, 100]
+    assert list(fsb.split_by_weight(w, 1)) == [0, 100]
+    w = np.array([1000, 1, 1, 1, 1, 1, 1, 1])
+    cut = fsb.split_by_weight(w, 2)
+    assert cut[0] == 0 and cut[-1] == 8 and 1 <= cut[1] <= 7
+    cut = fsb.split_by_weight(np.ones(3, dtype=np.int64), 8)   # more ranks than partitions: trailing ranks are empty
+    assert cut[0] == 0 and cut[-1] == 3 and all(cut[i] <= cut[i + 1] for i in range(8))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_solve_matches_single_gpu(world):
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    r = launch(world, ["gpu", "40"], 900)
+    assert r.returncode == 0 and "GPU_DIST_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-6000:]
