@@ -41,6 +41,16 @@ METRIC = "solve DOFs/sec (AMG-PCG to 1e-8)"
 UNIT = "DOF/s"
 
 
+# stdout carries exactly ONE JSON line: keep a private copy of fd 1 for it and point fd 1 at stderr so
+# that library chatter (e.g. "NCCL version ..." under NCCL_DEBUG) cannot land in front of the line.
+_JSON_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    os.write(_JSON_FD, (json.dumps(line) + "\n").encode())
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -176,7 +186,7 @@ def reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -327,7 +337,7 @@ def ours(args):
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
