@@ -148,6 +148,8 @@ struct Sell {
   DevBuf<long long> sptr;  // nslices + 1 entry offsets
   IBuf col;
   DBuf val;
+  IBuf rowmap;             // optional: list position -> row (rows sorted by length inside windows of `window` rows)
+  int window = 0;
   bool ready() const { return nslices > 0; }
 };
 

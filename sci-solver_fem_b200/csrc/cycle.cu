@@ -248,7 +248,8 @@ void spmv_dispatch(const Ctx& c, const DCsr& A, const double* x, double* y, cons
 // request per warp for col and one for val; four steps are kept in flight together with their x
 // gathers.  The row sum runs in column order (same rounding sequence as a sequential CSR loop).
 template <int MODE, bool DOT>
-__global__ void __launch_bounds__(256) sell_spmv_kernel(DistDev dist, int row_begin, int row_end, int n, const long long* __restrict__ sptr,
+__global__ void __launch_bounds__(256) sell_spmv_kernel(DistDev dist, int row_begin, int row_end, int list_begin, const int* __restrict__ rowmap, int n,
+                                                        const long long* __restrict__ sptr,
                                                         const int* __restrict__ col, const double* __restrict__ val,
                                                         const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ b,
                                                         double* __restrict__ partials, PcgScalars* __restrict__ sc,
@@ -256,8 +257,9 @@ __global__ void __launch_bounds__(256) sell_spmv_kernel(DistDev dist, int row_be
   __shared__ double s_warp[32];
   __shared__ int s_flag;
   if (done && *done) return;
-  const int row = (row_begin & ~31) + blockIdx.x * blockDim.x + threadIdx.x;  // owned rows [row_begin, row_end)
-  const int slice = row >> 5, lane = threadIdx.x & 31;
+  // list position i (rows may be length-sorted inside windows: rowmap); owned rows are [row_begin, row_end)
+  const int i = list_begin + blockIdx.x * blockDim.x + threadIdx.x;
+  const int slice = i >> 5, lane = threadIdx.x & 31;
   const int nslices = (n + 31) >> 5;
   double acc = 0.0;
   if (slice < nslices) {
@@ -275,6 +277,7 @@ __global__ void __launch_bounds__(256) sell_spmv_kernel(DistDev dist, int row_be
     for (; k < K; k++) acc += __ldg(vp + k * 32) * __ldg(x + __ldg(cp + k * 32));
   }
   double contrib = 0.0;
+  const int row = (i < n) ? (rowmap ? __ldg(rowmap + i) : i) : -1;
   if (row >= row_begin && row < row_end) {
     if (MODE == 0) y[row] = acc;
     else if (MODE == 1) y[row] = b[row] - acc;
@@ -299,9 +302,12 @@ void sell_dispatch(const Ctx& c, const Sell& A, const double* x, double* y, cons
   const int r0 = rr.end >= 0 ? rr.begin : 0, r1 = rr.end >= 0 ? rr.end : A.nrows;
   g_launch_counter++;
   ProfScope ps(c, name);
-  const int span = r1 - (r0 & ~31);
-  if (span <= 0) return;
-  sell_spmv_kernel<MODE, DOT><<<cdiv(span, 256), 256, 0, c.stream>>>(c.dist, r0, r1, A.nrows, A.sptr, A.col, A.val, x, y, b, partials, sc, done);
+  // list positions that can hold the owned rows: whole sort windows when the rows are length-sorted
+  const int gran = A.window > 0 ? A.window : 32;
+  const int l0 = r0 / gran * gran, l1 = std::min(A.nrows, (r1 + gran - 1) / gran * gran);
+  if (l1 <= l0) return;
+  sell_spmv_kernel<MODE, DOT><<<cdiv(l1 - l0, 256), 256, 0, c.stream>>>(c.dist, r0, r1, l0, A.rowmap.size() ? A.rowmap.get() : nullptr, A.nrows,
+                                                                       A.sptr, A.col, A.val, x, y, b, partials, sc, done);
   FSB_CHECK_LAUNCH();
 }
 
@@ -559,7 +565,20 @@ __global__ void __launch_bounds__(256) spmv_vector_kernel(int row_begin, int n, 
   if (row >= n) return;
   double s = 0.0;
   const int e1 = ptr[row + 1];
-  for (int e = ptr[row] + lane; e < e1; e += 32) s += val[e] * __ldg(x + col[e]);
+  int e = ptr[row] + lane;
+  for (; e + 96 < e1; e += 128) {  // four independent (col, val) -> x chains per lane: two latency hops per 128 entries
+    const int c0 = __ldg(col + e), c1 = __ldg(col + e + 32), c2 = __ldg(col + e + 64), c3 = __ldg(col + e + 96);
+    const double v0 = __ldg(val + e), v1 = __ldg(val + e + 32), v2 = __ldg(val + e + 64), v3 = __ldg(val + e + 96);
+    const double x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
+    s += v0 * x0; s += v1 * x1; s += v2 * x2; s += v3 * x3;
+  }
+  {  // tail of up to 4 x 32 entries, predicated so that the loads still issue together
+    const bool p0 = e < e1, p1 = e + 32 < e1, p2 = e + 64 < e1, p3 = e + 96 < e1;
+    const int c0 = p0 ? __ldg(col + e) : 0, c1 = p1 ? __ldg(col + e + 32) : 0, c2 = p2 ? __ldg(col + e + 64) : 0, c3 = p3 ? __ldg(col + e + 96) : 0;
+    const double v0 = p0 ? __ldg(val + e) : 0.0, v1 = p1 ? __ldg(val + e + 32) : 0.0, v2 = p2 ? __ldg(val + e + 64) : 0.0, v3 = p3 ? __ldg(val + e + 96) : 0.0;
+    const double x0 = p0 ? __ldg(x + c0) : 0.0, x1 = p1 ? __ldg(x + c1) : 0.0, x2 = p2 ? __ldg(x + c2) : 0.0, x3 = p3 ? __ldg(x + c3) : 0.0;
+    s += v0 * x0; s += v1 * x1; s += v2 * x2; s += v3 * x3;
+  }
   s = warp_sum(s);
   if (lane == 0) {
     if (MODE == 0) y[row] = s;

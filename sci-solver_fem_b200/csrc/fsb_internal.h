@@ -40,7 +40,7 @@ void build_prolongator(const Ctx& c, const DCsr& A, const double* diag, const in
 void transpose_csr(const Ctx& c, const DCsr& A, DCsr& At);
 void spgemm(const Ctx& c, const DCsr& A, const DCsr& B, DCsr& C);
 void dense_inverse(const Ctx& c, const DCsr& A, DBuf& Ainv);  // n x n row-major, n < 1024
-void build_sell(const Ctx& c, const DCsr& A, Sell& S);
+void build_sell(const Ctx& c, const DCsr& A, Sell& S, int sort_window = 0);  // sort_window > 0: SELL-32-sigma
 struct LevelData;
 void split_partitions(const Ctx& c, LevelData& L);  // A -> A_out (CSR) + intra-partition sliced ELL
 

@@ -383,6 +383,7 @@ void split_partitions(const Ctx& c, LevelData& L) {
   L.ellMaxK = reduce_max_i32(partK, np, s);
   double avg = (double)L.A.nnz / std::max(1, n);
   L.coopG = avg > 192 ? 32 : avg > 96 ? 16 : avg > 48 ? 8 : avg > 16 ? 4 : 2;
+  if (const char* g = getenv("FSB_COOP_G")) L.coopG = std::max(1, std::min(32, atoi(g)));  // tuning knob
   L.use_ell = (L.ellMaxK <= 16) || (L.ellMaxK <= 32 && L.maxPartRows <= 512);
   L.nSmall = L.nBig = 0;
   L.smemBytes = 0;
@@ -397,7 +398,8 @@ void split_partitions(const Ctx& c, LevelData& L) {
         int chunkRows = (L.maxPartRows + C - 1) / C;
         // layout of smooth_cluster_kernel: val[cap] | 2 x double[npmax] | 3 x double[chunkmax] | int[chunkmax+1] | u16[cap]
         size_t bytes = (size_t)mx * 8 + (size_t)L.maxPartRows * 16 + (size_t)chunkRows * 24 + ((size_t)chunkRows + 1) * 4 + (size_t)mx * 2 + 32;
-        size_t limit = pass == 0 ? 110 * 1024 : 220 * 1024;
+        static const char* env_kb = getenv("FSB_CLUSTER_LIMIT_KB");  // tuning knob (default 110 KB: two CTAs per SM)
+        size_t limit = pass == 0 ? (size_t)(env_kb ? atoi(env_kb) : 110) * 1024 : 220 * 1024;
         if (bytes <= limit) { L.clusterC = C; L.maxChunkNnz = mx; L.maxChunkRows = chunkRows; L.smemBytes = (int)bytes; break; }
       }
     }
@@ -434,43 +436,59 @@ void split_partitions(const Ctx& c, LevelData& L) {
 // CSR -> SELL-32 (the streaming format of the fine-level SpMV family)
 // ---------------------------------------------------------------------------------------------
 namespace {
-__global__ void sell_width_kernel(int n, int nslices, const int* __restrict__ ptr, long long* __restrict__ sz) {
+__global__ void sell_width_kernel(int n, int nslices, const int* __restrict__ ptr, const int* __restrict__ rowmap, long long* __restrict__ sz) {
   int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (s >= nslices) return;
-  int r = s * 32 + lane, len = r < n ? ptr[r + 1] - ptr[r] : 0;
+  int i = s * 32 + lane, r = i < n ? (rowmap ? rowmap[i] : i) : -1;
+  int len = r >= 0 ? ptr[r + 1] - ptr[r] : 0;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
   if (lane == 0) sz[s] = 32ll * len;
 }
 __global__ void sell_fill_kernel(int n, int ncols, int nslices, const int* __restrict__ ptr, const int* __restrict__ col, const double* __restrict__ val,
-                                 const long long* __restrict__ sptr, int* __restrict__ scol, double* __restrict__ sval) {
+                                 const int* __restrict__ rowmap, const long long* __restrict__ sptr, int* __restrict__ scol, double* __restrict__ sval) {
   int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (s >= nslices) return;
   long long base = sptr[s];
-  int K = (int)((sptr[s + 1] - base) >> 5), r = s * 32 + lane;
-  int e0 = r < n ? ptr[r] : 0, len = r < n ? ptr[r + 1] - e0 : 0;
-  int padcol = min(r, ncols - 1);  // any valid column: the padded value is 0
+  int K = (int)((sptr[s + 1] - base) >> 5), i = s * 32 + lane;
+  int r = i < n ? (rowmap ? rowmap[i] : i) : -1;
+  int e0 = r >= 0 ? ptr[r] : 0, len = r >= 0 ? ptr[r + 1] - e0 : 0;
+  int padcol = min(max(r, 0), ncols - 1);  // any valid column: the padded value is 0
   for (int k = 0; k < K; k++) {
     bool has = k < len;
     scol[base + (long long)k * 32 + lane] = has ? col[e0 + k] : padcol;
     sval[base + (long long)k * 32 + lane] = has ? val[e0 + k] : 0.0;
   }
 }
+// sort key: window id in the high bits, row length (capped) in the low 8 bits
+__global__ void sell_sort_keys_kernel(int n, int window, const int* __restrict__ ptr, int* __restrict__ keys) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) keys[r] = ((r / window) << 8) | min(ptr[r + 1] - ptr[r], 255);
+}
 }  // namespace
 
-void build_sell(const Ctx& c, const DCsr& A, Sell& S) {
+void build_sell(const Ctx& c, const DCsr& A, Sell& S, int sort_window) {
   cudaStream_t s = c.stream;
-  S.nrows = A.nrows; S.ncols = A.ncols; S.nslices = (A.nrows + 31) / 32;
+  S.nrows = A.nrows; S.ncols = A.ncols; S.nslices = (A.nrows + 31) / 32; S.window = sort_window;
   if (S.nslices == 0) return;
+  const int* rowmap = nullptr;
+  if (sort_window > 0) {  // SELL-32-sigma: rows ordered by length inside windows, so short rows do not pay for long ones
+    IBuf keys(A.nrows, s), keys2(A.nrows, s), iota(A.nrows, s);
+    sell_sort_keys_kernel<<<cdiv(A.nrows, 256), 256, 0, s>>>(A.nrows, sort_window, A.ptr, keys);
+    iota_i32(iota, A.nrows, s);
+    S.rowmap.alloc(A.nrows, s);
+    sort_pairs_i32_i32(keys, keys2, iota, S.rowmap, A.nrows, 8 + bits_for(A.nrows / sort_window + 1), s);
+    rowmap = S.rowmap;
+  }
   DevBuf<long long> sz((size_t)S.nslices + 1, s);
   sz.zero();
-  sell_width_kernel<<<cdiv(S.nslices, 8), 256, 0, s>>>(A.nrows, S.nslices, A.ptr, sz);
+  sell_width_kernel<<<cdiv(S.nslices, 8), 256, 0, s>>>(A.nrows, S.nslices, A.ptr, rowmap, sz);
   S.sptr.alloc((size_t)S.nslices + 1, s);
   exclusive_scan_i64(sz, S.sptr, (size_t)S.nslices + 1, s);
   S.nstored = S.sptr.read(S.nslices);
   S.col.alloc((size_t)std::max<long long>(S.nstored, 1), s);
   S.val.alloc((size_t)std::max<long long>(S.nstored, 1), s);
-  sell_fill_kernel<<<cdiv(S.nslices, 8), 256, 0, s>>>(A.nrows, A.ncols, S.nslices, A.ptr, A.col, A.val, S.sptr, S.col, S.val);
+  sell_fill_kernel<<<cdiv(S.nslices, 8), 256, 0, s>>>(A.nrows, A.ncols, S.nslices, A.ptr, A.col, A.val, rowmap, S.sptr, S.col, S.val);
   FSB_CHECK_LAUNCH();
 }
 

@@ -183,7 +183,7 @@ void Solver::setup() {
     transpose_csr(ctx, L.P, L.R);
     if (N >= 32768) {  // streaming copies for the levels where bandwidth (not latency) matters
       if (L.level_id == 0) build_sell(ctx, L.A, L.sA);
-      build_sell(ctx, L.Aout, L.sAout);
+      build_sell(ctx, L.Aout, L.sAout, 1024);  // rows have 0..8 inter-partition entries: sort by length inside 1024-row windows
       build_sell(ctx, L.P, L.sP);
     }
     DCsr AP, Ac;
