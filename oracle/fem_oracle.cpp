@@ -739,17 +739,107 @@ static void remap_induced_graph(ivec& xadj, ivec& adj, const ivec& partition) {
   part_indices(slab, xadj);
 }
 
+// -----------------------------------------------------------------------------
+// a15: METIS aggregation (aggregatorType_ = 1).  Help::GetMetisAggregation
+// ComputePermutationMethods.cu:989-1047, _Large :1048-1094, GetSubGraphs :1095-1165,
+// EnsureConnectedAndNonEmpty :1166-1218.  Upstream links METIS 4.0.3 (not vendored);
+// this container only has METIS 5 (libmetis_static.a of the CUDA toolkit, 64-bit
+// idx_t), so "same partitioner" means: oracle and CUDA product call the identical
+// METIS 5 entry point with default options (deterministic).  Parity unpinned vs METIS 4.
+// -----------------------------------------------------------------------------
+extern "C" int METIS_PartGraphKway(int64_t* nvtxs, int64_t* ncon, int64_t* xadj, int64_t* adjncy, int64_t* vwgt, int64_t* vsize,
+                                   int64_t* adjwgt, int64_t* nparts, float* tpwgts, float* ubvec, int64_t* options, int64_t* objval,
+                                   int64_t* part);
+
+static int ensure_connected_and_nonempty(const ivec& indices, const ivec& adjacency, ivec& aggregation) {
+  int n = (int)aggregation.size();
+  ivec temp(n);
+  for (int i = 0; i < n; i++) temp[i] = i;
+  bool changed = true;
+  while (changed) {
+    changed = false;
+    for (int root = 0; root < n; root++) {
+      int rootValue = temp[root], rootAggregate = aggregation[root];
+      for (int e = indices[root]; e < indices[root + 1]; e++) {
+        int nb = adjacency[e];
+        if (rootAggregate == aggregation[nb] && temp[nb] > rootValue) rootValue = temp[nb];
+      }
+      if (rootValue > temp[root]) { temp[root] = rootValue; changed = true; }
+    }
+  }
+  ivec mapping = temp;
+  std::sort(mapping.begin(), mapping.end());
+  mapping.erase(std::unique(mapping.begin(), mapping.end()), mapping.end());
+  for (int i = 0; i < n; i++) aggregation[i] = (int)(std::lower_bound(mapping.begin(), mapping.end(), temp[i]) - mapping.begin());
+  return (int)mapping.size();
+}
+
+static int metis_aggregation(const ivec& indices, const ivec& adjacency, ivec& result, int partSize);
+
+static int metis_aggregation_large(const ivec& indices, const ivec& adjacency, ivec& result, int partSize) {
+  int graphSize = (int)indices.size() - 1;
+  metis_aggregation(indices, adjacency, result, graphSize / 4);
+  // GetSubGraphs
+  std::vector<ivec> nodeMaps;
+  ivec mapToSub(graphSize);
+  for (int i = 0; i < graphSize; i++) {
+    int pid = result[i];
+    while (pid + 1 > (int)nodeMaps.size()) nodeMaps.emplace_back();
+    nodeMaps[pid].push_back(i);
+    mapToSub[i] = (int)nodeMaps[pid].size() - 1;
+  }
+  ivec partition = result;
+  int offset = 0;
+  for (size_t g = 0; g < nodeMaps.size(); g++) {
+    const ivec& nodes = nodeMaps[g];
+    ivec ind(nodes.size() + 1, 0), adj;
+    for (size_t k = 0; k < nodes.size(); k++) {
+      int node = nodes[k];
+      for (int e = indices[node]; e < indices[node + 1]; e++)
+        if (partition[adjacency[e]] == (int)g) adj.push_back(mapToSub[adjacency[e]]);
+      ind[k + 1] = (int)adj.size();
+    }
+    ivec agg;
+    int aggCount = metis_aggregation(ind, adj, agg, partSize);
+    for (size_t k = 0; k < agg.size(); k++) result[nodes[k]] = agg[k] + offset;
+    offset += aggCount;
+  }
+  return offset;
+}
+
+static int metis_aggregation(const ivec& indices, const ivec& adjacency, ivec& result, int partSize) {
+  int graphSize = (int)indices.size() - 1;
+  result.assign(graphSize, 0);
+  int nparts = graphSize / partSize;
+  if (nparts < 8192) {
+    if (nparts < 2) nparts = 2;
+    std::vector<int64_t> xa(indices.begin(), indices.end()), ad(adjacency.begin(), adjacency.end()), part(graphSize, 0);
+    int64_t nv = graphSize, ncon = 1, np = nparts, objval = 0;
+    if (graphSize > 0) {
+      int rc = METIS_PartGraphKway(&nv, &ncon, xa.data(), ad.data(), nullptr, nullptr, nullptr, &np, nullptr, nullptr, nullptr, &objval, part.data());
+      if (rc != 1) throw std::runtime_error("METIS_PartGraphKway failed");
+    }
+    for (int i = 0; i < graphSize; i++) result[i] = (int)part[i];
+    return ensure_connected_and_nonempty(indices, adjacency, result);
+  }
+  return metis_aggregation_large(indices, adjacency, result, partSize);
+}
+
 struct AggOut {
   ivec permutation, ipermutation, aggregateIdx, partitionIdx, partitionLabel, xadjOut, adjOut;
   ivec fineAggregate;  // per OLD vertex: final (renumbered) aggregate id
 };
 
-// a13: CP::OldMIS, ComputePermutationMethods.cu:22-150.
-static void old_mis(const ivec& xadj, const ivec& adj, int parameters, int part_max_size, unsigned seed, AggOut& o) {
+// a13: CP::OldMIS, ComputePermutationMethods.cu:22-150 (agg_type 0) and a15: CP::MetisBottomUp
+// :151-266 (agg_type 1).  The two differ only in how the fine and the coarse labels are obtained.
+static void compute_permutation(const ivec& xadj, const ivec& adj, int agg_type, int parameters, int part_max_size, unsigned seed, AggOut& o) {
   int n = (int)xadj.size() - 1;
   int fineDepth = parameters % 100, coarseDepth = (parameters / 100) % 100, minAgg = (parameters / 10000) % 10;
+  int coarseSize = part_max_size % 1000, fineSize = (part_max_size / 1000) % 1000;  // MetisBottomUp :180-182
+  fineSize = fineSize <= 0 ? 1 : fineSize;
   ivec fineAggregate;
-  aggregate_graph(minAgg, fineDepth, xadj, adj, fineAggregate, seed);
+  if (agg_type == 0) aggregate_graph(minAgg, fineDepth, xadj, adj, fineAggregate, seed);
+  else metis_aggregation(xadj, adj, fineAggregate, fineSize);
   ivec perm(n);
   std::iota(perm.begin(), perm.end(), 0);
   std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return fineAggregate[a] < fineAggregate[b]; });
@@ -759,7 +849,8 @@ static void old_mis(const ivec& xadj, const ivec& adj, int parameters, int part_
   part_sizes(fineSort, weights, &aggIdx);
   induced_graph(xadj, adj, fineAggregate, o.xadjOut, o.adjOut);
   ivec coarse;
-  aggregate_weighted_graph(part_max_size, n, coarseDepth, o.xadjOut, o.adjOut, coarse, weights, seed);
+  if (agg_type == 0) aggregate_weighted_graph(part_max_size, n, coarseDepth, o.xadjOut, o.adjOut, coarse, weights, seed);
+  else metis_aggregation(o.xadjOut, o.adjOut, coarse, coarseSize);
   remap_induced_graph(o.xadjOut, o.adjOut, coarse);
   ivec plabel(n);
   for (int i = 0; i < n; i++) plabel[i] = coarse[fineSort[i]];  // fillPartitionLabelKernel :190-197
@@ -965,8 +1056,8 @@ struct Hierarchy {
       Level<T>& L = levels.back();
       int N = L.A.nrows;
       if (N < prm.topSize || num_levels >= prm.maxLevels) { LU.factor(L.A); break; }
-      if (prm.aggregatorType != 0) throw std::runtime_error("oracle: only aggregatorType_ 0 (OldMIS) is restated");
-      old_mis(L.xadj, L.adj, prm.randMisParameters, prm.partitionMaxSize, prm.seed, L.agg);
+      if (prm.aggregatorType != 0 && prm.aggregatorType != 1) throw std::runtime_error("oracle: only aggregatorType_ 0 (OldMIS) and 1 (METIS bottom-up) are restated");
+      compute_permutation(L.xadj, L.adj, prm.aggregatorType, prm.randMisParameters, prm.partitionMaxSize, prm.seed, L.agg);
       L.nnout = (int)L.agg.aggregateIdx.size() - 1;
       permute_and_split(L);
       if (L.largestblocksize > 1024) throw std::runtime_error("largest block size is larger than shared size");  // gauss_seidel.cu:2059-2064

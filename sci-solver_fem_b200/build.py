@@ -17,6 +17,7 @@ OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libfemsolver_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+METIS = os.environ.get("METIS_LIB", "/usr/local/cuda/targets/x86_64-linux/lib/libmetis_static.a")  # METIS 5 (aggregatorType_ = 1)
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++",
           "-Xcudafe", "--diag_suppress=177", "-Xcompiler", "-Wno-deprecated-declarations"]
 SOURCES = {
@@ -24,6 +25,7 @@ SOURCES = {
     "pattern.cu": [],
     "assembly.cu": ["-fmad=false"],
     "quadrature.cpp": [],
+    "metis_agg.cpp": [],
     "aggregation.cu": [],
     "hierarchy.cu": ["-fmad=false"],
     "cycle.cu": [],
@@ -68,7 +70,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
         list(ex.map(run, jobs))
     if jobs or force or not os.path.exists(LIB):
-        run([NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart"])
+        run([NVCC] + ARCH + ["-shared", "-o", LIB] + objs + [METIS, "-lcudart"])
     return LIB
 
 

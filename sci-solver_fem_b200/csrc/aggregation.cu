@@ -417,17 +417,24 @@ __global__ void agg_start_indices(int n, const int* __restrict__ fineSort, int* 
 
 }  // namespace
 
-// CP::OldMIS (ComputePermutationMethods.cu:22-150)
-void aggregate_old_mis(const Ctx& c, int n, const int* xadj, const int* adj, int parameters, int partMaxSize, unsigned seed,
-                       Aggregation& out) {
+int metis_aggregate_device_graph(const Ctx& c, int n, const int* xadj_d, const int* adj_d, int partSize, IBuf& label_d);  // metis_agg.cpp
+
+// CP::OldMIS (ComputePermutationMethods.cu:22-150, agg_type 0) and CP::MetisBottomUp (:151-266, agg_type 1): the two
+// pipelines differ only in how the fine labels (aggregates) and the coarse labels (partitions) are obtained.
+void compute_permutation(const Ctx& c, int n, const int* xadj, const int* adj, int agg_type, int parameters, int partMaxSize, unsigned seed,
+                         Aggregation& out) {
   cudaStream_t s = c.stream;
   const int fineDepth = parameters % 100, coarseDepth = (parameters / 100) % 100, minAgg = (parameters / 10000) % 10;
   int nedges;
   FSB_CUDA(cudaMemcpyAsync(&nedges, xadj + n, sizeof(int), cudaMemcpyDeviceToHost, s));
   FSB_CUDA(cudaStreamSynchronize(s));
 
+  const int coarseSize = partMaxSize % 1000;  // MetisBottomUp :180-182
+  int fineSize = (partMaxSize / 1000) % 1000;
+  fineSize = fineSize <= 0 ? 1 : fineSize;
   IBuf fineAggregate;
-  int nAgg = aggregate_graph(c, n, xadj, adj, minAgg, fineDepth, seed, fineAggregate);
+  int nAgg = agg_type == 0 ? aggregate_graph(c, n, xadj, adj, minAgg, fineDepth, seed, fineAggregate)
+                           : metis_aggregate_device_graph(c, n, xadj, adj, fineSize, fineAggregate);
 
   // rows ordered by (aggregate, vertex): stable sort of the vertex ids by aggregate id (:72-75)
   IBuf perm(n, s), fineSort(n, s), iotaN(n, s);
@@ -443,7 +450,8 @@ void aggregate_old_mis(const Ctx& c, int n, const int* xadj, const int* adj, int
   int nInducedEdges = (int)out.adjOut.size();
 
   IBuf coarse;
-  int nParts = aggregate_weighted_graph(c, nAgg, out.xadjOut, out.adjOut, weights, partMaxSize, n, coarseDepth, seed, coarse);
+  int nParts = agg_type == 0 ? aggregate_weighted_graph(c, nAgg, out.xadjOut, out.adjOut, weights, partMaxSize, n, coarseDepth, seed, coarse)
+                             : metis_aggregate_device_graph(c, nAgg, out.xadjOut, out.adjOut, std::max(coarseSize, 1), coarse);
 
   // remapInducedGraph (misHelpers.cu:1258-1280): aggregates renumbered by (partition, old id)
   {

@@ -30,8 +30,8 @@ struct Aggregation {
   IBuf permutation, ipermutation, aggregateIdx, partitionIdx, partitionLabel, xadjOut, adjOut;
   int n = 0, nAgg = 0, nParts = 0;
 };
-void aggregate_old_mis(const Ctx& c, int n, const int* xadj, const int* adj, int parameters, int partMaxSize,
-                       unsigned seed, Aggregation& out);
+void compute_permutation(const Ctx& c, int n, const int* xadj, const int* adj, int agg_type, int parameters, int partMaxSize,
+                         unsigned seed, Aggregation& out);  // agg_type 0: OldMIS, 1: METIS bottom-up
 
 // Stage 2 — hierarchy.cu
 void permute_csr(const Ctx& c, const DCsr& A, const int* perm, DCsr& B);

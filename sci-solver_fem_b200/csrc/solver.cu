@@ -132,9 +132,10 @@ __global__ static void part_rows_kernel(int nparts, const int* __restrict__ psta
 void Solver::setup() {
   if (A0.nrows == 0) throw std::invalid_argument("Error no matrix specified");  // FEMSolver::checkMatrixForValidContents
   if (pat.n == 0) throw std::runtime_error("setup needs the mesh graph: call assemble() first");
-  if (prm.aggregatorType != 0) throw std::invalid_argument("only aggregatorType_ 0 (OldMIS) is implemented in this build");
+  if (prm.aggregatorType != 0 && prm.aggregatorType != 1)
+    throw std::invalid_argument("aggregatorType_ 0 (OldMIS) and 1 (METIS bottom-up) are implemented; 2-5 are out of scope (SURVEY 8f-2)");
   if (prm.dsType != 0) throw std::invalid_argument("only dsType_ 0 is implemented (dsType_ 1 cannot run upstream either)");
-  if (prm.partitionMaxSize > 1024) throw std::invalid_argument("partitionMaxSize_ must be <= 1024");
+  if (prm.aggregatorType == 0 && prm.partitionMaxSize > 1024) throw std::invalid_argument("partitionMaxSize_ must be <= 1024");
   FSB_CUDA(cudaSetDevice(ctx.device));
   cudaStream_t s = ctx.stream;
   dist_disconnect();
@@ -161,7 +162,7 @@ void Solver::setup() {
       break;
     }
     // createNextLevel (smoothedMG_amg_level.cu:402-494)
-    aggregate_old_mis(ctx, N, L.xadj, L.adj, prm.randMisParameters, prm.partitionMaxSize, prm.seed, L.agg);
+    compute_permutation(ctx, N, L.xadj, L.adj, prm.aggregatorType, prm.randMisParameters, prm.partitionMaxSize, prm.seed, L.agg);
     L.nnout = L.agg.nAgg; L.nparts = L.agg.nParts;
     L.pstart.alloc(L.nparts + 1, s);
     pstart_kernel<<<cdiv(L.nparts + 1, 256), 256, 0, s>>>(L.nparts, L.agg.partitionIdx, L.agg.aggregateIdx, L.pstart);

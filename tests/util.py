@@ -31,7 +31,7 @@ def make_oracle(verts, elems, labels=None, precision=64, **params):
 PARAM_MAP = dict(solverType="solverType_", tolerance="tolerance_", maxIters="maxIters_", seed="seed_", topSize="topSize_",
                  preInnerIters="preInnerIters_", postInnerIters="postInnerIters_", postRelaxes="postRelaxes_",
                  partitionMaxSize="partitionMaxSize_", randMisParameters="randMisParameters_", smootherWeight="smootherWeight_",
-                 proOmega="proOmega_", maxLevels="maxLevels_", refLevel0NoPerm="refLevel0NoPerm_")
+                 proOmega="proOmega_", maxLevels="maxLevels_", refLevel0NoPerm="refLevel0NoPerm_", aggregatorType="aggregatorType_")
 
 
 def make_gpu(verts, elems, labels=None, **params):
