@@ -18,7 +18,8 @@ LIB = os.path.join(HERE, "libfemsolver_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 METIS = os.environ.get("METIS_LIB", "/usr/local/cuda/targets/x86_64-linux/lib/libmetis_static.a")  # METIS 5 (aggregatorType_ = 1)
-COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++",
+EXTRA = os.environ.get("NVCC_EXTRA", "").split()
+COMMON = EXTRA + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++",
           "-Xcudafe", "--diag_suppress=177", "-Xcompiler", "-Wno-deprecated-declarations"]
 SOURCES = {
     "prims.cu": [],

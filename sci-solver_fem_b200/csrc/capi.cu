@@ -5,7 +5,7 @@
 #include "../../include/femsolver_b200.h"
 #include "solver.h"
 
-namespace fsb { void split_by_weight(int nparts, const long long* w, int nranks, int* out); }
+namespace fsb { void split_by_weight(int nparts, const long long* w, int nranks, int* out); void debug_stamps(int cta_plus1, long long* out64); }
 
 struct fsb_solver {
   fsb::Solver* impl = nullptr;
@@ -262,6 +262,8 @@ int fsb_dist_ranges(const fsb_solver* s, int* part_begin, int* row_begin, int* c
   return d.nranks;
 }
 void fsb_split_by_weight(int nparts, const long long* weights, int nranks, int* out_begin) { fsb::split_by_weight(nparts, weights, nranks, out_begin); }
+// tools only (not part of the public header): phase timestamps of one CTA of the cluster smoother
+void fsb_debug_stamps(int cta_plus1, long long* out64) { fsb::debug_stamps(cta_plus1, out64); }
 void* fsb_stream(const fsb_solver* s) { return (s && s->impl) ? (void*)s->impl->ctx.stream : nullptr; }
 
 void fsb_tet_mass_integrals(double out10[10]) { fsb::tet_mass_integrals_host(out10); }

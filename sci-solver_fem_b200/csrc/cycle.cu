@@ -56,10 +56,16 @@ __device__ __forceinline__ bool publish_partial(double blocksum, double* partial
 
 __device__ __forceinline__ double final_sum(const double* partials, int n, double* s_warp) {
   __threadfence();
-  double v = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) v += __ldcg(partials + i);
+  // four independent strided chains per thread (fixed order): the loads of a thread overlap
+  double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+  const int B = blockDim.x;
+  int i = threadIdx.x;
+  for (; i + 3 * B < n; i += 4 * B) {
+    v0 += __ldcg(partials + i); v1 += __ldcg(partials + i + B); v2 += __ldcg(partials + i + 2 * B); v3 += __ldcg(partials + i + 3 * B);
+  }
+  for (; i < n; i += B) v0 += __ldcg(partials + i);
   __syncthreads();
-  return block_sum(v, s_warp);
+  return block_sum((v0 + v1) + (v2 + v3), s_warp);
 }
 
 // ------------------------------------------------------------------ cross-GPU exchange (NVLink peer memory)
@@ -430,6 +436,15 @@ __global__ void __launch_bounds__(BLOCK) smooth_coop_kernel(int G, const int* __
   }
 }
 
+// debug timestamps (tools only): CTA 0 stamps clock64 at phase boundaries when g_dbg_on != 0
+__device__ long long g_dbg[64];
+__device__ int g_dbg_on = 0;
+#ifdef FSB_DEBUG_STAMPS  // build with NVCC_EXTRA=-DFSB_DEBUG_STAMPS for tools/cluster_timing.py
+#define FSB_STAMP(k) do { if (g_dbg_on && blockIdx.x == g_dbg_on - 1 && threadIdx.x == 0 && (k) < 64) g_dbg[k] = clock64(); } while (0)
+#else
+#define FSB_STAMP(k) do { } while (0)
+#endif
+
 // (c) cluster kernel (coarse levels: long rows, few partitions).  A partition is owned by a
 // thread-block CLUSTER of C CTAs: every CTA stages the CSR slice of its np/C rows in shared memory
 // once (16-bit local columns; diagonal and inter-partition entries neutralised to 0 * x[t]) and
@@ -458,6 +473,7 @@ __global__ void __launch_bounds__(BLOCK) smooth_cluster_kernel(int C, int G, int
   int* srp = reinterpret_cast<int*>(swd + chunkmax);
   unsigned short* scol = reinterpret_cast<unsigned short*>(srp + chunkmax + 1);
   if (done && *done) return;  // uniform over the whole grid
+  FSB_STAMP(0);
   const int crank = (int)cluster.block_rank();
   const int p = blockIdx.x / C;
   const int r0 = pstart[p], np = pstart[p + 1] - r0, tid = threadIdx.x;
@@ -481,6 +497,7 @@ __global__ void __launch_bounds__(BLOCK) smooth_cluster_kernel(int C, int G, int
   }
   for (int t = tid; t <= mn; t += BLOCK) srp[t] = ptr[r0 + m0 + t] - e0;
   __syncthreads();
+  FSB_STAMP(1);
   const int lane = tid & (G - 1), grp = tid / G, RP = BLOCK / G;
   {
     // stage the slice: flat, fully coalesced, every thread keeps several independent loads in flight;
@@ -501,7 +518,9 @@ __global__ void __launch_bounds__(BLOCK) smooth_cluster_kernel(int C, int G, int
       }
     }
   }
+  FSB_STAMP(2);
   cluster.sync();  // all CTAs of the cluster are resident and initialised before remote writes start
+  FSB_STAMP(3);
   double* xc = sx0;
   double* xn = sx1;
   for (int it = 0; it < nsweeps; it++) {
@@ -509,14 +528,19 @@ __global__ void __launch_bounds__(BLOCK) smooth_cluster_kernel(int C, int G, int
       const int t = rb + grp;
       double s = 0.0;
       if (t < mn) {
+        // batches of 8 entries per lane: all column loads, then all x / value loads, then the FMAs —
+        // the dependent chain is two shared-memory latencies per batch instead of two per entry
         const int qb = srp[t + 1];
-        int q = srp[t] + lane;
         double s1 = 0.0;
-        for (; q + G < qb; q += 2 * G) {  // two independent chains per lane
-          s += sval[q] * xc[scol[q]];
-          s1 += sval[q + G] * xc[scol[q + G]];
+        for (int q = srp[t] + lane; q < qb; q += 8 * G) {
+          int cc[8]; double vv[8], xx[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) { const int qq = q + u * G; cc[u] = qq < qb ? scol[qq] : 0; vv[u] = qq < qb ? sval[qq] : 0.0; }
+#pragma unroll
+          for (int u = 0; u < 8; u++) xx[u] = xc[cc[u]];
+#pragma unroll
+          for (int u = 0; u < 8; u += 2) { s += vv[u] * xx[u]; s1 += vv[u + 1] * xx[u + 1]; }
         }
-        if (q < qb) s += sval[q] * xc[scol[q]];
         s += s1;
       }
       for (int o = G >> 1; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, G);
@@ -526,7 +550,9 @@ __global__ void __launch_bounds__(BLOCK) smooth_cluster_kernel(int C, int G, int
         for (int c = 0; c < C; c++) cluster.map_shared_rank(xn, c)[m0 + t] = xnew;  // DSMEM broadcast
       }
     }
-    cluster.sync();
+    FSB_STAMP(4 + 2 * it);
+    if (C == 1) __syncthreads(); else cluster.sync();
+    FSB_STAMP(5 + 2 * it);
     double* tmp = xc; xc = xn; xn = tmp;
   }
   if (r_out) {
@@ -534,25 +560,32 @@ __global__ void __launch_bounds__(BLOCK) smooth_cluster_kernel(int C, int G, int
       const int t = rb + grp;
       double s = 0.0;
       if (t < mn) {
+        // batches of 8 entries per lane: all column loads, then all x / value loads, then the FMAs —
+        // the dependent chain is two shared-memory latencies per batch instead of two per entry
         const int qb = srp[t + 1];
-        int q = srp[t] + lane;
         double s1 = 0.0;
-        for (; q + G < qb; q += 2 * G) {  // two independent chains per lane
-          s += sval[q] * xc[scol[q]];
-          s1 += sval[q + G] * xc[scol[q + G]];
+        for (int q = srp[t] + lane; q < qb; q += 8 * G) {
+          int cc[8]; double vv[8], xx[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) { const int qq = q + u * G; cc[u] = qq < qb ? scol[qq] : 0; vv[u] = qq < qb ? sval[qq] : 0.0; }
+#pragma unroll
+          for (int u = 0; u < 8; u++) xx[u] = xc[cc[u]];
+#pragma unroll
+          for (int u = 0; u < 8; u += 2) { s += vv[u] * xx[u]; s1 += vv[u + 1] * xx[u + 1]; }
         }
-        if (q < qb) s += sval[q] * xc[scol[q]];
         s += s1;
       }
       for (int o = G >> 1; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, G);
       if (t < mn && lane == 0) r_out[r0 + m0 + t] = sb[t] - s - sd[t] * xc[m0 + t];
     }
   }
+  FSB_STAMP(40);
   for (int t = tid; t < mn; t += BLOCK) {
     const double xv = xc[m0 + t];
     if (x_out) x_out[r0 + m0 + t] = xv;
     if (scatter) x_ext[scatter[r0 + m0 + t]] = xv;
   }
+  FSB_STAMP(41);
 }
 
 // warp-per-row SpMV for long rows (restriction operators, coarse operators)
@@ -613,8 +646,12 @@ __global__ void __launch_bounds__(256) dot_kernel(DistDev dist, int n, const dou
   __shared__ double s_warp[32];
   __shared__ int s_flag;
   if (sc->done) return;
-  double v = 0.0;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) v += a[i] * b[i];
+  double v = 0.0, vb = 0.0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  for (; i + stride < n; i += 2 * stride) { v += a[i] * b[i]; vb += a[i + stride] * b[i + stride]; }
+  for (; i < n; i += stride) v += a[i] * b[i];
+  v += vb;
   double bs = block_sum(v, s_warp);
   if (publish_partial(bs, partials, &sc->ticket[1], &s_flag)) {
     double tot = final_sum(partials, gridDim.x, s_warp);
@@ -635,13 +672,24 @@ __global__ void __launch_bounds__(256) cg_update_kernel(DistDev dist, int n, dou
   __shared__ int s_flag;
   if (sc->done) return;
   const double alpha = sc->alpha;
-  double v = 0.0;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+  double v = 0.0, vb = 0.0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  for (; i + stride < n; i += 2 * stride) {  // two independent elements in flight per thread
+    const long long j = i + stride;
+    const double pi = p[i], pj = p[j], yi = y[i], yj = y[j], xi = x[i], xj = x[j], ri0 = r[i], rj0 = r[j];
+    x[i] = xi + alpha * pi; x[j] = xj + alpha * pj;
+    const double ri = ri0 + (-alpha) * yi, rj = rj0 + (-alpha) * yj;
+    r[i] = ri; r[j] = rj;
+    v += ri * ri; vb += rj * rj;
+  }
+  for (; i < n; i += stride) {
     x[i] += alpha * p[i];
     double ri = r[i] + (-alpha) * y[i];
     r[i] = ri;
     v += ri * ri;
   }
+  v += vb;
   double bs = block_sum(v, s_warp);
   if (publish_partial(bs, partials, &sc->ticket[2], &s_flag)) {
     double tot = final_sum(partials, gridDim.x, s_warp);
@@ -756,6 +804,11 @@ void launch_smooth(const Ctx& c, const LevelData& L, const double* b_src, const 
                                                     nsweeps, x_out, scatter, x_ext, r_out, done);
 #undef FSB_ELL_ARGS
   FSB_CHECK_LAUNCH();
+}
+
+void debug_stamps(int cta_plus1, long long* out64) {
+  if (out64) FSB_CUDA(cudaMemcpyFromSymbol(out64, g_dbg, sizeof(long long) * 64));
+  FSB_CUDA(cudaMemcpyToSymbol(g_dbg_on, &cta_plus1, sizeof(int)));
 }
 
 void launch_coarse_solve(const Ctx& c, int n, const double* Ainv, const double* b, double* x, const int* done) {

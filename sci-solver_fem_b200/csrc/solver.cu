@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <chrono>
 #include <cstring>
 
 #include "kernels.h"
@@ -152,17 +153,22 @@ void Solver::setup() {
     graph_from_pattern(ctx, pat.n, pat.ptr, pat.col, L.xadj, L.adj);
   }
   int num_levels = 1;
+  auto now_ms = [&]() { cudaStreamSynchronize(s); return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  for (const char* k : {"setup_aggregation", "setup_permute_split", "setup_prolongator", "setup_galerkin", "setup_coarse_inverse"}) times_ms[k] = 0;
   while (true) {
     LevelData& L = levels.back();
     int N = L.A.nrows;
+    double t0 = now_ms();
     if (prm.verbose) printf("Rows: %d of max: %d\n", N, prm.topSize);
     if (N < prm.topSize || num_levels >= prm.maxLevels) {  // amg.cu:101
       if (N > 4096) throw std::runtime_error("coarsest level too large for the dense inverse");
       dense_inverse(ctx, L.A, Ainv);
+      times_ms["setup_coarse_inverse"] += now_ms() - t0;
       break;
     }
     // createNextLevel (smoothedMG_amg_level.cu:402-494)
     compute_permutation(ctx, N, L.xadj, L.adj, prm.aggregatorType, prm.randMisParameters, prm.partitionMaxSize, prm.seed, L.agg);
+    times_ms["setup_aggregation"] += now_ms() - t0; t0 = now_ms();
     L.nnout = L.agg.nAgg; L.nparts = L.agg.nParts;
     L.pstart.alloc(L.nparts + 1, s);
     pstart_kernel<<<cdiv(L.nparts + 1, 256), 256, 0, s>>>(L.nparts, L.agg.partitionIdx, L.agg.aggregateIdx, L.pstart);
@@ -180,6 +186,7 @@ void Solver::setup() {
     L.diag.alloc(N, s);
     extract_diag(ctx, L.A, L.diag);
     split_partitions(ctx, L);
+    times_ms["setup_permute_split"] += now_ms() - t0; t0 = now_ms();
     build_prolongator(ctx, L.A, L.diag, L.agg.aggregateIdx, L.nnout, prm.proOmega, L.P);
     transpose_csr(ctx, L.P, L.R);
     if (N >= 32768) {  // streaming copies for the levels where bandwidth (not latency) matters
@@ -187,9 +194,11 @@ void Solver::setup() {
       build_sell(ctx, L.Aout, L.sAout, 1024);  // rows have 0..8 inter-partition entries: sort by length inside 1024-row windows
       build_sell(ctx, L.P, L.sP);
     }
+    times_ms["setup_prolongator"] += now_ms() - t0; t0 = now_ms();
     DCsr AP, Ac;
     spgemm(ctx, L.A, L.P, AP);
     spgemm(ctx, L.R, AP, Ac);
+    times_ms["setup_galerkin"] += now_ms() - t0;
     L.b.alloc(N, s); L.x.alloc(N, s); L.x2.alloc(N, s); L.r.alloc(N, s);
     L.bc.alloc(L.nnout, s); L.xc.alloc(L.nnout, s);
     LevelData nx;
