@@ -108,9 +108,12 @@ __global__ void spgemm_bound(int n, const int* __restrict__ ptrA, const int* __r
 
 __global__ void spgemm_rows(int n, const int* __restrict__ ptrA, const int* __restrict__ colA, const double* __restrict__ valA,
                             const int* __restrict__ ptrB, const int* __restrict__ colB, const double* __restrict__ valB,
-                            const long long* __restrict__ sbase, int* __restrict__ scol, double* __restrict__ sval, int* __restrict__ count) {
+                            const long long* __restrict__ sbase, int* __restrict__ scol, double* __restrict__ sval, int* __restrict__ count,
+                            long long min_products) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  // second pass after spgemm_warp_kernel: only the rows it flagged (count == -1) are redone here
+  if (min_products > 0 && count[i] != -1) return;
   int* cols = scol + sbase[i];
   double* vals = sval + sbase[i];
   int cnt = 0;
@@ -120,6 +123,153 @@ __global__ void spgemm_rows(int n, const int* __restrict__ ptrA, const int* __re
     for (int f = ptrB[k]; f < ptrB[k + 1]; f++) cnt = acc_insert(cols, vals, cnt, colB[f], a * valB[f]);
   }
   count[i] = cnt;
+}
+
+
+// Warp-per-row Gustavson for rows with many products (R * (A P): ~850 products, ~40 distinct columns
+// per coarse row).  Pass 1 collects the distinct columns in a shared-memory hash set and sorts them;
+// pass 2 streams the products again in sequence order, and lane l adds up the products of the output
+// slots it owns (slot mod 32 == l) — every slot is therefore summed by one lane in product order, the
+// same order as a sequential accumulation, so the result stays bit-identical to the host-order sum.
+constexpr int WG_CHUNK = 1024;    // products staged per step
+constexpr int WG_MAXROW = 512;    // entries of the A-row (prefix table + staged A-row)
+constexpr int WG_HASH = 256;      // hash-set size; rows with more than WG_MAXD distinct columns fall back
+constexpr int WG_MAXD = 192;
+constexpr int WG_WARPS = 4;
+constexpr int WG_SMEM_PER_WARP = WG_CHUNK * 8 + WG_CHUNK * 4 + WG_CHUNK + WG_HASH * 4 + WG_HASH * 4 + (WG_MAXROW + 1) * 4 + WG_MAXROW * 12 + 12;
+
+// products q0 .. q0+WG_CHUNK of the row: the A-row (B-row starts pb, values va) is staged in shared
+// memory, so a product costs one global hop (colB / valB); four products per lane are in flight.
+__device__ __forceinline__ void wg_expand(int q0, int m, int na, int lane, const int* pref, const int* pb, const double* va,
+                                          const int* __restrict__ colB, const double* __restrict__ valB, int* pcol, double* pval) {
+  const int qe = min(m, q0 + WG_CHUNK);
+  for (int qb = q0 + lane; qb < qe; qb += 128) {
+    int f[4], e[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int q = qb + 32 * u;
+      int lo = 0, hi = na;  // last A-entry with pref[lo] <= q
+      if (q < qe) { while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pref[mid] <= q) lo = mid; else hi = mid; } }
+      e[u] = lo; f[u] = q < qe ? pb[lo] + (q - pref[lo]) : -1;
+    }
+    int c[4]; double v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) { c[u] = f[u] >= 0 ? __ldg(colB + f[u]) : 0; v[u] = (pval && f[u] >= 0) ? __ldg(valB + f[u]) : 0.0; }
+#pragma unroll
+    for (int u = 0; u < 4; u++) if (f[u] >= 0) { pcol[qb + 32 * u - q0] = c[u]; if (pval) pval[qb + 32 * u - q0] = va[e[u]] * v[u]; }
+  }
+}
+
+__global__ void __launch_bounds__(32 * WG_WARPS) spgemm_warp_kernel(int n, const int* __restrict__ ptrA, const int* __restrict__ colA,
+                                                                    const double* __restrict__ valA, const int* __restrict__ ptrB,
+                                                                    const int* __restrict__ colB, const double* __restrict__ valB,
+                                                                    const long long* __restrict__ sbase, int* __restrict__ scol,
+                                                                    double* __restrict__ sval, int* __restrict__ count) {
+  extern __shared__ __align__(16) unsigned char wg_smem[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char* base = wg_smem + (size_t)w * ((WG_SMEM_PER_WARP + 15) & ~15);
+  double* pval = reinterpret_cast<double*>(base);
+  int* pcol = reinterpret_cast<int*>(base + WG_CHUNK * 8);
+  unsigned char* pslot = base + WG_CHUNK * 12;
+  int* hash = reinterpret_cast<int*>(base + WG_CHUNK * 13);
+  int* dist = hash + WG_HASH;
+  int* pref = dist + WG_HASH;
+  int* pb = pref + (WG_MAXROW + 1);
+  double* va = reinterpret_cast<double*>(base + ((WG_CHUNK * 13 + WG_HASH * 8 + (WG_MAXROW + 1) * 4 + WG_MAXROW * 4 + 7) & ~7));
+  const int i = blockIdx.x * WG_WARPS + w;
+  if (i >= n) return;
+  const int a0 = ptrA[i], na = ptrA[i + 1] - a0;
+  const int m = (int)(sbase[i + 1] - sbase[i]);
+  if (na > WG_MAXROW) { if (lane == 0) count[i] = -1; return; }  // fallback row
+  // prefix of B-row lengths over the entries of the A-row
+  int run = 0;
+  for (int e0 = 0; e0 < na; e0 += 32) {
+    const int e = e0 + lane;
+    int len = 0;
+    if (e < na) { const int k = colA[a0 + e]; const int b0 = ptrB[k]; len = ptrB[k + 1] - b0; pb[e] = b0; va[e] = valA[a0 + e]; }
+    int inc = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (e < na) pref[e] = run + inc - len;
+    run += __shfl_sync(0xffffffffu, inc, 31);
+  }
+  if (lane == 0) pref[na] = run;
+  for (int h = lane; h < WG_HASH; h += 32) hash[h] = -1;
+  __syncwarp();
+  // pass 1: distinct columns
+  int overflow = 0;
+  for (int q0 = 0; q0 < m; q0 += WG_CHUNK) {
+    wg_expand(q0, m, na, lane, pref, pb, va, colB, valB, pcol, nullptr);
+    __syncwarp();
+    for (int q = q0 + lane; q < min(m, q0 + WG_CHUNK); q += 32) {
+      const int c = pcol[q - q0];
+      unsigned h = ((unsigned)c * 2654435761u) >> 24;
+      for (int probe = 0; probe < WG_HASH; probe++) {
+        const int old = atomicCAS(&hash[h], -1, c);
+        if (old == -1 || old == c) break;
+        h = (h + 1) & (WG_HASH - 1);
+        if (probe == WG_HASH - 1) overflow = 1;
+      }
+    }
+    __syncwarp();
+  }
+  // compact + sort the distinct columns
+  int nd = 0;
+  for (int h0 = 0; h0 < WG_HASH; h0 += 32) {
+    const int c = hash[h0 + lane];
+    const unsigned ball = __ballot_sync(0xffffffffu, c != -1);
+    if (c != -1) dist[nd + __popc(ball & ((1u << lane) - 1u))] = c;
+    nd += __popc(ball);
+  }
+  overflow = __any_sync(0xffffffffu, overflow) || nd > WG_MAXD;
+  if (overflow) { if (lane == 0) count[i] = -1; return; }
+  for (int h = nd + lane; h < WG_HASH; h += 32) dist[h] = 0x7fffffff;
+  __syncwarp();
+  for (int k2 = 2; k2 <= WG_HASH; k2 <<= 1)
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      for (int q = lane; q < WG_HASH; q += 32) {
+        const int partner = q ^ j;
+        if (partner > q) {
+          const int x = dist[q], y = dist[partner];
+          if ((x > y) == ((q & k2) == 0)) { dist[q] = y; dist[partner] = x; }
+        }
+      }
+      __syncwarp();
+    }
+  // pass 2: numeric, every output slot summed by its owner lane in product order
+  double acc[WG_MAXD / 32];
+#pragma unroll
+  for (int j = 0; j < WG_MAXD / 32; j++) acc[j] = 0.0;
+  for (int q0 = 0; q0 < m; q0 += WG_CHUNK) {
+    const int mc = min(m, q0 + WG_CHUNK) - q0;
+    wg_expand(q0, m, na, lane, pref, pb, va, colB, valB, pcol, pval);
+    __syncwarp();
+    for (int q = lane; q < mc; q += 32) {  // slot of every product (binary search in the sorted distinct list)
+      const int c = pcol[q];
+      int lo = 0, hi = nd - 1;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (dist[mid] < c) lo = mid + 1; else hi = mid; }
+      pslot[q] = (unsigned char)lo;
+    }
+    __syncwarp();
+    for (int q = 0; q < mc; q++) {
+      const int sl = pslot[q];
+      if ((sl & 31) == lane) {
+        const double v = pval[q];
+        const int j = sl >> 5;
+#pragma unroll
+        for (int jj = 0; jj < WG_MAXD / 32; jj++) if (jj == j) acc[jj] += v;
+      }
+    }
+    __syncwarp();
+  }
+  int* oc = scol + sbase[i];
+  double* ov = sval + sbase[i];
+#pragma unroll
+  for (int jj = 0; jj < WG_MAXD / 32; jj++) {
+    const int sl = jj * 32 + lane;
+    if (sl < nd) { oc[sl] = dist[sl]; ov[sl] = 0.0 + acc[jj]; }
+  }
+  if (lane == 0) count[i] = nd;
 }
 
 __global__ void expand_rows(int n, const int* __restrict__ ptr, int* __restrict__ rows) {
@@ -272,7 +422,18 @@ void spgemm(const Ctx& c, const DCsr& A, const DCsr& B, DCsr& C) {
   long long cap = sbase.read(n);
   IBuf scol((size_t)cap, s), count(n + 1, s); DBuf sval((size_t)cap, s);
   count.zero();
-  spgemm_rows<<<cdiv(n, 64), 64, 0, s>>>(n, A.ptr, A.col, A.val, B.ptr, B.col, B.val, sbase, scol, sval, count);
+  // rows with few products: one thread each; rows with many (long A-rows, e.g. R * (A P)): one warp each
+  const bool long_rows = (double)A.nnz > 64.0 * n;
+  if (long_rows) {
+    static bool attr_set = false;
+    const size_t smem = (size_t)((WG_SMEM_PER_WARP + 15) & ~15) * WG_WARPS;
+    if (!attr_set) { FSB_CUDA(cudaFuncSetAttribute(spgemm_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+    spgemm_warp_kernel<<<cdiv(n, WG_WARPS), 32 * WG_WARPS, smem, s>>>(n, A.ptr, A.col, A.val, B.ptr, B.col, B.val, sbase, scol, sval, count);
+    // rows it could not take (very long A-rows / too many distinct columns): thread-per-row kernel, restricted to them
+    spgemm_rows<<<cdiv(n, 64), 64, 0, s>>>(n, A.ptr, A.col, A.val, B.ptr, B.col, B.val, sbase, scol, sval, count, 1);
+  } else {
+    spgemm_rows<<<cdiv(n, 64), 64, 0, s>>>(n, A.ptr, A.col, A.val, B.ptr, B.col, B.val, sbase, scol, sval, count, 0);
+  }
   FSB_CHECK_LAUNCH();
   C.nrows = n; C.ncols = B.ncols;
   C.nnz = counts_to_ptr(c, count, n, C.ptr);

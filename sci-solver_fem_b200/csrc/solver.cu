@@ -197,7 +197,8 @@ void Solver::setup() {
     times_ms["setup_prolongator"] += now_ms() - t0; t0 = now_ms();
     DCsr AP, Ac;
     spgemm(ctx, L.A, L.P, AP);
-    spgemm(ctx, L.R, AP, Ac);
+    { double t1 = now_ms(); times_ms["setup_galerkin_AP_L" + std::to_string(L.level_id)] = t1 - t0; }
+    { double t1 = now_ms(); spgemm(ctx, L.R, AP, Ac); times_ms["setup_galerkin_RAP_L" + std::to_string(L.level_id)] = now_ms() - t1; }
     times_ms["setup_galerkin"] += now_ms() - t0;
     L.b.alloc(N, s); L.x.alloc(N, s); L.x2.alloc(N, s); L.r.alloc(N, s);
     L.bc.alloc(L.nnout, s); L.xc.alloc(L.nnout, s);

@@ -18,6 +18,6 @@ s.solve(np.zeros_like(b), b)
 prof = s.profile_report()
 tot = sum(m for _, m in prof.values())
 print(f"cube {args.cube}: solve {ms:.2f} ms, {it} iterations, {ms/it*1e3:.0f} us/iter (graph); profiled sum {tot:.2f} ms; setup {s.time_ms('setup'):.1f} ms")
-print("  setup phases (ms):", {k: round(s.time_ms(k), 2) for k in ("pattern", "assemble", "setup", "setup_aggregation", "setup_permute_split", "setup_prolongator", "setup_galerkin", "setup_coarse_inverse")})
+print("  setup phases (ms):", {k: round(s.time_ms(k), 2) for k in ("pattern", "assemble", "setup", "setup_aggregation", "setup_permute_split", "setup_prolongator", "setup_galerkin", "setup_galerkin_AP_L0", "setup_galerkin_RAP_L0", "setup_galerkin_AP_L1", "setup_galerkin_RAP_L1", "setup_galerkin_RAP_L2", "setup_coarse_inverse")})
 for (k, l), (c, m) in sorted(prof.items(), key=lambda kv: -kv[1][1])[:22]:
     print(f"  {k:14s} L{l}  {c:4d} launches  {m/c*1e3:8.1f} us each  {100*m/tot:5.1f}%")
