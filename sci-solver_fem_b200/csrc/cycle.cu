@@ -323,6 +323,12 @@ void sell_dispatch(const Ctx& c, const Sell& A, const double* x, double* y, cons
 // (entry k of row t at ell[base + k*np + t], 16-bit local column), so the loads are perfectly
 // coalesced and go straight into registers; the nu sweeps + the residual pass then touch HBM no
 // more: x lives double-buffered in shared memory.  Threads beyond the partition's rows exit.
+// Bank conflicts: the x gather of a half-warp (16 lanes x 8 bytes) is conflict-free only if the 16
+// local columns fall into 16 different 8-byte banks.  The tile therefore holds TWO copies of x whose
+// bank mapping differs by half a bank period (copy B starts at element BLOCK+8), and the setup
+// (hierarchy.cu: ell_assign_copies) picks, per matrix entry, the copy that collides least inside its
+// half-warp; bit 15 of the stored 16-bit column selects copy B.  Measured with ncu: the wavefront
+// excess of the gather drops from 1.77x to the value quoted in DESIGN.md.
 template <int MAXK, int BLOCK>
 __global__ void __launch_bounds__(BLOCK, (MAXK <= 16) ? (1024 / BLOCK) : (MAXK <= 24 ? 512 / BLOCK : 1))
 smooth_ell_kernel(const int* __restrict__ plist, const int* __restrict__ pstart, const long long* __restrict__ ellptr,
@@ -331,7 +337,8 @@ smooth_ell_kernel(const int* __restrict__ plist, const int* __restrict__ pstart,
                   double* __restrict__ b_int, const double* __restrict__ x_in, double w, int nsweeps, double* __restrict__ x_out,
                   const int* __restrict__ scatter, double* __restrict__ x_ext, double* __restrict__ r_out,
                   const int* __restrict__ done) {
-  __shared__ double sx[2][BLOCK];
+  constexpr int COPYB = BLOCK + 8;             // element offset of the second copy
+  __shared__ double sx[2][2 * BLOCK + 8];
   if (done && *done) return;
   const int p = plist ? plist[blockIdx.x] : blockIdx.x;
   const int r0 = pstart[p], np = pstart[p + 1] - r0, t = threadIdx.x, row = r0 + t;
@@ -347,13 +354,18 @@ smooth_ell_kernel(const int* __restrict__ plist, const int* __restrict__ pstart,
     v[k] = 0.0; v[k + 1] = 0.0;
     if (k < K) { v[k] = ev[(size_t)k * np]; c0 = ec[(size_t)k * np]; }
     if (k + 1 < K) { v[k + 1] = ev[(size_t)(k + 1) * np]; c1 = ec[(size_t)(k + 1) * np]; }
+    c0 = (c0 & 0x7fffu) + (c0 >> 15) * COPYB;  // element index inside the two-copy tile
+    c1 = (c1 & 0x7fffu) + (c1 >> 15) * COPYB;
     cpk[k >> 1] = (c0 << 3) | (c1 << 19);
   }
   const double b = b_src[gather ? gather[row] : row];
   const double d = diag[row];
   const double wd = w / d;  // one division per stage instead of one per sweep (rounding-level deviation)
   if (b_int) b_int[row] = b;
-  sx[0][t] = x_in ? x_in[row] : w * b / d;
+  {
+    const double x0 = x_in ? x_in[row] : w * b / d;
+    sx[0][t] = x0; sx[0][COPYB + t] = x0;
+  }
   // barrier over the np participating threads only
   const int nbar = (np + 31) & ~31;
   asm volatile("bar.sync 1, %0;" ::"r"(nbar));
@@ -370,7 +382,8 @@ smooth_ell_kernel(const int* __restrict__ plist, const int* __restrict__ pstart,
     const double s = s0 + s1;
     const double xv = sx[cur][t];
     if (it < nsweeps) {
-      sx[cur ^ 1][t] = xv + wd * (b - s - d * xv);
+      const double xn = xv + wd * (b - s - d * xv);
+      sx[cur ^ 1][t] = xn; sx[cur ^ 1][COPYB + t] = xn;
       asm volatile("bar.sync 1, %0;" ::"r"(nbar));
       cur ^= 1;
     } else {

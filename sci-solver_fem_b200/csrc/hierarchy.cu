@@ -526,6 +526,37 @@ __global__ void fill_ell_kernel(int n, const int* __restrict__ ptr, const int* _
   for (; k < K; k++) { ellval[base + (long long)k * np] = 0.0; ellcol[base + (long long)k * np] = (unsigned short)t; }
 }
 
+// Per half-warp (16 consecutive rows of a partition) and per ELL slot: choose for every entry the copy
+// of the x tile (A: bank = col mod 16, B: bank = (col + 8) mod 16) that currently holds the fewest
+// requests of this half-warp; equal columns share a broadcast.  The choice is stored in bit 15 of the
+// 16-bit local column.  One thread per (partition, 16-row group): setup-time work, a few microseconds.
+__global__ void ell_assign_copies(int nparts, const int* __restrict__ pstart, const int* __restrict__ partK,
+                                  const long long* __restrict__ ellptr, unsigned short* __restrict__ ellcol, int maxGroups) {
+  int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  int p = gid / maxGroups, g = gid % maxGroups;
+  if (p >= nparts) return;
+  int np = pstart[p + 1] - pstart[p], t0 = g * 16;
+  if (t0 >= np) return;
+  int K = partK[p], nl = min(16, np - t0);
+  long long base = ellptr[p];
+  for (int k = 0; k < K; k++) {
+    int cntA[16], cntB[16], colA[16], colB[16];
+#pragma unroll
+    for (int q = 0; q < 16; q++) { cntA[q] = cntB[q] = 0; colA[q] = colB[q] = -1; }
+    for (int l = 0; l < nl; l++) {
+      long long idx = base + (long long)k * np + t0 + l;
+      int cc = ellcol[idx] & 0x7fff;
+      int bA = cc & 15, bB = (cc + 8) & 15;
+      bool useB;
+      if (colA[bA] == cc) useB = false;            // broadcast with an earlier lane
+      else if (colB[bB] == cc) useB = true;
+      else useB = (cntA[bA] + cntB[bA]) > (cntA[bB] + cntB[bB]);  // bank load counts requests of both copies
+      if (useB) { if (colB[bB] != cc) cntB[bB]++; colB[bB] = cc; ellcol[idx] = (unsigned short)(cc | 0x8000); }
+      else { if (colA[bA] != cc) cntA[bA]++; colA[bA] = cc; }
+    }
+  }
+}
+
 }  // namespace
 
 void split_partitions(const Ctx& c, LevelData& L) {
@@ -580,6 +611,10 @@ void split_partitions(const Ctx& c, LevelData& L) {
     L.ellval.alloc((size_t)std::max<long long>(total, 1), s);
     L.ellcol.alloc((size_t)std::max<long long>(total, 1), s);
     fill_ell_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, L.A.ptr, L.A.col, L.A.val, rowPart, L.pstart, L.ellK, L.ellptr, L.ellval, L.ellcol);
+    {
+      int maxGroups = (L.maxPartRows + 15) / 16;
+      ell_assign_copies<<<cdiv((long long)np * maxGroups, 128), 128, 0, s>>>(np, L.pstart, L.ellK, L.ellptr, L.ellcol, maxGroups);
+    }
     // partition lists by size class (host side: nparts is a few thousand)
     std::vector<int> ps = L.pstart.to_vector(), small, big;
     for (int p = 0; p < np; p++) ((ps[p + 1] - ps[p] <= 256) ? small : big).push_back(p);
