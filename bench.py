@@ -211,11 +211,13 @@ def ours(args):
     s = fsb.FEMSolver.from_arrays(verts, tets, None, device=local)
     s.solverType_, s.tolerance_, s.maxIters_, s.seed_ = 1, 1e-8, 200, 0
     t_pattern_cold = s.time_ms("pattern")   # first GPU work of the process: includes pool growth / module load
-    s.getMatrixFromMesh()                    # steady-state pattern + assembly timings
-    t_pattern, t_assemble = s.time_ms("pattern"), s.time_ms("assemble")
-    s.setup()
-    s.setup()                                # second build: allocator pool warm
-    t_setup = s.time_ms("setup")
+    t_pattern = t_assemble = t_setup = float("inf")
+    for _ in range(3):                       # steady-state stage timings: best of 3 rebuilds (allocator pool warm)
+        s.getMatrixFromMesh()
+        t_pattern, t_assemble = min(t_pattern, s.time_ms("pattern")), min(t_assemble, s.time_ms("assemble"))
+    for _ in range(3):
+        s.setup()
+        t_setup = min(t_setup, s.time_ms("setup"))
     nnz = s._L.fsb_matrix_nnz(s.handle)
     levels = [(s.level_rows(l), s.level_nnz(l)) for l in range(s.num_levels())]
     log(f"[rank {rank}] n={n} nnz={nnz} levels={levels} pattern {t_pattern:.1f} ms assemble {t_assemble:.1f} ms setup {t_setup:.1f} ms")
