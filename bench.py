@@ -121,16 +121,19 @@ def build_problem(N):
 
 
 # ----------------------------------------------------------------------------- algorithmic bytes
-def algorithmic_bytes(kernel, n, nnz, nnzP=0, nc=0):
-    """DESIGN.md 'algorithmic bytes per launch': fp64 values, int32 indices, every array once."""
+def algorithmic_bytes(kernel, n, nnz, nnzP=0, nc=0, nnz_in=None):
+    """DESIGN.md 'algorithmic bytes per launch': fp64 values, int32 indices, every array once.
+    The smoother stages touch only the intra-partition block A_in (nnz_in entries incl. the diagonal)."""
+    if nnz_in is None:
+        nnz_in = nnz
     if kernel in ("spmv", "spmv_dot"):
         return 12 * nnz + 4 * (n + 1) + 8 * n + 8 * n          # A, x gather once, y
     if kernel == "residual":
         return 12 * nnz + 4 * (n + 1) + 8 * n * 3              # A, x, b, r
     if kernel == "pre_smooth":
-        return 12 * nnz + 4 * (n + 1) + 8 * n * 3              # A once (nu sweeps partition-resident), b, d, x out
+        return 12 * nnz_in + 4 * (n + 1) + 8 * n * 3           # A_in once (nu sweeps partition-resident), b, x out, r out
     if kernel == "post_smooth":
-        return 12 * nnz + 4 * (n + 1) + 8 * n * 4              # A once, b, d, x in (+ghost), x out
+        return 12 * nnz_in + 4 * (n + 1) + 8 * n * 3           # A_in once, b', x in, x out
     if kernel == "restrict":
         return 12 * nnzP + 4 * (nc + 1) + 8 * n + 8 * nc
     if kernel == "prolong_add":
@@ -304,7 +307,12 @@ def ours(args):
     own = 1.0
     if world > 1 and klev == 0:  # the fine level is sharded: a launch touches this GPU's rows only
         own = float(rb[rank + 1] - rb[rank]) / n
-    bytes_per_launch = algorithmic_bytes(kname_alg, ln, lnnz, nnzP, nc) * own
+    def nnz_in_of(lev):  # entries inside the partitions' diagonal blocks = nnz - nnz(A_out)
+        if lev >= len(levels) - 1:
+            return levels[lev][1]
+        ap = s.level_int(lev, "Aout_ptr")
+        return levels[lev][1] - int(ap[-1])
+    bytes_per_launch = algorithmic_bytes(kname_alg, ln, lnnz, nnzP, nc, nnz_in_of(klev)) * own
     peak, peak_src = measured_peaks()
     # DRAM traffic of the dominant kernel from the committed ncu --set full capture of the same workload
     traffic = None
@@ -318,10 +326,11 @@ def ours(args):
     kernels = {f"{k}@L{l}": {"launches": c, "ms": round(ms, 4), "share": round(ms / tot, 4)} for (k, l), (c, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1])[:8]}
     # per-kernel achieved GB/s on the fine level (SpMV + smoother % of HBM peak is part of the metric)
     fine = {}
+    nnz_in0 = nnz_in_of(0)
     for k in ("spmv_dot", "pre_smooth", "residual", "post_smooth", "cg_update", "dot", "cg_pdir"):
         if (k, 0) in prof:
             c, ms = prof[(k, 0)]
-            gbs = algorithmic_bytes(k, levels[0][0], levels[0][1]) * (own if world > 1 else 1.0) / (ms / c * 1e-3) / 1e9
+            gbs = algorithmic_bytes(k, levels[0][0], levels[0][1], nnz_in=nnz_in0) * (own if world > 1 else 1.0) / (ms / c * 1e-3) / 1e9
             fine[k] = {"us": round(ms / c * 1e3, 2), "GBps": round(gbs, 1), "frac_of_peak": round(gbs / peak, 4)}
 
     cpu = None

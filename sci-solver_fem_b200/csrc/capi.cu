@@ -177,6 +177,7 @@ long long fsb_level_int(fsb_solver* s, int level, const char* name, int* buf, lo
     else if (n == "adjOut") b = &L.agg.adjOut; else if (n == "A_ptr") b = &L.A.ptr; else if (n == "A_col") b = &L.A.col;
     else if (n == "P_ptr") b = &L.P.ptr; else if (n == "P_col") b = &L.P.col; else if (n == "R_ptr") b = &L.R.ptr;
     else if (n == "R_col") b = &L.R.col; else if (n == "pstart") b = &L.pstart;
+    else if (n == "Aout_ptr") b = &L.Aout.ptr; else if (n == "Aout_col") b = &L.Aout.col;
     else throw std::invalid_argument("unknown level array: " + n);
     rc = copy_ints(*b, buf, cap);
   });

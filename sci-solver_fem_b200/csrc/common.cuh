@@ -66,6 +66,8 @@ struct Ctx {
   Profiler* prof = nullptr;
   DistDev dist;                        // nranks == 1 unless a sharded solve is connected
   unsigned int* dist_ticket = nullptr; // last-CTA ticket of the push kernels
+  cudaStream_t side[2] = {nullptr, nullptr};  // helper streams: kernels that may run next to each other (fork/join by events)
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
 };
 
 struct RowRange { int begin = 0, end = -1; };  // end < 0: all rows

@@ -317,82 +317,301 @@ void sell_dispatch(const Ctx& c, const Sell& A, const double* x, double* y, cons
   FSB_CHECK_LAUNCH();
 }
 
+// debug timestamps (tools only): one CTA stamps clock64 at phase boundaries when g_dbg_on != 0
+// (g_dbg_on = (CTA index + 1) | kernel kind << 24; kind 0: cluster smoother, 1: ELL smoother (256-thread class), 3: shared-memory ELL smoother)
+__device__ long long g_dbg[64];
+__device__ int g_dbg_on = 0;
+#ifdef FSB_DEBUG_STAMPS  // build with NVCC_EXTRA=-DFSB_DEBUG_STAMPS for tools/cluster_timing.py, tools/ell_timing.py
+#define FSB_STAMPK(kind, k) do { if (g_dbg_on && (g_dbg_on >> 24) == (kind) && blockIdx.x == (g_dbg_on & 0xffffff) - 1 && threadIdx.x == 0 && (k) < 64) g_dbg[k] = clock64(); } while (0)
+#else
+#define FSB_STAMPK(kind, k) do { } while (0)
+#endif
+#define FSB_STAMP(k) FSB_STAMPK(0, k)
+
 // ------------------------------------------------------------------ fused smoother
-// (a) register-resident sliced-ELL kernel (fine levels).  One CTA per partition, thread t owns row
-// t.  The intra-partition off-diagonal entries of the partition are stored column-major
-// (entry k of row t at ell[base + k*np + t], 16-bit local column), so the loads are perfectly
-// coalesced and go straight into registers; the nu sweeps + the residual pass then touch HBM no
-// more: x lives double-buffered in shared memory.  Threads beyond the partition's rows exit.
+// (a) register-resident ELL kernel (fine levels).  One CTA per partition, one thread per row, rows in
+// order of decreasing intra-partition length, so a warp's slab is 32 x Kw (entry k of lane l at
+// slab[k*32 + l], 16-bit column = position of the column's row in that order): coalesced loads straight
+// into registers, no partition-wide padding.  The nu sweeps + the residual pass then touch HBM no
+// more: x lives double-buffered in shared memory in thread order, each thread keeps its own x in a
+// register.  Vectors enter and leave through a small staging tile so that global accesses stay
+// coalesced although the rows are handled in sorted order.  Threads beyond the partition's rows exit.
 // Bank conflicts: the x gather of a half-warp (16 lanes x 8 bytes) is conflict-free only if the 16
-// local columns fall into 16 different 8-byte banks.  The tile therefore holds TWO copies of x whose
-// bank mapping differs by half a bank period (copy B starts at element BLOCK+8), and the setup
-// (hierarchy.cu: ell_assign_copies) picks, per matrix entry, the copy that collides least inside its
-// half-warp; bit 15 of the stored 16-bit column selects copy B.  Measured with ncu: the wavefront
-// excess of the gather drops from 1.77x to the value quoted in DESIGN.md.
+// columns fall into 16 different 8-byte banks (or coincide).  The tile therefore holds TWO copies of x
+// whose bank mapping differs by half a bank period (copy B starts at element BLOCK+8), and the setup
+// (hierarchy.cu: ell_assign_slots) orders every row's entries and picks the copy (bit 15 of the stored
+// column) so that the lanes of a half-warp collide as little as possible.
+constexpr int ell_min_blocks(int maxk, int block) {  // register budget: 85 per thread up to 16 slots, 128 up to 24, then 255
+  const int threads = maxk <= 16 ? 768 : maxk <= 24 ? 512 : 256;
+  return threads / block > 0 ? threads / block : 1;
+}
 template <int MAXK, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, (MAXK <= 16) ? (1024 / BLOCK) : (MAXK <= 24 ? 512 / BLOCK : 1))
-smooth_ell_kernel(const int* __restrict__ plist, const int* __restrict__ pstart, const long long* __restrict__ ellptr,
-                  const int* __restrict__ ellK, const double* __restrict__ ellval, const unsigned short* __restrict__ ellcol,
-                  const double* __restrict__ diag, const double* __restrict__ b_src, const int* __restrict__ gather,
-                  double* __restrict__ b_int, const double* __restrict__ x_in, double w, int nsweeps, double* __restrict__ x_out,
-                  const int* __restrict__ scatter, double* __restrict__ x_ext, double* __restrict__ r_out,
+__global__ void __launch_bounds__(BLOCK, ell_min_blocks(MAXK, BLOCK))
+smooth_ell_kernel(const EllDesc* __restrict__ desc, const double* __restrict__ ellval, const unsigned short* __restrict__ ellcol,
+                  const unsigned short* __restrict__ ellrow, const double* __restrict__ diag, const double* __restrict__ b_src,
+                  const int* __restrict__ gather, double* __restrict__ b_int, const double* __restrict__ x_in, double w, int nsweeps,
+                  double* __restrict__ x_out, const int* __restrict__ scatter, double* __restrict__ x_ext, double* __restrict__ r_out,
                   const int* __restrict__ done) {
   constexpr int COPYB = BLOCK + 8;             // element offset of the second copy
-  __shared__ double sx[2][2 * BLOCK + 8];
-  if (done && *done) return;
-  const int p = plist ? plist[blockIdx.x] : blockIdx.x;
-  const int r0 = pstart[p], np = pstart[p + 1] - r0, t = threadIdx.x, row = r0 + t;
+  __shared__ double sx[2][2 * BLOCK + 8];      // also the staging tile (local row order) on the way in and out
+  // one dependent-load hop to everything: the descriptor (and the done flag) first, the slabs right after
+  if (BLOCK == 256) FSB_STAMPK(1, 0);
+  const uint4* dp = reinterpret_cast<const uint4*>(desc + blockIdx.x);
+  const uint4 dh = dp[0];
+  uint4 dk[2];
+  dk[0] = dp[1];
+  dk[1] = BLOCK > 512 ? dp[2] : make_uint4(0, 0, 0, 0);
+  const int dn = done ? *done : 0;
+  if (dn) return;
+  const int r0 = (int)dh.x, np = (int)dh.y, t = threadIdx.x;
+  if (BLOCK == 256) FSB_STAMPK(1, 1);
   if (t >= np) return;  // exited threads do not take part in the barriers below
-  const int K = ellK[p];
-  const double* ev = ellval + ellptr[p] + t;
-  const unsigned short* ec = ellcol + ellptr[p] + t;
+  const int nbar = (np + 31) & ~31;  // barrier over the participating warps only
+  // this thread's slab column: widths of the partition's warps are bytes of the descriptor
+  int K = 0, skip = 0;
+  {
+    const unsigned kw[8] = {dk[0].x, dk[0].y, dk[0].z, dk[0].w, dk[1].x, dk[1].y, dk[1].z, dk[1].w};
+    const int wq = t >> 5;
+#pragma unroll
+    for (int j = 0; j < BLOCK / 32; j++) {
+      const int kj = (int)((kw[j >> 2] >> (8 * (j & 3))) & 0xffu);
+      if (j < wq) skip += kj;
+      if (j == wq) K = kj;  // warp-uniform
+    }
+  }
+  const long long wbase = ((long long)dh.z | ((long long)dh.w << 32)) + 32LL * skip + (t & 31);
+  const double* ev = ellval + wbase;
+  const unsigned short* ec = ellcol + wbase;
   double v[MAXK];
   unsigned cpk[MAXK / 2];  // two 16-bit byte offsets into the x tile per register
 #pragma unroll
   for (int k = 0; k < MAXK; k += 2) {
-    unsigned c0 = t, c1 = t;
+    unsigned c0 = 0, c1 = 0;
     v[k] = 0.0; v[k + 1] = 0.0;
-    if (k < K) { v[k] = ev[(size_t)k * np]; c0 = ec[(size_t)k * np]; }
-    if (k + 1 < K) { v[k + 1] = ev[(size_t)(k + 1) * np]; c1 = ec[(size_t)(k + 1) * np]; }
+    if (k < K) { v[k] = ev[32 * k]; c0 = ec[32 * k]; v[k + 1] = ev[32 * (k + 1)]; c1 = ec[32 * (k + 1)]; }  // K is even
     c0 = (c0 & 0x7fffu) + (c0 >> 15) * COPYB;  // element index inside the two-copy tile
     c1 = (c1 & 0x7fffu) + (c1 >> 15) * COPYB;
     cpk[k >> 1] = (c0 << 3) | (c1 << 19);
   }
-  const double b = b_src[gather ? gather[row] : row];
-  const double d = diag[row];
-  const double wd = w / d;  // one division per stage instead of one per sweep (rounding-level deviation, DESIGN.md)
-  if (b_int) b_int[row] = b;
+  const int lr = ellrow[r0 + t];
   {
-    const double x0 = x_in ? x_in[row] : w * b / d;
-    sx[0][t] = x0; sx[0][COPYB + t] = x0;
+    const int row = r0 + t;
+    const double bv = b_src[gather ? gather[row] : row], dv = diag[row];
+    if (b_int) b_int[row] = bv;
+    sx[1][t] = bv; sx[1][BLOCK + t] = dv;
+    sx[0][t] = x_in ? x_in[row] : w * bv / dv;
   }
-  // barrier over the np participating threads only
-  const int nbar = (np + 31) & ~31;
+  if (BLOCK == 256) FSB_STAMPK(1, 2);
+  asm volatile("bar.sync 1, %0;" ::"r"(nbar));
+  if (BLOCK == 256) FSB_STAMPK(1, 3);
+  const double b = sx[1][lr], d = sx[1][BLOCK + lr];
+  double xv = sx[0][lr];
+  const double wd = w / d;  // one division per stage instead of one per sweep (rounding-level deviation, DESIGN.md)
+  asm volatile("bar.sync 1, %0;" ::"r"(nbar));
+  sx[0][t] = xv; sx[0][COPYB + t] = xv;
   asm volatile("bar.sync 1, %0;" ::"r"(nbar));
   int cur = 0;
   const int npasses = nsweeps + (r_out ? 1 : 0);
+  double res = 0.0;
+  if (BLOCK == 256) FSB_STAMPK(1, 4);
   for (int it = 0; it < npasses; it++) {
+    if (BLOCK == 256) FSB_STAMPK(1, 5 + it);
     const char* xs = reinterpret_cast<const char*>(sx[cur]);
     double s0 = 0.0, s1 = 0.0;  // two independent FMA chains (fixed order)
 #pragma unroll
     for (int k = 0; k < MAXK; k += 2) {
-      s0 += v[k] * *reinterpret_cast<const double*>(xs + (cpk[k >> 1] & 0xffffu));
-      s1 += v[k + 1] * *reinterpret_cast<const double*>(xs + (cpk[k >> 1] >> 16));
+      if (k < K) {
+        s0 += v[k] * *reinterpret_cast<const double*>(xs + (cpk[k >> 1] & 0xffffu));
+        s1 += v[k + 1] * *reinterpret_cast<const double*>(xs + (cpk[k >> 1] >> 16));
+      }
     }
     const double s = s0 + s1;
-    const double xv = sx[cur][t];
     if (it < nsweeps) {
-      const double xn = xv + wd * (b - s - d * xv);
-      sx[cur ^ 1][t] = xn; sx[cur ^ 1][COPYB + t] = xn;
+      xv = xv + wd * (b - s - d * xv);
+      sx[cur ^ 1][t] = xv; sx[cur ^ 1][COPYB + t] = xv;
       asm volatile("bar.sync 1, %0;" ::"r"(nbar));
       cur ^= 1;
     } else {
-      r_out[row] = b - s - d * xv;  // in-partition residual b - A_in x - d x (gauss_seidel.cu:1352-1375)
+      res = b - s - d * xv;  // in-partition residual b - A_in x - d x (gauss_seidel.cu:1352-1375)
     }
   }
-  const double xv = sx[cur][t];
-  if (x_out) x_out[row] = xv;
-  if (scatter) x_ext[scatter[row]] = xv;
+  if (BLOCK == 256) FSB_STAMPK(1, 12);
+  // back to row order through the tile that is not being read (its last readers passed a barrier)
+  double* so = sx[cur ^ 1];
+  so[lr] = xv;
+  if (r_out) so[BLOCK + lr] = res;
+  asm volatile("bar.sync 1, %0;" ::"r"(nbar));
+  const int row = r0 + t;
+  const double xo = so[t];
+  if (x_out) x_out[row] = xo;
+  if (scatter) x_ext[scatter[row]] = xo;
+  if (r_out) r_out[row] = so[BLOCK + t];
+  if (BLOCK == 256) FSB_STAMPK(1, 13);
+}
+
+// (a') shared-memory variant of (a) for the coarser levels (rows too long for registers, few
+// partitions).  Same sorted slabs, but G lanes share a row (lane g owns the row's entries g, g+G, ...)
+// and the slabs of the partition are brought into shared memory once by two TMA bulk copies
+// (cp.async.bulk -> mbarrier); whatever exceeds the shared-memory budget streams from L2 in every pass.
+// One CTA of 1024 threads per partition; up to SELLG_NVB virtual-row blocks per thread.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+
+
+template <int SELLG_BLOCK>
+__global__ void __launch_bounds__(SELLG_BLOCK, 1024 / SELLG_BLOCK)
+smooth_sellg_kernel(const SellgDesc* __restrict__ desc, int G, int npad, int smemSlots, const long long* __restrict__ wptr,
+                    const double* __restrict__ ellval, const unsigned short* __restrict__ ellcol, const unsigned short* __restrict__ ellrow,
+                    const double* __restrict__ diag, const double* __restrict__ b_src, const int* __restrict__ gather,
+                    double* __restrict__ b_int, const double* __restrict__ x_in, double w, int nsweeps, double* __restrict__ x_out,
+                    const int* __restrict__ scatter, double* __restrict__ x_ext, double* __restrict__ r_out, const int* __restrict__ done) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // layout: val[smemSlots] | x tiles 2 x (2*npad + 8) | b, d, w/d in sorted order 3 x npad | mbarrier | col[smemSlots]
+  const int COPYB = npad + 8, TILE = 2 * npad + 8;  // npad: multiple of 16 >= rows of the largest partition
+  double* sval = reinterpret_cast<double*>(smem_raw);
+  double* sx0 = sval + smemSlots;
+  double* sb = sx0 + 2 * TILE;
+  double* sd = sb + npad;
+  double* swd = sd + npad;
+  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(swd + npad);
+  unsigned short* scol = reinterpret_cast<unsigned short*>(mbar + 2);
+  constexpr int SELLG_NVB = 4;  // virtual-row blocks per thread: rows x lanes per row <= 4 * SELLG_BLOCK (split_partitions)
+  const int t = threadIdx.x, lane = t & 31;
+  const uint4* dp = reinterpret_cast<const uint4*>(desc + blockIdx.x);
+  const uint4 d0 = dp[0], d1 = dp[1];
+  const int dn = done ? *done : 0;
+  if (dn) return;
+  FSB_STAMPK(3, 0);
+  const int r0 = (int)d0.x, np = (int)d0.y, w0 = (int)d0.z;
+  const long long base = (long long)d1.x | ((long long)d1.y << 32);
+  const int slots = (int)d1.z, inSmem = min(slots, smemSlots);
+  const unsigned bar = smem_u32(mbar);
+  if (t == 0) {
+    mbar_init(bar, 1);
+    mbar_expect_tx(bar, (unsigned)inSmem * 10u);
+    if (inSmem > 0) {
+      bulk_g2s(smem_u32(sval), ellval + base, (unsigned)inSmem * 8u, bar);
+      bulk_g2s(smem_u32(scol), ellcol + base, (unsigned)inSmem * 2u, bar);
+    }
+  }
+  // this thread's virtual rows: slab offset and width of their warps
+  const int nvr = np * G, gsh = 31 - __clz(G);
+  int woff[SELLG_NVB], K[SELLG_NVB];
+#pragma unroll
+  for (int vb = 0; vb < SELLG_NVB; vb++) {
+    const int vt = vb * SELLG_BLOCK + t;
+    woff[vb] = 0; K[vb] = 0;
+    if ((vt & ~31) < nvr) {
+      const long long a = wptr[w0 + (vt >> 5)], b = wptr[w0 + (vt >> 5) + 1];
+      woff[vb] = (int)(a - base); K[vb] = (int)((b - a) >> 5);
+    }
+  }
+  // vectors: in through the tiles in row order, then into sorted order (np <= 1024: at most 2 rows per thread)
+  constexpr int NR = 1024 / SELLG_BLOCK;
+  for (int i = t; i < np; i += SELLG_BLOCK) {
+    const int row = r0 + i;
+    const double bv = b_src[gather ? gather[row] : row], dv = diag[row];
+    if (b_int) b_int[row] = bv;
+    double* s1 = sx0 + TILE;
+    s1[i] = bv; s1[npad + i] = dv;
+    sx0[i] = x_in ? x_in[row] : w * bv / dv;
+  }
+  __syncthreads();
+  double bq[NR], dq[NR], xq[NR];
+#pragma unroll
+  for (int j = 0; j < NR; j++) {
+    const int i = t + j * SELLG_BLOCK;
+    bq[j] = 0.0; dq[j] = 1.0; xq[j] = 0.0;
+    if (i < np) { const int lr = ellrow[r0 + i]; const double* s1 = sx0 + TILE; bq[j] = s1[lr]; dq[j] = s1[npad + lr]; xq[j] = sx0[lr]; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < NR; j++) {
+    const int i = t + j * SELLG_BLOCK;
+    if (i < np) { sb[i] = bq[j]; sd[i] = dq[j]; swd[i] = w / dq[j]; sx0[i] = xq[j]; sx0[COPYB + i] = xq[j]; }
+  }
+  FSB_STAMPK(3, 1);
+  mbar_wait(bar, 0);
+  FSB_STAMPK(3, 2);
+  __syncthreads();
+  int cb = 0;
+  const int npasses = nsweeps + (r_out ? 1 : 0);
+  for (int it = 0; it < npasses; it++) {
+    FSB_STAMPK(3, 3 + it);
+    const double* xs = sx0 + cb * TILE;
+    double* xn = sx0 + (cb ^ 1) * TILE;
+    const bool sweep = it < nsweeps;
+#pragma unroll
+    for (int vb = 0; vb < SELLG_NVB; vb++) {
+      const int vt = vb * SELLG_BLOCK + t;
+      if ((vt & ~31) >= nvr) break;  // warp-uniform
+      const int kk = K[vb], off = woff[vb] + lane;
+      const bool in = woff[vb] + 32 * kk <= inSmem;  // the whole warp slab is shared-memory resident
+      const double* pv = in ? sval + off : ellval + base + off;
+      const unsigned short* pc = in ? scol + off : ellcol + base + off;
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll 4
+      for (int k = 0; k < kk; k += 2) {
+        const unsigned c0 = pc[32 * k], c1 = pc[32 * k + 32];
+        const double v0 = pv[32 * k], v1 = pv[32 * k + 32];
+        s0 += v0 * xs[(c0 & 0x7fffu) + (c0 >> 15) * COPYB];
+        s1 += v1 * xs[(c1 & 0x7fffu) + (c1 >> 15) * COPYB];
+      }
+      double sum = s0 + s1;
+      for (int o = G >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const int srow = vt >> gsh;
+      if ((vt & (G - 1)) == 0 && srow < np) {
+        const double xv = xs[srow];
+        if (sweep) {
+          const double xnew = xv + swd[srow] * (sb[srow] - sum - sd[srow] * xv);
+          xn[srow] = xnew; xn[COPYB + srow] = xnew;
+        } else {
+          sb[srow] = sb[srow] - sum - sd[srow] * xv;  // in-partition residual, parked in sb (each row reads only its own b)
+        }
+      }
+    }
+    __syncthreads();
+    if (sweep) cb ^= 1;
+  }
+  FSB_STAMPK(3, 10);
+  // back to row order through the tile that is not being read
+  double* so = sx0 + (cb ^ 1) * TILE;
+  for (int i = t; i < np; i += SELLG_BLOCK) {
+    const int lr = ellrow[r0 + i];
+    so[lr] = sx0[cb * TILE + i];
+    if (r_out) so[npad + lr] = sb[i];
+  }
+  __syncthreads();
+  for (int i = t; i < np; i += SELLG_BLOCK) {
+    const int row = r0 + i;
+    const double xo = so[i];
+    if (x_out) x_out[row] = xo;
+    if (scatter) x_ext[scatter[row]] = xo;
+    if (r_out) r_out[row] = so[npad + i];
+  }
+  FSB_STAMPK(3, 11);
 }
 
 // (b) cooperative CSR kernel (coarse levels: long rows, few partitions).  G lanes share a row,
@@ -448,15 +667,6 @@ __global__ void __launch_bounds__(BLOCK) smooth_coop_kernel(int G, const int* __
     if (scatter) x_ext[scatter[r0 + t]] = xv;
   }
 }
-
-// debug timestamps (tools only): CTA 0 stamps clock64 at phase boundaries when g_dbg_on != 0
-__device__ long long g_dbg[64];
-__device__ int g_dbg_on = 0;
-#ifdef FSB_DEBUG_STAMPS  // build with NVCC_EXTRA=-DFSB_DEBUG_STAMPS for tools/cluster_timing.py
-#define FSB_STAMP(k) do { if (g_dbg_on && blockIdx.x == g_dbg_on - 1 && threadIdx.x == 0 && (k) < 64) g_dbg[k] = clock64(); } while (0)
-#else
-#define FSB_STAMP(k) do { } while (0)
-#endif
 
 // (c) cluster kernel (coarse levels: long rows, few partitions).  A partition is owned by a
 // thread-block CLUSTER of C CTAs: every CTA stages the CSR slice of its np/C rows in shared memory
@@ -780,24 +990,61 @@ void launch_smooth(const Ctx& c, const LevelData& L, const double* b_src, const 
   ProfScope ps(c, x_in ? "post_smooth" : "pre_smooth");
   cudaStream_t s = c.stream;
   if (owned_only && !L.use_ell) throw std::runtime_error("sharded smoothing needs the ELL path on the sharded level");
-  const int nSmall = owned_only ? L.nSmallOwn : L.nSmall, nBig = owned_only ? L.nBigOwn : L.nBig;
-  const int* plS = owned_only ? L.plistSmallOwn.get() : L.plistSmall.get();
-  const int* plB = owned_only ? L.plistBigOwn.get() : L.plistBig.get();
-#define FSB_ELL_ARGS(pl) pl, L.pstart, L.ellptr, L.ellK, L.ellval, L.ellcol, L.diag, b_src, gather, b_int, x_in, w, nsweeps, x_out, scatter, x_ext, r_out, done
-#define FSB_ELL_LAUNCH(MK)                                                                                                  \
-  do {                                                                                                                     \
-    if (nSmall > 0) smooth_ell_kernel<MK, 256><<<nSmall, 256, 0, s>>>(FSB_ELL_ARGS(plS));                                   \
-    if (nBig > 0 && L.maxPartRows <= 512) smooth_ell_kernel<MK, 512><<<nBig, 512, 0, s>>>(FSB_ELL_ARGS(plB));               \
-    else if (nBig > 0) smooth_ell_kernel<MK, 1024><<<nBig, (L.maxPartRows + 31) & ~31, 0, s>>>(FSB_ELL_ARGS(plB));          \
-    if (nSmall > 0 && nBig > 0) g_launch_counter++;                                                                        \
+  const int* nl = owned_only ? L.nlistOwn : L.nlist;
+  const DevBuf<EllDesc>* pl = owned_only ? L.plistOwn : L.plist;
+  static const bool serial = getenv("FSB_ELL_SERIAL") && atoi(getenv("FSB_ELL_SERIAL")) != 0;  // tuning knob: size classes one after the other
+#define FSB_ELL_TAIL L.ellval, L.ellcol, L.ellrow, L.diag, b_src, gather, b_int, x_in, w, nsweeps, x_out, scatter, x_ext, r_out, done
+// the size classes run side by side (fork/join on two helper streams, also inside a captured graph):
+// the CTAs of the small classes fill the tail of the big one
+#define FSB_ELL_LAUNCH1(MK, BL, q)                                                                                   \
+  do {                                                                                                             \
+    cudaStream_t sq = s;                                                                                           \
+    if (launched > 0 && c.side[launched - 1] && !serial) {                                                                  \
+      sq = c.side[launched - 1];                                                                                   \
+      FSB_CUDA(cudaStreamWaitEvent(sq, c.ev_fork, 0));                                                             \
+    }                                                                                                              \
+    smooth_ell_kernel<MK, BL><<<nl[q], (q == 2 && BL == 1024) ? ((L.maxPartRows + 31) & ~31) : BL, 0, sq>>>(pl[q].get(), FSB_ELL_TAIL); \
+    if (sq != s) { FSB_CUDA(cudaEventRecord(c.ev_join[launched - 1], sq)); FSB_CUDA(cudaStreamWaitEvent(s, c.ev_join[launched - 1], 0)); } \
+    launched++;                                                                                                    \
+  } while (0)
+#define FSB_ELL_LAUNCH(MK)                                                                                          \
+  do {                                                                                                             \
+    int launched = 0;                                                                                              \
+    if ((nl[0] > 0) + (nl[1] > 0) + (nl[2] > 0) > 1 && c.side[0] && !serial) FSB_CUDA(cudaEventRecord(c.ev_fork, s)); \
+    if (nl[0] > 0) FSB_ELL_LAUNCH1(MK, 256, 0);                                                                     \
+    if (nl[1] > 0) FSB_ELL_LAUNCH1(MK, 384, 1);                                                                     \
+    if (nl[2] > 0 && L.maxPartRows <= 512) FSB_ELL_LAUNCH1(MK, 512, 2);                                             \
+    else if (nl[2] > 0) FSB_ELL_LAUNCH1(MK, 1024, 2);                                                               \
+    if (launched > 1) g_launch_counter += launched - 1;                                                            \
   } while (0)
   if (L.use_ell && L.ellMaxK <= 8) FSB_ELL_LAUNCH(8);
   else if (L.use_ell && L.ellMaxK <= 16) FSB_ELL_LAUNCH(16);
   else if (L.use_ell && L.ellMaxK <= 24 && L.maxPartRows <= 512) FSB_ELL_LAUNCH(24);
   else if (L.use_ell && L.ellMaxK <= 32 && L.maxPartRows <= 512) FSB_ELL_LAUNCH(32);
 #undef FSB_ELL_LAUNCH
-#undef FSB_ELL_ARGS
-  else if (L.smemBytes > 0) {
+#undef FSB_ELL_LAUNCH1
+#undef FSB_ELL_TAIL
+  else if (L.use_sellg) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      FSB_CUDA(cudaFuncSetAttribute(smooth_sellg_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      FSB_CUDA(cudaFuncSetAttribute(smooth_sellg_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_set = true;
+    }
+    // more partitions than SMs: two 512-thread CTAs per SM, each with half of the shared memory; else one 1024-thread CTA
+    static const char* env_two = getenv("FSB_SELLG_TWO");  // tuning knob
+    const bool two = env_two ? atoi(env_two) != 0 : L.nparts > c.num_sms;
+    const int npad = (L.maxPartRows + 15) & ~15;
+    const size_t fixed = (size_t)(2 * (2 * npad + 8) + 3 * npad) * 8 + 16;
+    const size_t limit = (two ? 113 : 226) * 1024 - 1024;
+    int smemSlots = (int)std::min<long long>(L.sellgMaxSlots, (long long)((limit - fixed) / 10) & ~31LL);
+    if (smemSlots < 0) smemSlots = 0;
+    const size_t smem = fixed + (size_t)smemSlots * 10;
+#define FSB_SELLG_ARGS L.sellgDesc, L.ellG, npad, smemSlots, L.ellwptr, L.ellval, L.ellcol, L.ellrow, L.diag, b_src, gather, b_int, x_in, w, nsweeps, x_out, scatter, x_ext, r_out, done
+    if (two) smooth_sellg_kernel<512><<<L.nparts, 512, smem, s>>>(FSB_SELLG_ARGS);
+    else smooth_sellg_kernel<1024><<<L.nparts, 1024, smem, s>>>(FSB_SELLG_ARGS);
+#undef FSB_SELLG_ARGS
+  } else if (L.smemBytes > 0) {
     static bool attr_set = false;
     if (!attr_set) {
       FSB_CUDA(cudaFuncSetAttribute(smooth_cluster_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -815,7 +1062,6 @@ void launch_smooth(const Ctx& c, const LevelData& L, const double* b_src, const 
   } else
     smooth_coop_kernel<512><<<L.nparts, 512, 0, s>>>(L.coopG, L.pstart, L.A.ptr, L.A.col, L.A.val, L.diag, b_src, gather, b_int, x_in, w,
                                                     nsweeps, x_out, scatter, x_ext, r_out, done);
-#undef FSB_ELL_ARGS
   FSB_CHECK_LAUNCH();
 }
 

@@ -127,14 +127,15 @@ void Solver::dist_prepare(int rank, int nranks) {
   split_by_weight(np, w.data(), nranks, dist.pbeg);
   for (int r = 0; r <= nranks; r++) { dist.rbeg[r] = ps[dist.pbeg[r]]; dist.abeg[r] = pidx[dist.pbeg[r]]; }
   const int myb = dist.rbeg[rank], mye = dist.rbeg[rank + 1], nown = mye - myb;
-  // 2. owned partition lists of the two smoother size classes
+  // 2. owned partition lists of the smoother's size classes
   {
-    std::vector<int> small, big;
-    for (int p = dist.pbeg[rank]; p < dist.pbeg[rank + 1]; p++) ((ps[p + 1] - ps[p] <= 256) ? small : big).push_back(p);
-    L0.nSmallOwn = (int)small.size(); L0.nBigOwn = (int)big.size();
-    L0.plistSmallOwn.alloc(std::max<size_t>(1, small.size()), s); L0.plistBigOwn.alloc(std::max<size_t>(1, big.size()), s);
-    if (!small.empty()) L0.plistSmallOwn.from_host(small.data(), small.size());
-    if (!big.empty()) L0.plistBigOwn.from_host(big.data(), big.size());
+    std::vector<EllDesc> lists[kEllClasses];
+    for (int p = dist.pbeg[rank]; p < dist.pbeg[rank + 1]; p++) lists[ell_class(ps[p + 1] - ps[p])].push_back(L0.ellDescHost[p]);
+    for (int q = 0; q < kEllClasses; q++) {
+      L0.nlistOwn[q] = (int)lists[q].size();
+      L0.plistOwn[q].alloc(std::max<size_t>(1, lists[q].size()), s);
+      if (!lists[q].empty()) L0.plistOwn[q].from_host(lists[q].data(), lists[q].size());
+    }
   }
   // 3. send lists: my rows that a peer's operator rows (A) / restriction rows (R) reference
   Ranges rowsR, aggsR;

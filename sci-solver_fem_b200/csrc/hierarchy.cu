@@ -14,6 +14,8 @@
 #include <cub/cub.cuh>
 
 #include "fsb_internal.h"
+#include <ctime>
+#include <cstdio>
 #include "solver.h"
 
 namespace fsb {
@@ -503,57 +505,157 @@ __global__ void chunk_nnz_kernel(int nparts, int C, const int* __restrict__ psta
   cnnz[q] = ptr[r0 + m1] - ptr[r0 + m0];
 }
 
-__global__ void slab_size_kernel(int nparts, const int* __restrict__ pstart, const int* __restrict__ partK, long long* __restrict__ sz) {
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < nparts) sz[p] = (long long)partK[p] * (pstart[p + 1] - pstart[p]);
-}
+// ---- sorted, warp-sliced ELL slabs of the fine-level smoother -------------------------------------
+// Inside a partition the rows are handled in order of decreasing intra-partition length (stable), so
+// the 32 rows of a warp have (almost) the same length and the slab of a warp is 32 x Kw with
+// Kw = length of its longest row rounded up to even: no partition-wide padding.  Columns are stored
+// as positions in that sorted order (the x tile of the kernel lives in thread order).
 
-__global__ void fill_ell_kernel(int n, const int* __restrict__ ptr, const int* __restrict__ col, const double* __restrict__ val,
-                                const int* __restrict__ rowPart, const int* __restrict__ pstart, const int* __restrict__ partK,
-                                const long long* __restrict__ ellptr, double* __restrict__ ellval, unsigned short* __restrict__ ellcol) {
+__global__ void sort_key_kernel(int n, const int* __restrict__ rowPart, const int* __restrict__ nin, uint64_t* __restrict__ keys,
+                                uint32_t* __restrict__ rows) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
-  int p = rowPart[r], r0 = pstart[p], np = pstart[p + 1] - r0, t = r - r0, K = partK[p], k = 0;
-  long long base = ellptr[p] + t;
-  for (int e = ptr[r]; e < ptr[r + 1]; e++) {
-    int c = col[e];
-    if ((unsigned)(c - r0) < (unsigned)np && c != r) {
-      ellval[base + (long long)k * np] = val[e];
-      ellcol[base + (long long)k * np] = (unsigned short)(c - r0);
-      k++;
-    }
-  }
-  for (; k < K; k++) { ellval[base + (long long)k * np] = 0.0; ellcol[base + (long long)k * np] = (unsigned short)t; }
+  keys[r] = ((uint64_t)rowPart[r] << 8) | (uint64_t)(255 - min(nin[r], 255));
+  rows[r] = (uint32_t)r;
 }
 
-// Per half-warp (16 consecutive rows of a partition) and per ELL slot: choose for every entry the copy
-// of the x tile (A: bank = col mod 16, B: bank = (col + 8) mod 16) that currently holds the fewest
-// requests of this half-warp; equal columns share a broadcast.  The choice is stored in bit 15 of the
-// 16-bit local column.  One thread per (partition, 16-row group): setup-time work, a few microseconds.
-__global__ void ell_assign_copies(int nparts, const int* __restrict__ pstart, const int* __restrict__ partK,
-                                  const long long* __restrict__ ellptr, unsigned short* __restrict__ ellcol, int maxGroups) {
-  int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  int p = gid / maxGroups, g = gid % maxGroups;
+// sorted index i (partition-contiguous) -> local row (ellrow), local row -> sorted position (pos), sorted length
+__global__ void sorted_maps_kernel(int n, const uint32_t* __restrict__ order, const int* __restrict__ rowPart, const int* __restrict__ pstart,
+                                   const int* __restrict__ nin, unsigned short* __restrict__ ellrow, unsigned short* __restrict__ pos,
+                                   int* __restrict__ lenSorted) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int r = (int)order[i], r0 = pstart[rowPart[r]];
+  ellrow[i] = (unsigned short)(r - r0);
+  pos[r] = (unsigned short)(i - r0);
+  lenSorted[i] = nin[r];
+}
+
+__global__ void warps_of_partition(int nparts, int G, const int* __restrict__ pstart, int* __restrict__ cnt) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < nparts) cnt[p] = ((pstart[p + 1] - pstart[p]) * G + 31) >> 5;
+  if (p == nparts) cnt[p] = 0;
+}
+
+__global__ void warp_slab_size(int nparts, int G, const int* __restrict__ pstart, const int* __restrict__ pwarp, const int* __restrict__ lenSorted,
+                               int* __restrict__ warpPart, long long* __restrict__ sz) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nparts) return;
-  int np = pstart[p + 1] - pstart[p], t0 = g * 16;
-  if (t0 >= np) return;
-  int K = partK[p], nl = min(16, np - t0);
-  long long base = ellptr[p];
-  for (int k = 0; k < K; k++) {
-    int cntA[16], cntB[16], colA[16], colB[16];
-#pragma unroll
-    for (int q = 0; q < 16; q++) { cntA[q] = cntB[q] = 0; colA[q] = colB[q] = -1; }
-    for (int l = 0; l < nl; l++) {
-      long long idx = base + (long long)k * np + t0 + l;
-      int cc = ellcol[idx] & 0x7fff;
-      int bA = cc & 15, bB = (cc + 8) & 15;
-      bool useB;
-      if (colA[bA] == cc) useB = false;            // broadcast with an earlier lane
-      else if (colB[bB] == cc) useB = true;
-      else useB = (cntA[bA] + cntB[bA]) > (cntA[bB] + cntB[bB]);  // bank load counts requests of both copies
-      if (useB) { if (colB[bB] != cc) cntB[bB]++; colB[bB] = cc; ellcol[idx] = (unsigned short)(cc | 0x8000); }
-      else { if (colA[bA] != cc) cntA[bA]++; colA[bA] = cc; }
+  int r0 = pstart[p], np = pstart[p + 1] - r0, w0 = pwarp[p];
+  for (int j = 0; j * 32 < np * G; j++) {
+    // rows are sorted by decreasing length: the first row of the warp is its longest; G lanes share a row
+    int K = (lenSorted[r0 + 32 * j / G] + G - 1) / G;
+    K += K & 1;
+    warpPart[w0 + j] = p;
+    sz[w0 + j] = 32LL * K;
+  }
+}
+
+// one thread per (warp slab, lane): real entries first (column order), then zero padding that reads the row's own x
+__global__ void fill_ell_kernel(long long nthreads, int G, const int* __restrict__ warpPart, const int* __restrict__ pstart, const int* __restrict__ pwarp,
+                                const long long* __restrict__ wptr, const unsigned short* __restrict__ ellrow,
+                                const unsigned short* __restrict__ pos, const int* __restrict__ ptr, const int* __restrict__ col,
+                                const double* __restrict__ val, double* __restrict__ ellval, unsigned short* __restrict__ ellcol) {
+  long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= nthreads) return;
+  int w = (int)(gid >> 5), lane = (int)(gid & 31), p = warpPart[w];
+  int r0 = pstart[p], np = pstart[p + 1] - r0, t = 32 * (w - pwarp[p]) + lane;  // t: virtual row = (sorted row, lane of the row)
+  long long base = wptr[w] + lane;
+  int K = (int)((wptr[w + 1] - wptr[w]) >> 5), k = 0;
+  const int srow = t / G, g = t % G;
+  if (srow < np) {
+    int r = r0 + ellrow[r0 + srow], idx = 0;
+    for (int e = ptr[r]; e < ptr[r + 1]; e++) {
+      int c = col[e];
+      if ((unsigned)(c - r0) < (unsigned)np && c != r) {
+        if (idx % G == g) {  // lane g of the row takes its entries g, g + G, ...
+          ellval[base + 32LL * k] = val[e];
+          ellcol[base + 32LL * k] = pos[c];
+          k++;
+        }
+        idx++;
+      }
     }
+  }
+  for (; k < K; k++) { ellval[base + 32LL * k] = 0.0; ellcol[base + 32LL * k] = (unsigned short)min(srow, np - 1); }
+}
+
+// Slot and copy assignment.  The x tile of the smoother holds two copies of x whose bank mapping
+// differs by half a bank period (copy A: bank = col mod 16, copy B: bank = (col + 8) mod 16; bit 15 of the
+// stored column selects B).  A half-warp's gather of slot k is conflict-free when its 16 lanes hit 16
+// different 8-byte banks or share addresses (broadcast).  The order of a row's entries inside the slab
+// is free, so per half-warp the rows are placed one after the other: an entry first looks for a slot
+// in which an earlier lane already reads the same address, then for a slot whose bank (either copy) is
+// still unused, then for the least loaded one; padding slots point at an unused bank.
+// One thread per (warp slab, half): setup-time work.
+__global__ void ell_assign_slots(int nwarps, int G, const int* __restrict__ warpPart, const int* __restrict__ pstart, const int* __restrict__ pwarp,
+                                 const long long* __restrict__ wptr, const int* __restrict__ lenSorted, double* __restrict__ ellval,
+                                 unsigned short* __restrict__ ellcol) {
+  int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  int w = gid >> 1, h = gid & 1;
+  if (w >= nwarps) return;
+  int p = warpPart[w], r0 = pstart[p], np = pstart[p + 1] - r0, t0 = 32 * (w - pwarp[p]) + 16 * h;
+  if (t0 >= np * G) return;
+  const int K = (int)((wptr[w + 1] - wptr[w]) >> 5), nl = min(16, np * G - t0);
+  if (K == 0) return;
+  const long long base = wptr[w] + 16 * h;
+  short bankElem[32][16];          // first address (column | copy << 15) assigned to the bank, -1 = unused
+  unsigned char bankCnt[32][16];   // distinct addresses in the bank
+  for (int k = 0; k < K; k++)
+    for (int q = 0; q < 16; q++) { bankElem[k][q] = -1; bankCnt[k][q] = 0; }
+  for (int l = 0; l < nl; l++) {
+    const int srow = (t0 + l) / G, g = (t0 + l) % G;
+    const int len = min(max(lenSorted[r0 + srow] - g + G - 1, 0) / G, K);
+    unsigned short ec[32], oc[32];
+    double ev[32], ov[32];
+    for (int e = 0; e < len; e++) { ec[e] = ellcol[base + 32LL * e + l]; ev[e] = ellval[base + 32LL * e + l]; }
+    unsigned freeSlots = K == 32 ? 0xffffffffu : ((1u << K) - 1u), todo = len == 32 ? 0xffffffffu : ((1u << len) - 1u);
+    auto place = [&](int e, int k, int copy) {
+      const int cc = ec[e], b = (cc + 8 * copy) & 15;
+      const short addr = (short)(cc | (copy << 15));
+      oc[k] = (unsigned short)addr; ov[k] = ev[e];
+      freeSlots &= ~(1u << k); todo &= ~(1u << e);
+      if (bankElem[k][b] != addr) { bankCnt[k][b]++; if (bankElem[k][b] == -1) bankElem[k][b] = addr; }
+    };
+    for (int e = 0; e < len; e++) {  // 1. share an address with an earlier lane
+      const int cc = ec[e], bA = cc & 15, bB = (cc + 8) & 15;
+      for (unsigned f = freeSlots; f; f &= f - 1) {
+        int k = __ffs(f) - 1;
+        if (bankElem[k][bA] == (short)cc) { place(e, k, 0); break; }
+        if (bankElem[k][bB] == (short)(cc | 0x8000)) { place(e, k, 1); break; }
+      }
+    }
+    for (int e = 0; e < len; e++) {  // 2. an unused bank
+      if (!(todo >> e & 1u)) continue;
+      const int cc = ec[e], bA = cc & 15, bB = (cc + 8) & 15;
+      for (unsigned f = freeSlots; f; f &= f - 1) {
+        int k = __ffs(f) - 1;
+        if (bankCnt[k][bA] == 0) { place(e, k, 0); break; }
+        if (bankCnt[k][bB] == 0) { place(e, k, 1); break; }
+      }
+    }
+    for (int e = 0; e < len; e++) {  // 3. the least loaded bank
+      if (!(todo >> e & 1u)) continue;
+      const int cc = ec[e];
+      int best = 1 << 30, bk = 0, bc = 0;
+      for (unsigned f = freeSlots; f; f &= f - 1) {
+        int k = __ffs(f) - 1;
+        for (int copy = 0; copy < 2; copy++) {
+          int load = bankCnt[k][(cc + 8 * copy) & 15];
+          if (load < best) { best = load; bk = k; bc = copy; }
+        }
+      }
+      place(e, bk, bc);
+    }
+    for (unsigned f = freeSlots; f; f &= f - 1) {  // padding: 0 * x[some unused bank]
+      int k = __ffs(f) - 1, cc = srow;
+      for (int q = 0; q < 16; q++)
+        if (bankCnt[k][q] == 0 && q < np) { cc = q; break; }
+      const int b = cc & 15;
+      oc[k] = (unsigned short)cc; ov[k] = 0.0;
+      if (bankElem[k][b] != (short)cc) { bankCnt[k][b]++; if (bankElem[k][b] == -1) bankElem[k][b] = (short)cc; }
+    }
+    for (int k = 0; k < K; k++) { ellcol[base + 32LL * k + l] = oc[k]; ellval[base + 32LL * k + l] = ov[k]; }
   }
 }
 
@@ -562,6 +664,17 @@ __global__ void ell_assign_copies(int nparts, const int* __restrict__ pstart, co
 void split_partitions(const Ctx& c, LevelData& L) {
   cudaStream_t s = c.stream;
   const int n = L.n, np = L.nparts;
+  static const bool trace = getenv("FSB_SETUP_TRACE") != nullptr;  // tools: wall-clock of the sub-steps on stderr
+  double tlast = 0.0;
+  auto lap = [&](const char* what) {
+    if (!trace) return;
+    cudaStreamSynchronize(s);
+    timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+    const double now = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    if (tlast > 0.0) fprintf(stderr, "[split L%d] %-12s %8.3f ms\n", L.level_id, what, now - tlast);
+    tlast = now;
+  };
+  lap("start");
   IBuf rowPart(n, s), nin(n, s), nout(n + 1, s), partK(np, s);
   nout.zero(); partK.zero();
   row_partition_kernel<<<cdiv(np, 128), 128, 0, s>>>(np, L.pstart, rowPart);
@@ -573,11 +686,12 @@ void split_partitions(const Ctx& c, LevelData& L) {
   L.Aout.col.alloc(std::max(1, L.Aout.nnz), s); L.Aout.val.alloc(std::max(1, L.Aout.nnz), s);
   fill_out_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, L.A.ptr, L.A.col, L.A.val, rowPart, L.pstart, L.Aout.ptr, L.Aout.col, L.Aout.val);
   L.ellMaxK = reduce_max_i32(partK, np, s);
+  lap("A_out");
   double avg = (double)L.A.nnz / std::max(1, n);
   L.coopG = avg > 192 ? 32 : avg > 96 ? 16 : avg > 48 ? 8 : avg > 16 ? 4 : 2;
   if (const char* g = getenv("FSB_COOP_G")) L.coopG = std::max(1, std::min(32, atoi(g)));  // tuning knob
   L.use_ell = (L.ellMaxK <= 16) || (L.ellMaxK <= 32 && L.maxPartRows <= 512);
-  L.nSmall = L.nBig = 0;
+  for (int q = 0; q < kEllClasses; q++) L.nlist[q] = 0;
   L.smemBytes = 0;
   if (!L.use_ell) {
     // smallest cluster size whose per-CTA slice fits comfortably (two CTAs per SM), else the
@@ -596,33 +710,95 @@ void split_partitions(const Ctx& c, LevelData& L) {
       }
     }
   }
-  if (L.use_ell) {
-    DevBuf<long long> sz((size_t)np + 1, s);
+  // levels that do not take the register-resident kernel: the same sorted slabs with G lanes per row,
+  // kept in shared memory by smooth_sellg_kernel (one CTA per partition)
+  L.ellG = 1;
+  L.use_sellg = false;
+  {
+    static const char* env = getenv("FSB_SELLG");  // tuning knob: 0 = cluster / cooperative kernels instead
+    // (with few partitions the cluster kernel, which spreads a partition over several SMs, is the better fit)
+    if (!L.use_ell && L.maxPartRows <= 1024 && 2 * np >= c.num_sms && !(env && atoi(env) == 0)) {
+      const double meanRows = (double)n / std::max(1, np);
+      int G = 1;
+      const double target = np > c.num_sms ? 512.0 : 1024.0;          // threads of the CTA that will own a partition
+      while (G < 32 && meanRows * (2 * G) <= target * 1.25) G *= 2;   // about one virtual row per thread
+      while (G < 32 && (L.ellMaxK + G - 1) / G > 30) G *= 2;          // at most 32 slots per lane (even-rounded)
+      if ((L.ellMaxK + G - 1) / G <= 30 && (long long)L.maxPartRows * G <= 4 * (long long)target) { L.use_sellg = true; L.ellG = G; }
+    }
+  }
+  lap("cluster_cfg");
+  if (L.use_sellg) L.smemBytes = 0;  // the cluster kernel is not used
+  if (L.use_ell || L.use_sellg) {
+    const int G = L.ellG;
+    // rows of a partition by decreasing intra-partition length (stable radix sort of (partition, 255 - length))
+    DevBuf<uint64_t> k0(n, s), k1(n, s);
+    DevBuf<uint32_t> v0(n, s), order(n, s);
+    sort_key_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, rowPart, nin, k0, v0);
+    sort_pairs_u64_u32(k0, k1, v0, order, n, bits_for(np) + 8, s);
+    DevBuf<unsigned short> pos(n, s);
+    IBuf lenSorted(n, s);
+    L.ellrow.alloc(n, s);
+    sorted_maps_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, order, rowPart, L.pstart, nin, L.ellrow, pos, lenSorted);
+    lap("sort_rows");
+    // warp slabs
+    IBuf wcnt((size_t)np + 1, s);
+    warps_of_partition<<<cdiv(np + 1, 256), 256, 0, s>>>(np, G, L.pstart, wcnt);
+    L.pwarp.alloc((size_t)np + 1, s);
+    exclusive_scan_i32(wcnt, L.pwarp, (size_t)np + 1, s);
+    const int nw = L.pwarp.read(np);
+    L.ellWarps = nw;
+    IBuf warpPart(std::max(1, nw), s);
+    DevBuf<long long> sz((size_t)nw + 1, s);
     sz.zero();
-    slab_size_kernel<<<cdiv(np, 256), 256, 0, s>>>(np, L.pstart, partK, sz);
-    L.ellptr.alloc((size_t)np + 1, s);
+    warp_slab_size<<<cdiv(np, 128), 128, 0, s>>>(np, G, L.pstart, L.pwarp, lenSorted, warpPart, sz);
+    L.ellwptr.alloc((size_t)nw + 1, s);
     void* tmp = nullptr; size_t bytes = 0;
-    FSB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, sz.get(), L.ellptr.get(), np + 1, s));
+    FSB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, sz.get(), L.ellwptr.get(), nw + 1, s));
     FSB_CUDA(cudaMallocAsync(&tmp, bytes, s));
-    FSB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, bytes, sz.get(), L.ellptr.get(), np + 1, s));
+    FSB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, bytes, sz.get(), L.ellwptr.get(), nw + 1, s));
     cudaFreeAsync(tmp, s);
-    long long total = L.ellptr.read(np);
-    L.ellK.swap(partK);
+    const long long total = L.ellwptr.read(nw);
+    L.ellSlots = total;
     L.ellval.alloc((size_t)std::max<long long>(total, 1), s);
     L.ellcol.alloc((size_t)std::max<long long>(total, 1), s);
-    fill_ell_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, L.A.ptr, L.A.col, L.A.val, rowPart, L.pstart, L.ellK, L.ellptr, L.ellval, L.ellcol);
-    {
-      int maxGroups = (L.maxPartRows + 15) / 16;
-      ell_assign_copies<<<cdiv((long long)np * maxGroups, 128), 128, 0, s>>>(np, L.pstart, L.ellK, L.ellptr, L.ellcol, maxGroups);
+    lap("slab_ptrs");
+    fill_ell_kernel<<<cdiv(32LL * nw, 256), 256, 0, s>>>(32LL * nw, G, warpPart, L.pstart, L.pwarp, L.ellwptr, L.ellrow, pos, L.A.ptr, L.A.col, L.A.val,
+                                                         L.ellval, L.ellcol);
+    lap("fill");
+    ell_assign_slots<<<cdiv(2LL * nw, 64), 64, 0, s>>>(nw, G, warpPart, L.pstart, L.pwarp, L.ellwptr, lenSorted, L.ellval, L.ellcol);
+    lap("assign_slots");
+    // per-partition descriptors and the lists by size class (host side: nparts is a few thousand)
+    std::vector<int> ps = L.pstart.to_vector(), pw = L.pwarp.to_vector();
+    std::vector<long long> wp = L.ellwptr.to_vector();
+    if (L.use_ell) {
+      L.ellDescHost.assign(np, EllDesc());
+      std::vector<EllDesc> lists[kEllClasses];
+      for (int p = 0; p < np; p++) {
+        EllDesc& d = L.ellDescHost[p];
+        d.r0 = ps[p]; d.np = ps[p + 1] - ps[p]; d.base = wp[pw[p]];
+        for (int j = 0; j < 32; j++) d.K[j] = (pw[p] + j < pw[p + 1]) ? (unsigned char)((wp[pw[p] + j + 1] - wp[pw[p] + j]) >> 5) : 0;
+        lists[ell_class(d.np)].push_back(d);
+      }
+      for (int q = 0; q < kEllClasses; q++) {
+        L.nlist[q] = (int)lists[q].size();
+        L.plist[q].alloc(std::max<size_t>(1, lists[q].size()), s);
+        if (!lists[q].empty()) L.plist[q].from_host(lists[q].data(), lists[q].size());
+      }
+    } else {
+      std::vector<SellgDesc> dl(np);
+      long long maxSlots = 0;
+      for (int p = 0; p < np; p++) {
+        SellgDesc& d = dl[p];
+        d.r0 = ps[p]; d.np = ps[p + 1] - ps[p]; d.w0 = pw[p]; d.nw = pw[p + 1] - pw[p];
+        d.base = wp[pw[p]]; d.slots = (int)(wp[pw[p + 1]] - wp[pw[p]]); d.pad = 0;
+        maxSlots = std::max<long long>(maxSlots, d.slots);
+      }
+      L.sellgDesc.alloc(std::max(1, np), s);
+      if (np) L.sellgDesc.from_host(dl.data(), np);
+      L.sellgMaxSlots = (int)maxSlots;
     }
-    // partition lists by size class (host side: nparts is a few thousand)
-    std::vector<int> ps = L.pstart.to_vector(), small, big;
-    for (int p = 0; p < np; p++) ((ps[p + 1] - ps[p] <= 256) ? small : big).push_back(p);
-    L.nSmall = (int)small.size(); L.nBig = (int)big.size();
-    L.plistSmall.alloc(std::max<size_t>(1, small.size()), s); L.plistBig.alloc(std::max<size_t>(1, big.size()), s);
-    if (!small.empty()) L.plistSmall.from_host(small.data(), small.size());
-    if (!big.empty()) L.plistBig.from_host(big.data(), big.size());
     FSB_CUDA(cudaStreamSynchronize(s));
+    lap("descriptors");
   }
   FSB_CHECK_LAUNCH();
 }

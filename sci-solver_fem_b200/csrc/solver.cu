@@ -22,6 +22,11 @@ Solver::Solver(int device) {
   FSB_CUDA(cudaGetDeviceProperties(&prop, device));
   ctx.num_sms = prop.multiProcessorCount;
   FSB_CUDA(cudaStreamCreateWithFlags(&ctx.stream, cudaStreamNonBlocking));
+  FSB_CUDA(cudaEventCreateWithFlags(&ctx.ev_fork, cudaEventDisableTiming));
+  for (int q = 0; q < 2; q++) {
+    FSB_CUDA(cudaStreamCreateWithFlags(&ctx.side[q], cudaStreamNonBlocking));
+    FSB_CUDA(cudaEventCreateWithFlags(&ctx.ev_join[q], cudaEventDisableTiming));
+  }
   // keep freed setup temporaries in the pool: setup allocates hundreds of short-lived buffers
   cudaMemPool_t pool;
   FSB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -41,6 +46,11 @@ Solver::~Solver() {
   if (ev1_) cudaEventDestroy(ev1_);
   // buffers are stream-ordered: drain before the stream goes away
   cudaStreamSynchronize(ctx.stream);
+  for (int q = 0; q < 2; q++) {
+    if (ctx.side[q]) { cudaStreamSynchronize(ctx.side[q]); cudaStreamDestroy(ctx.side[q]); }
+    if (ctx.ev_join[q]) cudaEventDestroy(ctx.ev_join[q]);
+  }
+  if (ctx.ev_fork) cudaEventDestroy(ctx.ev_fork);
 }
 
 void Solver::destroy_graph() {
@@ -189,7 +199,9 @@ void Solver::setup() {
     times_ms["setup_permute_split"] += now_ms() - t0; t0 = now_ms();
     build_prolongator(ctx, L.A, L.diag, L.agg.aggregateIdx, L.nnout, prm.proOmega, L.P);
     transpose_csr(ctx, L.P, L.R);
-    if (N >= 32768) {  // streaming copies for the levels where bandwidth (not latency) matters
+    static const int sell_min_rows = getenv("FSB_SELL_MINROWS") ? atoi(getenv("FSB_SELL_MINROWS")) : 32768;  // tuning knob
+    // streaming copies for the levels where bandwidth (not latency) matters; levels with long rows keep the warp-per-row kernels
+    if (N >= sell_min_rows && (double)L.A.nnz <= 24.0 * N) {
       if (L.level_id == 0) build_sell(ctx, L.A, L.sA);
       build_sell(ctx, L.Aout, L.sAout, 1024);  // rows have 0..8 inter-partition entries: sort by length inside 1024-row windows
       build_sell(ctx, L.P, L.sP);

@@ -31,6 +31,22 @@ struct PcgScalars {
   unsigned int ticket[4];
 };
 
+// per-partition descriptor of the shared-memory variant (levels >= 1)
+struct alignas(16) SellgDesc {
+  int r0, np;        // first row / rows of the partition
+  int w0, nw;        // first warp slab / number of warp slabs
+  long long base;    // offset of the first slab (entries)
+  int slots, pad;    // entries of all slabs
+};
+constexpr int kEllClasses = 3;
+// everything a CTA of the fine-level smoother needs to find its slabs, in one 48-byte load
+struct alignas(16) EllDesc {
+  int r0, np;            // first row / rows of the partition
+  long long base;        // offset of the partition's first warp slab (entries)
+  unsigned char K[32];   // slab width of each warp
+};
+inline int ell_class(int rows) { return rows <= 256 ? 0 : rows <= 384 ? 1 : 2; }
+
 struct LevelData {
   int n = 0, nnout = 0, nparts = 0, maxPartRows = 0, level_id = 0;
   DCsr A;             // permuted numbering (rows of a partition contiguous); coarsest: external numbering
@@ -46,14 +62,24 @@ struct LevelData {
   int maxChunkNnz = 0;   // largest number of CSR entries of one CTA's row chunk
   int maxChunkRows = 0;
   int smemBytes = 0;     // > 0: the cluster smoother is usable (chunk fits in shared memory)
-  IBuf plistSmall, plistBig;  // partitions with <= 256 rows / more: two CTA sizes keep occupancy up
-  int nSmall = 0, nBig = 0;
-  IBuf plistSmallOwn, plistBigOwn;  // the same lists restricted to this GPU's partitions (sharded solve)
-  int nSmallOwn = 0, nBigOwn = 0;
-  DevBuf<long long> ellptr;  // nparts+1 slab offsets (entries)
-  IBuf ellK;                 // slab width of each partition
+  // fine-level smoother: partitions by CTA size class (<= 256 / <= 384 / more rows) keep occupancy up
+  DevBuf<EllDesc> plist[kEllClasses];
+  int nlist[kEllClasses] = {0, 0, 0};
+  DevBuf<EllDesc> plistOwn[kEllClasses];  // the same lists restricted to this GPU's partitions (sharded solve)
+  int nlistOwn[kEllClasses] = {0, 0, 0};
+  std::vector<EllDesc> ellDescHost;       // one descriptor per partition (host copy, used to build the lists)
+  // sorted, warp-sliced ELL slabs (hierarchy.cu: split_partitions)
+  bool use_sellg = false;          // sorted slabs with ellG lanes per row, shared-memory resident (smooth_sellg_kernel)
+  int ellG = 1;
+  DevBuf<SellgDesc> sellgDesc;
+  int sellgMaxSlots = 0;
+  DevBuf<unsigned short> ellrow;  // n: local row handled by thread t of the partition's CTA (rows by decreasing length)
+  IBuf pwarp;                     // nparts+1: first warp slab of each partition
+  DevBuf<long long> ellwptr;      // warps+1: slab offsets (entries); width of a slab = (ellwptr[w+1]-ellwptr[w]) / 32
+  int ellWarps = 0;
+  long long ellSlots = 0;         // stored entries (incl. padding)
   DBuf ellval;
-  DevBuf<unsigned short> ellcol;
+  DevBuf<unsigned short> ellcol;  // position of the column in the partition's sorted order; bit 15: copy B of the x tile
   IBuf xadj, adj;     // graph handed to the aggregator (external numbering)
   DBuf b, x, x2, r;   // work vectors, internal numbering
   DBuf bc, xc;        // restricted residual / coarse correction, external numbering of level l+1
