@@ -344,7 +344,7 @@ void sell_dispatch(const Ctx& c, const Sell& A, const double* x, double* y, cons
   const int gran = A.window > 0 ? A.window : 32;
   const int l0 = r0 / gran * gran, l1 = std::min(A.nrows, (r1 + gran - 1) / gran * gran);
   if (l1 <= l0) return;
-  static const int dot_ctas_per_sm = getenv("FSB_DOT_CTAS") ? atoi(getenv("FSB_DOT_CTAS")) : 8;  // tuning knob
+  static const int dot_ctas_per_sm = getenv("FSB_DOT_CTAS") ? atoi(getenv("FSB_DOT_CTAS")) : 12;  // tuning knob
   int blocks = cdiv(l1 - l0, 256);
   if (DOT) blocks = std::min(blocks, c.num_sms * dot_ctas_per_sm);
   FSB_LAUNCH((sell_spmv_kernel<MODE, DOT>), blocks, 256, 0, c.stream, c.dist, r0, r1, l0, l1, A.rowmap.size() ? A.rowmap.get() : nullptr, A.nrows,
