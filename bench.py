@@ -3,8 +3,9 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--cube N]
 
-Workload (BASELINE.json configs[2], the largest single-GPU configuration): Kuhn tet cube with
-`--cube` cells per side (default 118: 1 685 159 DOF, 9 858 192 tets), operator K + M assembled on the
+Workload: Kuhn tet cube with `--cube` cells per side — on one GPU BASELINE.json configs[2] (default 118:
+1 685 159 DOF, 9 858 192 tets), on 2/4/8 GPUs configs[3] (default 255: 16 777 216 DOF, 99 488 250 tets;
+the line then also carries rank 0's single-GPU solve time of that same mesh) — operator K + M assembled on the
 GPU, AMG hierarchy built on the GPU (aggregation seed 0), right-hand side b = A x*, x* the egg-carton
 sin(2 pi x) sin(2 pi y) sin(2 pi z), initial guess 0, FEMSolver defaults + solverType_=1 (PCG),
 tolerance_=1e-8, maxIters_=200.  One STEP = one complete PCG solve from the initial residual to
@@ -18,7 +19,7 @@ tolerance_=1e-8, maxIters_=200.  One STEP = one complete PCG solve from the init
                 on this box's host cores, same workload, one full solve
 
 `--impl reference` times that CPU oracle alone (all host threads) and prints the same line shape.
-Under torchrun (N > 1) the SAME cube is solved by all N GPUs together (strong scaling): setup is
+Under torchrun (N > 1) one cube is solved by all N GPUs together (strong scaling): setup is
 replicated on every GPU, the fine level of the solve is sharded in contiguous partition ranges, halo
 values and dot products travel over NVLink peer memory.
 """
@@ -175,7 +176,10 @@ def reference_arm(args):
     if rank != 0:
         return 0
     N = args.cube
-    r = run_oracle(N, args.steps, args.warmup)
+    steps, warmup = args.steps, args.warmup
+    if N > 160:  # bounded sample of the ~100M-tet workload: one complete solve (about 1.5 min of CPU work with the setup)
+        steps, warmup = 1, 0
+    r = run_oracle(N, steps, warmup)
     value = r["n"] / r["t_solve"]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -184,7 +188,7 @@ def reference_arm(args):
         "config": {"workload": workload_name(N), "iterations": r["iters"], "relres": r["relres"], "rel_l2_err_vs_exact": r["err"],
                    "setup_s": r["t_setup"], "assemble_s": r["t_assemble"], "pattern_s": r["t_pattern"]},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["threads"], "kind": "port",
-                         "sample": f"full workload, {args.steps} complete PCG solves (setup excluded), CPU oracle = restatement of the reference "
+                         "sample": f"full workload, {steps} complete PCG solve(s) (setup excluded), CPU oracle = restatement of the reference "
                                    "(its CUDA-only build needs CUSP + METIS 4 at configure time; not producible offline)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -215,10 +219,11 @@ def ours(args):
     s.solverType_, s.tolerance_, s.maxIters_, s.seed_ = 1, 1e-8, 200, 0
     t_pattern_cold = s.time_ms("pattern")   # first GPU work of the process: includes pool growth / module load
     t_pattern = t_assemble = t_setup = float("inf")
-    for _ in range(3):                       # steady-state stage timings: best of 3 rebuilds (allocator pool warm)
+    rebuilds = 3 if N <= 160 else 1
+    for _ in range(rebuilds):                # steady-state stage timings: best of 3 rebuilds (allocator pool warm)
         s.getMatrixFromMesh()
         t_pattern, t_assemble = min(t_pattern, s.time_ms("pattern")), min(t_assemble, s.time_ms("assemble"))
-    for _ in range(3):
+    for _ in range(rebuilds):
         s.setup()
         t_setup = min(t_setup, s.time_ms("setup"))
     nnz = s._L.fsb_matrix_nnz(s.handle)
@@ -235,7 +240,17 @@ def ours(args):
     x_dev = torch.zeros(n, dtype=torch.float64, device="cuda")
     stream = torch.cuda.ExternalStream(s._L.fsb_stream(s.handle))
     torch.cuda.synchronize()
+    ms_single = None
     if world > 1:
+        # the hierarchy is replicated, so every GPU can also solve the whole system alone: rank 0 times that
+        # (same mesh, same build, same run) as the strong-scaling reference of this line
+        if rank == 0:
+            for i in range(2):
+                with torch.cuda.stream(stream):
+                    x_dev.zero_()
+                s.solve_device(x_dev.data_ptr(), b_dev.data_ptr())
+            ms_single = s.time_ms("solve")
+        dist.barrier()
         s.dist_connect(rank, world, fsb.exchange_handles_torch)
         pb, rb, ab = s.dist_ranges()
         log(f"[rank {rank}] owns partitions [{pb[rank]},{pb[rank+1]}) rows [{rb[rank]},{rb[rank+1]})")
@@ -353,6 +368,8 @@ def ours(args):
                        "iterations": iters, "relres": relres, "rel_l2_err_vs_exact": err, "levels": levels,
                        "pattern_ms": t_pattern, "pattern_cold_ms": t_pattern_cold, "assemble_ms": t_assemble, "setup_ms": t_setup, "solveFEM_host_ms": None if t_solvefem != t_solvefem else t_solvefem * 1e3,
                        "wall_ms_per_step": wall_dev,
+                       "single_gpu_same_mesh_ms": ms_single,
+                       "speedup_vs_single_gpu_same_mesh": (ms_single / ms_dev) if ms_single else None,
                        "dofs_per_s_incl_assembly_and_setup": n / ((t_pattern + t_assemble + t_setup + ms_dev) * 1e-3)},
             "e2e": {"value": n / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 8 * n,
                     "ms_per_step": ms_e2e, "call": "fsb_solve (host b/x0 in pinned memory -> x)"},
@@ -375,9 +392,12 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cube", type=int, default=118)
+    ap.add_argument("--cube", type=int, default=None,
+                    help="cells per side; default 118 (BASELINE configs[2], ~10M tets) on one GPU, 255 (configs[3], ~100M tets) on 2/4/8 GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.cube is None:
+        args.cube = 118 if args.gpus <= 1 and int(os.environ.get("WORLD_SIZE", "1")) <= 1 else 255
     if args.impl == "reference":
         return reference_arm(args)
     return ours(args)
