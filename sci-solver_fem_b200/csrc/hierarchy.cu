@@ -715,9 +715,11 @@ void split_partitions(const Ctx& c, LevelData& L) {
   L.ellG = 1;
   L.use_sellg = false;
   {
-    static const char* env = getenv("FSB_SELLG");  // tuning knob: 0 = cluster / cooperative kernels instead
+    // tuning / test knob, read at every setup: 0 = cluster or cooperative kernels instead, 2 = also on levels with few partitions
+    const char* env = getenv("FSB_SELLG");
+    const int mode = env ? atoi(env) : 1;
     // (with few partitions the cluster kernel, which spreads a partition over several SMs, is the better fit)
-    if (!L.use_ell && L.maxPartRows <= 1024 && 2 * np >= c.num_sms && !(env && atoi(env) == 0)) {
+    if (!L.use_ell && L.maxPartRows <= 1024 && (2 * np >= c.num_sms || mode == 2) && mode != 0) {
       const double meanRows = (double)n / std::max(1, np);
       int G = 1;
       const double target = np > c.num_sms ? 512.0 : 1024.0;          // threads of the CTA that will own a partition

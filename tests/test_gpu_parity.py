@@ -263,6 +263,25 @@ def test_large_levels_use_streaming_formats():
     assert rel(xg, xo) <= 1e-6
 
 
+@pytest.mark.parametrize("mode", ["2", "0"])
+def test_coarse_level_smoother_variants(mode, monkeypatch):
+    """Levels >= 1 pick their smoother kernel by size (shared-memory sorted-ELL kernel when there are many
+    partitions, CTA-cluster kernel when there are few); FSB_SELLG forces one or the other at setup time.
+    Whatever the kernel, V-cycle and PCG must agree with the oracle."""
+    monkeypatch.setenv("FSB_SELLG", mode)
+    v, t = kuhn(32)
+    o, s, nl = _setup_pair(v, t, **PCG)
+    assert nl >= 3
+    b = o.spmv(egg_carton(v))
+    xo, ito = o.solve(b)
+    xg = s.solve(np.zeros_like(b), b)
+    assert abs(s.iterations - ito) <= 2, (s.iterations, ito)
+    assert rel(xg, xo) <= 1e-6
+    ho, hg = o.resid_history(), s.resid_history()
+    m = min(len(ho), len(hg))
+    assert np.allclose(hg[:m], ho[:m], rtol=1e-6)
+
+
 def test_metis_bottom_up_aggregator():
     """aggregatorType_ = 1 (CP::MetisBottomUp): oracle and CUDA path call the same METIS 5 entry point,
     so aggregates / partitions must again be bit-exact; partitionMaxSize_ packs fineSize*1000 + coarseSize."""
