@@ -601,8 +601,10 @@ __global__ void ell_assign_slots(int nwarps, int G, const int* __restrict__ warp
   const long long base = wptr[w] + 16 * h;
   short bankElem[32][16];          // first address (column | copy << 15) assigned to the bank, -1 = unused
   unsigned char bankCnt[32][16];   // distinct addresses in the bank
+  unsigned occ[16];                // per bank: slots in which it is already used (bit k <=> bankCnt[k][bank] > 0)
   for (int k = 0; k < K; k++)
     for (int q = 0; q < 16; q++) { bankElem[k][q] = -1; bankCnt[k][q] = 0; }
+  for (int q = 0; q < 16; q++) occ[q] = 0u;
   for (int l = 0; l < nl; l++) {
     const int srow = (t0 + l) / G, g = (t0 + l) % G;
     const int len = min(max(lenSorted[r0 + srow] - g + G - 1, 0) / G, K);
@@ -615,23 +617,23 @@ __global__ void ell_assign_slots(int nwarps, int G, const int* __restrict__ warp
       const short addr = (short)(cc | (copy << 15));
       oc[k] = (unsigned short)addr; ov[k] = ev[e];
       freeSlots &= ~(1u << k); todo &= ~(1u << e);
-      if (bankElem[k][b] != addr) { bankCnt[k][b]++; if (bankElem[k][b] == -1) bankElem[k][b] = addr; }
+      if (bankElem[k][b] != addr) { bankCnt[k][b]++; occ[b] |= 1u << k; if (bankElem[k][b] == -1) bankElem[k][b] = addr; }
     };
-    for (int e = 0; e < len; e++) {  // 1. share an address with an earlier lane
+    for (int e = 0; e < len; e++) {  // 1. share an address with an earlier lane (only slots whose bank is in use can match)
       const int cc = ec[e], bA = cc & 15, bB = (cc + 8) & 15;
-      for (unsigned f = freeSlots; f; f &= f - 1) {
+      for (unsigned f = freeSlots & (occ[bA] | occ[bB]); f; f &= f - 1) {
         int k = __ffs(f) - 1;
         if (bankElem[k][bA] == (short)cc) { place(e, k, 0); break; }
         if (bankElem[k][bB] == (short)(cc | 0x8000)) { place(e, k, 1); break; }
       }
     }
-    for (int e = 0; e < len; e++) {  // 2. an unused bank
+    for (int e = 0; e < len; e++) {  // 2. an unused bank: the lowest free slot in which copy A's or copy B's bank is unused
       if (!(todo >> e & 1u)) continue;
       const int cc = ec[e], bA = cc & 15, bB = (cc + 8) & 15;
-      for (unsigned f = freeSlots; f; f &= f - 1) {
-        int k = __ffs(f) - 1;
-        if (bankCnt[k][bA] == 0) { place(e, k, 0); break; }
-        if (bankCnt[k][bB] == 0) { place(e, k, 1); break; }
+      const unsigned fa = freeSlots & ~occ[bA], fb = freeSlots & ~occ[bB];
+      if (fa | fb) {
+        const int k = __ffs(fa | fb) - 1;
+        place(e, k, (fa >> k & 1u) ? 0 : 1);
       }
     }
     for (int e = 0; e < len; e++) {  // 3. the least loaded bank
@@ -650,10 +652,10 @@ __global__ void ell_assign_slots(int nwarps, int G, const int* __restrict__ warp
     for (unsigned f = freeSlots; f; f &= f - 1) {  // padding: 0 * x[some unused bank]
       int k = __ffs(f) - 1, cc = srow;
       for (int q = 0; q < 16; q++)
-        if (bankCnt[k][q] == 0 && q < np) { cc = q; break; }
+        if (!(occ[q] >> k & 1u) && q < np) { cc = q; break; }
       const int b = cc & 15;
       oc[k] = (unsigned short)cc; ov[k] = 0.0;
-      if (bankElem[k][b] != (short)cc) { bankCnt[k][b]++; if (bankElem[k][b] == -1) bankElem[k][b] = (short)cc; }
+      if (bankElem[k][b] != (short)cc) { bankCnt[k][b]++; occ[b] |= 1u << k; if (bankElem[k][b] == -1) bankElem[k][b] = (short)cc; }
     }
     for (int k = 0; k < K; k++) { ellcol[base + 32LL * k + l] = oc[k]; ellval[base + 32LL * k + l] = ov[k]; }
   }
