@@ -306,6 +306,15 @@ __global__ void __launch_bounds__(256) sell_spmv_kernel(DistDev dist, int row_be
       const int* cp = col + base + lane;
       const double* vp = val + base + lane;
       int k = 0;
+      for (; k + 8 <= K; k += 8) {  // eight (col, val) -> x chains in flight
+        int c[8]; double v[8], xv[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) { c[u] = __ldg(cp + (k + u) * 32); v[u] = __ldg(vp + (k + u) * 32); }
+#pragma unroll
+        for (int u = 0; u < 8; u++) xv[u] = __ldg(x + c[u]);
+#pragma unroll
+        for (int u = 0; u < 8; u++) acc += v[u] * xv[u];
+      }
       for (; k + 4 <= K; k += 4) {
         const int c0 = __ldg(cp + k * 32), c1 = __ldg(cp + (k + 1) * 32), c2 = __ldg(cp + (k + 2) * 32), c3 = __ldg(cp + (k + 3) * 32);
         const double v0 = __ldg(vp + k * 32), v1 = __ldg(vp + (k + 1) * 32), v2 = __ldg(vp + (k + 2) * 32), v3 = __ldg(vp + (k + 3) * 32);
