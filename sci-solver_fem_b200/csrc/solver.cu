@@ -34,6 +34,8 @@ Solver::Solver(int device) {
   FSB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
   FSB_CUDA(cudaEventCreate(&ev0_));
   FSB_CUDA(cudaEventCreate(&ev1_));
+  FSB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&poll_host_), 2 * sizeof(PcgScalars)));
+  for (int q = 0; q < 2; q++) FSB_CUDA(cudaEventCreateWithFlags(&poll_ev_[q], cudaEventDisableTiming));
   prm.device = device;
   ctx.prof = &profiler;
 }
@@ -44,6 +46,8 @@ Solver::~Solver() {
   levels.clear();
   if (ev0_) cudaEventDestroy(ev0_);
   if (ev1_) cudaEventDestroy(ev1_);
+  for (int q = 0; q < 2; q++) if (poll_ev_[q]) cudaEventDestroy(poll_ev_[q]);
+  if (poll_host_) cudaFreeHost(poll_host_);
   // buffers are stream-ordered: drain before the stream goes away
   cudaStreamSynchronize(ctx.stream);
   for (int q = 0; q < 2; q++) {
@@ -383,19 +387,32 @@ void Solver::pcg(const double* b_user, double* x_user) {
     g_launch_counter = before;
   }
   const long long per_iter = iter_launches_;
+  // Convergence polling without pipeline bubbles: chunk i+1 is enqueued before the host waits for the scalars
+  // of chunk i (pinned double buffer + events), so the GPU never idles for a host round trip; once the
+  // device has set `done`, the kernels of an already enqueued chunk exit at their first instruction.
   PcgScalars h;
   int enq = 0;
   const int chunk = std::max(1, prm.checkEvery);
-  while (true) {
+  auto enqueue_chunk = [&](int slot) {
     for (int i = 0; i < chunk; i++) {
       if (iter_graph_) { FSB_CUDA(cudaGraphLaunch(iter_graph_, s)); g_launch_counter += per_iter; }
       else enqueue_pcg_iteration();
       enq++;
     }
-    FSB_CUDA(cudaMemcpyAsync(&h, sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, s));
-    FSB_CUDA(cudaStreamSynchronize(s));
-    if (h.done || enq > prm.maxIters + chunk) break;
+    FSB_CUDA(cudaMemcpyAsync(&poll_host_[slot], sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, s));
+    FSB_CUDA(cudaEventRecord(poll_ev_[slot], s));
+  };
+  int slot = 0;
+  enqueue_chunk(slot);
+  while (true) {
+    const bool more = enq <= prm.maxIters + chunk;
+    if (more) enqueue_chunk(slot ^ 1);
+    FSB_CUDA(cudaEventSynchronize(poll_ev_[slot]));
+    h = poll_host_[slot];
+    if (h.done || !more) break;
+    slot ^= 1;
   }
+  FSB_CUDA(cudaStreamSynchronize(s));
   iterations = h.niter;
   resid_history.resize(h.hist_len);
   if (h.hist_len) hist.to_host(resid_history.data(), h.hist_len);

@@ -157,6 +157,8 @@ class Solver {
   void tic(const char* name);
   void toc(const char* name);
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+  PcgScalars* poll_host_ = nullptr;            // pinned double buffer of the convergence poll
+  cudaEvent_t poll_ev_[2] = {nullptr, nullptr};
   // PCG state
   DBuf cg_b, cg_x, cg_r, cg_z, cg_p, cg_y, partials, hist;
   DevBuf<PcgScalars> scal;
