@@ -30,6 +30,7 @@ SOURCES = {
     "aggregation.cu": [],
     "hierarchy.cu": ["-fmad=false"],
     "cycle.cu": [],
+    "dense_tail.cu": [],
     "solver.cu": [],
     "dist.cu": [],
     "capi.cu": [],
@@ -71,7 +72,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
         list(ex.map(run, jobs))
     if jobs or force or not os.path.exists(LIB):
-        run([NVCC] + ARCH + ["-shared", "-o", LIB] + objs + [METIS, "-lcudart"])
+        run([NVCC] + ARCH + ["-shared", "-o", LIB] + objs + [METIS, "-lcudart", "-lcublas"])
     return LIB
 
 

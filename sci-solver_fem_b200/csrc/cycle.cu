@@ -893,17 +893,40 @@ __global__ void __launch_bounds__(256) spmv_vector_kernel(int row_begin, int n, 
   }
 }
 
-// x = Ainv b, dense, n < topSize_ (replaces the host LU round trip of amg_level.cu:25-31)
+// x = M b, dense, warp per row: the coarsest level's inverse (replaces the host LU round trip of amg_level.cu:25-31)
+// or the dense tail of the V-cycle (dense_tail.cu)
 __global__ void __launch_bounds__(256) coarse_gemv_kernel(int n, const double* __restrict__ Ainv, const double* __restrict__ b,
                                                           double* __restrict__ x, const int* __restrict__ done) {
   pdl_wait();
   if (done && *done) return;
   int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= n) return;
-  double s = 0.0;
-  for (int j = lane; j < n; j += 32) s += Ainv[(size_t)row * n + j] * b[j];
-  s = warp_sum(s);
+  // four independent strided chains per lane (fixed order): the loads of a row overlap
+  const double* a = Ainv + (size_t)row * n;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int j = lane;
+  for (; j + 96 < n; j += 128) { s0 += a[j] * b[j]; s1 += a[j + 32] * b[j + 32]; s2 += a[j + 64] * b[j + 64]; s3 += a[j + 96] * b[j + 96]; }
+  for (; j < n; j += 32) s0 += a[j] * b[j];
+  const double s = warp_sum((s0 + s1) + (s2 + s3));
   if (lane == 0) x[row] = s;
+}
+
+// same product for the larger dense tail (n in the thousands): one 128-thread CTA per row, every load independent
+__global__ void __launch_bounds__(128) coarse_gemv_row_kernel(int n, const double* __restrict__ M, const double* __restrict__ b,
+                                                              double* __restrict__ x, const int* __restrict__ done) {
+  pdl_wait();
+  __shared__ double s_warp[4];
+  if (done && *done) return;
+  const int row = blockIdx.x, t = threadIdx.x;
+  const double* a = M + (size_t)row * n;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int j = t;
+  for (; j + 384 < n; j += 512) { s0 += a[j] * b[j]; s1 += a[j + 128] * b[j + 128]; s2 += a[j + 256] * b[j + 256]; s3 += a[j + 384] * b[j + 384]; }
+  for (; j < n; j += 128) s0 += a[j] * b[j];
+  const double w = warp_sum((s0 + s1) + (s2 + s3));
+  if ((t & 31) == 0) s_warp[t >> 5] = w;
+  __syncthreads();
+  if (t == 0) x[row] = (s_warp[0] + s_warp[1]) + (s_warp[2] + s_warp[3]);
 }
 
 // ------------------------------------------------------------------ PCG vector kernels
@@ -1131,7 +1154,8 @@ void debug_stamps(int cta_plus1, long long* out64) {
 void launch_coarse_solve(const Ctx& c, int n, const double* Ainv, const double* b, double* x, const int* done) {
   g_launch_counter++;
   ProfScope ps(c, "coarse_solve");
-  FSB_LAUNCH((coarse_gemv_kernel), cdiv(n, 8), 256, 0, c.stream, n, Ainv, b, x, done);
+  if (n >= 512) FSB_LAUNCH((coarse_gemv_row_kernel), n, 128, 0, c.stream, n, Ainv, b, x, done);
+  else FSB_LAUNCH((coarse_gemv_kernel), cdiv(n, 8), 256, 0, c.stream, n, Ainv, b, x, done);
   FSB_CHECK_LAUNCH();
 }
 

@@ -43,6 +43,7 @@ Solver::Solver(int device) {
 Solver::~Solver() {
   try { dist_disconnect(); } catch (...) {}
   destroy_graph();
+  destroy_cublas();
   levels.clear();
   if (ev0_) cudaEventDestroy(ev0_);
   if (ev1_) cudaEventDestroy(ev1_);
@@ -229,6 +230,11 @@ void Solver::setup() {
     levels.push_back(std::move(nx));
     num_levels++;
   }
+  {
+    double t0 = now_ms();
+    build_dense_tail();
+    times_ms["setup_dense_tail"] = now_ms() - t0;
+  }
   toc("setup");
   has_setup = true;
 }
@@ -243,6 +249,10 @@ void Solver::vcycle(int lev, const double* b_src, const int* gather, double* x_d
   profiler.cur_level = lev;
   if (lev == (int)levels.size() - 1) {  // coarsest: direct solve (amg_level.cu:25-31)
     launch_coarse_solve(ctx, L.n, Ainv, b_src, x_dst, done);
+    return;
+  }
+  if (lev == tail_level_) {  // this level and everything below it: one dense GEMV (dense_tail.cu)
+    launch_coarse_solve(ctx, L.n, Mtail, b_src, x_dst, done);
     return;
   }
   const double w = prm.smootherWeight;
@@ -299,8 +309,18 @@ void Solver::apply_matrix(const double* x, double* y) {
 
 void Solver::spmv_fine(const double* x, double* y) { launch_spmv(ctx, levels.at(0).A, x, y, 0, nullptr, nullptr, "spmv"); FSB_CUDA(cudaStreamSynchronize(ctx.stream)); }
 
+// the dense tail encodes the smoother parameters: rebuild it when they changed since setup()
+void Solver::ensure_dense_tail() {
+  if (tail_level_ >= 0 && (tail_key_[0] != prm.preInnerIters || tail_key_[1] != prm.postInnerIters || tail_key_[2] != prm.postRelaxes ||
+                           tail_key_[3] != prm.smootherWeight)) {
+    build_dense_tail();
+    destroy_graph();
+  }
+}
+
 void Solver::precondition(const double* r, double* z) {
   if (!has_setup) throw std::runtime_error("precondition before setup");
+  ensure_dense_tail();
   cg_active_ = false;
   vcycle(0, r, nullptr, z, nullptr, nullptr);
   FSB_CUDA(cudaStreamSynchronize(ctx.stream));
@@ -432,6 +452,7 @@ void Solver::solve(const double* b, double* x, bool on_device) {
   FSB_CUDA(cudaSetDevice(ctx.device));
   cudaStream_t s = ctx.stream;
   const int n = levels[0].n;
+  ensure_dense_tail();
   g_launch_counter = 0;
   profiler.clear();
   profiler.on = prm.profile != 0;

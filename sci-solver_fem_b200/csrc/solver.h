@@ -148,6 +148,15 @@ class Solver {
   bool custom_matrix = false;
   std::vector<LevelData> levels;
   DBuf Ainv;                            // dense inverse of the coarsest operator
+  // dense tail (dense_tail.cu): one V-cycle on level tail_level_ (and everything below it) as a dense matrix
+  static constexpr int kDenseTailMaxRows = 3072;
+  DBuf Mtail;
+  int tail_level_ = -1;
+  double tail_key_[4] = {0, 0, 0, 0};    // smoother parameters Mtail was built for
+  void* cublas_ = nullptr;
+  void build_dense_tail();
+  void ensure_dense_tail();
+  void destroy_cublas();
   bool has_setup = false;
 
  private:

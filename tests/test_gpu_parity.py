@@ -282,6 +282,30 @@ def test_coarse_level_smoother_variants(mode, monkeypatch):
     assert np.allclose(hg[:m], ho[:m], rtol=1e-6)
 
 
+def test_dense_tail_equals_the_kernel_cycle(monkeypatch):
+    """Levels below a few thousand rows are applied as one dense matrix (csrc/dense_tail.cu).  That matrix is the
+    V-cycle's own linear map, so switching it off (FSB_DENSE_TAIL=0: smoother / transfer kernels on every level)
+    must give the same iterates up to rounding, for the default and for non-default smoother parameters."""
+    v, t = kuhn(28)
+    b = egg_carton(v) + 0.25
+    out = {}
+    for mode in ("0", "3072"):
+        monkeypatch.setenv("FSB_DENSE_TAIL", mode)
+        s = make_gpu(v, t, **PCG)
+        s.setup()
+        assert s.num_levels() >= 3
+        x = s.solve(np.zeros_like(b), b)
+        h = np.array(s.resid_history())
+        s.preInnerIters_, s.postInnerIters_, s.postRelaxes_, s.smootherWeight_ = 3, 2, 2, 0.9   # rebuilt lazily at the next solve
+        x2 = s.solve(np.zeros_like(b), b)
+        out[mode] = (x, s.iterations, h, x2, np.array(s.resid_history()))
+    (xa, ita, ha, xa2, ha2), (xb, itb, hb, xb2, hb2) = out["0"], out["3072"]
+    assert len(ha) == len(hb) and np.allclose(ha, hb, rtol=1e-8)
+    assert rel(xa, xb) <= 1e-12
+    assert len(ha2) == len(hb2) and np.allclose(ha2, hb2, rtol=1e-8)
+    assert rel(xa2, xb2) <= 1e-12
+
+
 def test_metis_bottom_up_aggregator():
     """aggregatorType_ = 1 (CP::MetisBottomUp): oracle and CUDA path call the same METIS 5 entry point,
     so aggregates / partitions must again be bit-exact; partitionMaxSize_ packs fineSize*1000 + coarseSize."""
