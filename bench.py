@@ -182,8 +182,8 @@ def reference_arm(args):
     r = run_oracle(N, steps, warmup)
     value = r["n"] / r["t_solve"]
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": r["t_solve"] * 1e3, "higher_is_better": True, "scaling": "strong",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": r["t_solve"] * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(N), "iterations": r["iters"], "relres": r["relres"], "rel_l2_err_vs_exact": r["err"],
                    "setup_s": r["t_setup"], "assemble_s": r["t_assemble"], "pattern_s": r["t_pattern"]},
