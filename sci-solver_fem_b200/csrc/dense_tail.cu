@@ -19,6 +19,7 @@
 // order of the floating-point sums (differences ~1e-16 relative; iteration counts unchanged).
 #include <cublas_v2.h>
 
+#include <cstdio>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -195,22 +196,31 @@ void Solver::build_dense_tail() {
   for (int l = 1; l < last; l++)
     if (levels[l].n <= limit) { lt = l; break; }
   if (lt < 0) return;
-  if (!cublas_) {
-    cublasHandle_t h;
-    FSB_CUBLAS(cublasCreate(&h));
-    cublas_ = h;
+  // The tail is an optimisation of levels that the smoother / transfer kernels can also run: if cuBLAS is not
+  // usable (library missing, out of memory for the n x n temporaries) the solve keeps those kernels.
+  try {
+    if (!cublas_) {
+      cublasHandle_t h;
+      FSB_CUBLAS(cublasCreate(&h));
+      cublas_ = h;
+    }
+    cublasHandle_t h = static_cast<cublasHandle_t>(cublas_);
+    FSB_CUBLAS(cublasSetStream(h, ctx.stream));
+    FSB_CUBLAS(cublasSetPointerMode(h, CUBLAS_POINTER_MODE_HOST));
+    DBuf Mcur;  // operator of the level below, external numbering (coarsest: the dense inverse)
+    for (int l = last - 1; l >= lt; l--) {
+      DBuf Mnew;
+      level_operator(ctx, h, levels[l], prm, l == last - 1 ? Ainv : Mcur, Mnew);
+      Mcur.swap(Mnew);
+    }
+    Mtail.swap(Mcur);
+    tail_level_ = lt;
+  } catch (const std::exception& e) {
+    cudaGetLastError();
+    if (prm.verbose) fprintf(stderr, "dense tail not built (%s): levels >= %d keep their kernels\n", e.what(), lt);
+    tail_level_ = -1;
+    Mtail.release();
   }
-  cublasHandle_t h = static_cast<cublasHandle_t>(cublas_);
-  FSB_CUBLAS(cublasSetStream(h, ctx.stream));
-  FSB_CUBLAS(cublasSetPointerMode(h, CUBLAS_POINTER_MODE_HOST));
-  DBuf Mcur;  // operator of the level below, external numbering (coarsest: the dense inverse)
-  for (int l = last - 1; l >= lt; l--) {
-    DBuf Mnew;
-    level_operator(ctx, h, levels[l], prm, l == last - 1 ? Ainv : Mcur, Mnew);
-    Mcur.swap(Mnew);
-  }
-  Mtail.swap(Mcur);
-  tail_level_ = lt;
   tail_key_[0] = prm.preInnerIters; tail_key_[1] = prm.postInnerIters; tail_key_[2] = prm.postRelaxes; tail_key_[3] = prm.smootherWeight;
 }
 
