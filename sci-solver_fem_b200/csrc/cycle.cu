@@ -299,6 +299,15 @@ __global__ void __launch_bounds__(256) sell_spmv_kernel(DistDev dist, int row_be
   double contrib = 0.0;
   for (int i = list_begin + blockIdx.x * blockDim.x + threadIdx.x; (i & ~31) < list_end; i += gridDim.x * blockDim.x) {
     const int slice = i >> 5;
+    // the row's own vector entries travel together with the matrix stream instead of after it
+    const int row = (i < n) ? (rowmap ? __ldg(rowmap + i) : i) : -1;
+    const bool mine = row >= row_begin && row < row_end;
+    double own = 0.0;
+    if (mine) {
+      if (MODE == 1) own = b[row];
+      else if (MODE >= 2) own = y[row];
+      else if (DOT) own = x[row];
+    }
     double acc = 0.0;
     if (slice < nslices) {
       const long long base = __ldg(sptr + slice);
@@ -323,13 +332,12 @@ __global__ void __launch_bounds__(256) sell_spmv_kernel(DistDev dist, int row_be
       }
       for (; k < K; k++) acc += __ldg(vp + k * 32) * __ldg(x + __ldg(cp + k * 32));
     }
-    const int row = (i < n) ? (rowmap ? __ldg(rowmap + i) : i) : -1;
-    if (row >= row_begin && row < row_end) {
+    if (mine) {
       if (MODE == 0) y[row] = acc;
-      else if (MODE == 1) y[row] = b[row] - acc;
-      else if (MODE == 2) y[row] = y[row] + acc;
-      else y[row] = y[row] - acc;
-      if (DOT) contrib += x[row] * acc;
+      else if (MODE == 1) y[row] = own - acc;
+      else if (MODE == 2) y[row] = own + acc;
+      else y[row] = own - acc;
+      if (DOT) contrib += own * acc;
     }
   }
   if (DOT) {
