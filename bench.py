@@ -303,7 +303,9 @@ def ours(args):
     # a rebuild ends the sharded mode)
     t_solvefem = float("nan")
     if world == 1:
-        t0 = time.perf_counter(); x_host.zero_(); s.solveFEM(x_host.numpy(), b_host.numpy()); t_solvefem = time.perf_counter() - t0
+        t_solvefem = float("inf")
+        for _ in range(2):  # steady state, like the stage timings above (the first rebuild after a solve re-grows pools)
+            t0 = time.perf_counter(); x_host.zero_(); s.solveFEM(x_host.numpy(), b_host.numpy()); t_solvefem = min(t_solvefem, time.perf_counter() - t0)
 
     # roofline pass: one profiled solve (CUDA events around every kernel; graphs off)
     s.profile_ = 1
