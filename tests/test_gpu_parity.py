@@ -307,6 +307,31 @@ def test_dense_tail_equals_the_kernel_cycle(monkeypatch):
     assert rel(xa2, xb2) <= 1e-12
 
 
+def test_config3_matches_the_oracle_golden():
+    """BASELINE configs[2] at full size (N=118, 1 685 159 DOF): the oracle's solve is stored as a golden fixture
+    (tests/golden/make_oracle_golden.py), so the comparison at this scale needs no CPU solve on the GPU box."""
+    import json, os
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "oracle_cube118_pcg.json")))
+    v, t = kuhn(g["cube"])
+    s = make_gpu(v, t, **PCG)
+    s.setup()
+    assert [s.level_rows(l) for l in range(s.num_levels())] == g["levels"]   # same aggregates => same level sizes
+    xstar = egg_carton(v)
+    import scipy.sparse as sp
+    ptr, col, val = s.matrix_csr()
+    b = sp.csr_matrix((val, col, ptr)) @ xstar
+    assert abs(np.linalg.norm(b) - g["b_norm2"]) <= 1e-12 * g["b_norm2"]
+    x = s.solve(np.zeros_like(b), b)
+    assert abs(s.iterations - g["iterations"]) <= 2, (s.iterations, g["iterations"])
+    h = np.array(s.resid_history())
+    ho = np.array(g["resid_history"])
+    m = min(len(h), len(ho))
+    assert np.allclose(h[:m], ho[:m], rtol=1e-6), "residual history differs from the oracle's"
+    assert abs(np.linalg.norm(x) - g["x_norm2"]) <= 1e-8 * g["x_norm2"]
+    assert np.allclose(x[g["sample_idx"]], g["x_samples"], rtol=1e-6, atol=1e-9)
+    assert rel(x, xstar) <= 2 * g["err_vs_exact"] + 1e-12
+
+
 def test_metis_bottom_up_aggregator():
     """aggregatorType_ = 1 (CP::MetisBottomUp): oracle and CUDA path call the same METIS 5 entry point,
     so aggregates / partitions must again be bit-exact; partitionMaxSize_ packs fineSize*1000 + coarseSize."""
