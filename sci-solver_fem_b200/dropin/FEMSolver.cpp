@@ -140,11 +140,12 @@ static void check(fsb_solver* s, int rc) {
 }
 
 FEMSolver::FEMSolver(std::string fname, bool isTetMesh, bool verbose)
-    : verbose_(verbose), filename_(fname), maxLevels_(100), maxIters_(100), preInnerIters_(5), postInnerIters_(5), postRelaxes_(1),
-      cycleIters_(1), dsType_(0), topSize_(256), randMisParameters_(90102), partitionMaxSize_(512), aggregatorType_(0),
-      convergeType_(0), tolerance_(1e-6), cycleType_(0), solverType_(0), smootherWeight_(1.0), proOmega_(0.67), device_(0),
-      blockSize_(256), tetMesh_(NULL), triMesh_(NULL), seed_(0), refLevel0NoPerm_(0), iterations_(0), relres_(-1), impl_(NULL),
-      A_from_file_(false) {
+    : filename_(fname), tetMesh_(NULL), triMesh_(NULL), verbose_(verbose), device_(0),
+      maxLevels_(100), topSize_(256), aggregatorType_(0), randMisParameters_(90102), partitionMaxSize_(512), proOmega_(0.67),
+      preInnerIters_(5), postInnerIters_(5), postRelaxes_(1), smootherWeight_(1.0), dsType_(0),
+      solverType_(0), maxIters_(100), tolerance_(1e-6),
+      cycleIters_(1), cycleType_(0), convergeType_(0), blockSize_(256),
+      seed_(0), refLevel0NoPerm_(0), iterations_(0), relres_(-1), impl_(NULL), A_from_file_(false) {
   if (fsb_create(&impl_, device_) != FSB_OK) {
     std::cerr << "FEMSolver (B200): " << fsb_last_error(NULL) << std::endl;
     exit(1);

@@ -114,3 +114,22 @@ def test_kuhn_cube_counts_and_orientation():
     assert np.all(vol > 0) and abs(vol.sum() - 1) < 1e-6
     lab = meshio.kuhn_cell_labels(16, block=8)
     assert lab.shape == (6 * 16 ** 3,) and set(np.unique(lab)) <= set(range(1, 7))
+
+
+def test_upstream_callers_compile_against_the_dropin_headers(tmp_path):
+    """Source compatibility of the drop-in layer: the reference's own example and gtest sources are compiled
+    (syntax + types only, in place, nothing copied) against dropin/FEMSolver.h and the gtest shim.  Needs the
+    read-only reference checkout, so it is skipped on the GPU box."""
+    import shutil
+    import subprocess
+    ref = "/root/reference/src"
+    if not os.path.isdir(ref) or not shutil.which("g++"):
+        pytest.skip("reference checkout or g++ not available")
+    dropin = os.path.join(ROOT, "sci-solver_fem_b200", "dropin")
+    sources = [os.path.join(ref, "test", f) for f in ("sanity2D.cc", "sanity3D.cc", "tetVol.cc")]
+    sources += [os.path.join(ref, "examples", f) for f in ("example1.cu", "example2.cu")]
+    for src in sources:
+        cmd = ["/usr/bin/g++", "-std=c++17", "-fsyntax-only", "-x", "c++", "-I", dropin, "-DTEST_DATA_DIR=fsb_test_data_dir()", src]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, src + "\n" + r.stderr[-2000:]
+
