@@ -901,6 +901,75 @@ __global__ void __launch_bounds__(256) spmv_vector_kernel(int row_begin, int n, 
   }
 }
 
+// bc = R b - T x, T = R A: warp per coarse row, first the row of R against b, then the row of T against x;
+// four independent (col, val) -> vector chains per lane in both parts
+__device__ __forceinline__ double warp_row_dot(const int* __restrict__ ptr, const int* __restrict__ col, const double* __restrict__ val,
+                                               const double* __restrict__ v, int row, int lane) {
+  double s = 0.0;
+  const int e1 = ptr[row + 1];
+  int e = ptr[row] + lane;
+  for (; e + 96 < e1; e += 128) {
+    const int c0 = __ldg(col + e), c1 = __ldg(col + e + 32), c2 = __ldg(col + e + 64), c3 = __ldg(col + e + 96);
+    const double v0 = __ldg(val + e), v1 = __ldg(val + e + 32), v2 = __ldg(val + e + 64), v3 = __ldg(val + e + 96);
+    const double x0 = __ldg(v + c0), x1 = __ldg(v + c1), x2 = __ldg(v + c2), x3 = __ldg(v + c3);
+    s += v0 * x0; s += v1 * x1; s += v2 * x2; s += v3 * x3;
+  }
+  {
+    const bool p0 = e < e1, p1 = e + 32 < e1, p2 = e + 64 < e1, p3 = e + 96 < e1;
+    const int c0 = p0 ? __ldg(col + e) : 0, c1 = p1 ? __ldg(col + e + 32) : 0, c2 = p2 ? __ldg(col + e + 64) : 0, c3 = p3 ? __ldg(col + e + 96) : 0;
+    const double v0 = p0 ? __ldg(val + e) : 0.0, v1 = p1 ? __ldg(val + e + 32) : 0.0, v2 = p2 ? __ldg(val + e + 64) : 0.0, v3 = p3 ? __ldg(val + e + 96) : 0.0;
+    const double x0 = p0 ? __ldg(v + c0) : 0.0, x1 = p1 ? __ldg(v + c1) : 0.0, x2 = p2 ? __ldg(v + c2) : 0.0, x3 = p3 ? __ldg(v + c3) : 0.0;
+    s += v0 * x0; s += v1 * x1; s += v2 * x2; s += v3 * x3;
+  }
+  return s;
+}
+__global__ void __launch_bounds__(256) restrict_fused_kernel(int nc, const int* __restrict__ rptr, const int* __restrict__ rcol,
+                                                             const double* __restrict__ rval, const double* __restrict__ b,
+                                                             const int* __restrict__ tptr, const int* __restrict__ tcol,
+                                                             const double* __restrict__ tval, const double* __restrict__ x,
+                                                             double* __restrict__ bc, const int* __restrict__ done) {
+  pdl_wait();
+  if (done && *done) return;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= nc) return;
+  const double s = warp_sum(warp_row_dot(rptr, rcol, rval, b, row, lane) - warp_row_dot(tptr, tcol, tval, x, row, lane));
+  if (lane == 0) bc[row] = s;
+}
+
+// the same product with one 128-thread CTA per coarse row (few, long rows: R A has several hundred entries per row)
+__device__ __forceinline__ double cta_row_dot(const int* __restrict__ ptr, const int* __restrict__ col, const double* __restrict__ val,
+                                              const double* __restrict__ v, int row, int t) {
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  const int e1 = ptr[row + 1];
+  int e = ptr[row] + t;
+  for (; e + 384 < e1; e += 512) {
+    const int c0 = __ldg(col + e), c1 = __ldg(col + e + 128), c2 = __ldg(col + e + 256), c3 = __ldg(col + e + 384);
+    const double v0 = __ldg(val + e), v1 = __ldg(val + e + 128), v2 = __ldg(val + e + 256), v3 = __ldg(val + e + 384);
+    s0 += v0 * __ldg(v + c0); s1 += v1 * __ldg(v + c1); s2 += v2 * __ldg(v + c2); s3 += v3 * __ldg(v + c3);
+  }
+  {
+    const bool p0 = e < e1, p1 = e + 128 < e1, p2 = e + 256 < e1, p3 = e + 384 < e1;
+    const int c0 = p0 ? __ldg(col + e) : 0, c1 = p1 ? __ldg(col + e + 128) : 0, c2 = p2 ? __ldg(col + e + 256) : 0, c3 = p3 ? __ldg(col + e + 384) : 0;
+    const double v0 = p0 ? __ldg(val + e) : 0.0, v1 = p1 ? __ldg(val + e + 128) : 0.0, v2 = p2 ? __ldg(val + e + 256) : 0.0, v3 = p3 ? __ldg(val + e + 384) : 0.0;
+    s0 += v0 * (p0 ? __ldg(v + c0) : 0.0); s1 += v1 * (p1 ? __ldg(v + c1) : 0.0); s2 += v2 * (p2 ? __ldg(v + c2) : 0.0); s3 += v3 * (p3 ? __ldg(v + c3) : 0.0);
+  }
+  return (s0 + s1) + (s2 + s3);
+}
+__global__ void __launch_bounds__(128) restrict_fused_row_kernel(int nc, const int* __restrict__ rptr, const int* __restrict__ rcol,
+                                                                 const double* __restrict__ rval, const double* __restrict__ b,
+                                                                 const int* __restrict__ tptr, const int* __restrict__ tcol,
+                                                                 const double* __restrict__ tval, const double* __restrict__ x,
+                                                                 double* __restrict__ bc, const int* __restrict__ done) {
+  pdl_wait();
+  __shared__ double s_warp[4];
+  if (done && *done) return;
+  const int row = blockIdx.x, t = threadIdx.x;
+  const double w = warp_sum(cta_row_dot(rptr, rcol, rval, b, row, t) - cta_row_dot(tptr, tcol, tval, x, row, t));
+  if ((t & 31) == 0) s_warp[t >> 5] = w;
+  __syncthreads();
+  if (t == 0) bc[row] = (s_warp[0] + s_warp[1]) + (s_warp[2] + s_warp[3]);
+}
+
 // x = M b, dense, warp per row: the coarsest level's inverse (replaces the host LU round trip of amg_level.cu:25-31)
 // or the dense tail of the V-cycle (dense_tail.cu)
 __global__ void __launch_bounds__(256) coarse_gemv_kernel(int n, const double* __restrict__ Ainv, const double* __restrict__ b,
@@ -1161,6 +1230,16 @@ void launch_smooth(const Ctx& c, const LevelData& L, const double* b_src, const 
 void debug_stamps(int cta_plus1, long long* out64) {
   if (out64) FSB_CUDA(cudaMemcpyFromSymbol(out64, g_dbg, sizeof(long long) * 64));
   FSB_CUDA(cudaMemcpyToSymbol(g_dbg_on, &cta_plus1, sizeof(int)));
+}
+
+void launch_restrict_fused(const Ctx& c, const DCsr& R, const double* b, const DCsr& T, const double* x, double* bc, const int* done) {
+  g_launch_counter++;
+  ProfScope ps(c, "restrict");
+  if (R.nrows <= 16384 && (long long)T.nnz >= 128LL * R.nrows)  // few, long rows: a CTA per row
+    FSB_LAUNCH((restrict_fused_row_kernel), R.nrows, 128, 0, c.stream, R.nrows, R.ptr, R.col, R.val, b, T.ptr, T.col, T.val, x, bc, done);
+  else
+    FSB_LAUNCH((restrict_fused_kernel), cdiv((long long)R.nrows * 32, 256), 256, 0, c.stream, R.nrows, R.ptr, R.col, R.val, b, T.ptr, T.col, T.val, x, bc, done);
+  FSB_CHECK_LAUNCH();
 }
 
 void launch_coarse_solve(const Ctx& c, int n, const double* Ainv, const double* b, double* x, const int* done) {

@@ -26,6 +26,8 @@ void launch_spmv_dot(const Ctx& c, const DCsr& A, const double* x, double* y, do
 void launch_smooth(const Ctx& c, const LevelData& L, const double* b_src, const int* gather, double* b_int, const double* x_in,
                    double w, int nsweeps, double* x_out, const int* scatter, double* x_ext, double* r_out, const int* done,
                    bool owned_only = false);
+// bc = R b - T x with T = R A: the restricted residual of a level without forming the residual (warp per coarse row)
+void launch_restrict_fused(const Ctx& c, const DCsr& R, const double* b, const DCsr& T, const double* x, double* bc, const int* done);
 void launch_coarse_solve(const Ctx& c, int n, const double* Ainv, const double* b, double* x, const int* done);
 
 // PCG vector kernels (device-resident scalars)

@@ -217,6 +217,18 @@ void Solver::setup() {
     { double t1 = now_ms(); times_ms["setup_galerkin_AP_L" + std::to_string(L.level_id)] = t1 - t0; }
     { double t1 = now_ms(); spgemm(ctx, L.R, AP, Ac); times_ms["setup_galerkin_RAP_L" + std::to_string(L.level_id)] = now_ms() - t1; }
     times_ms["setup_galerkin"] += now_ms() - t0;
+    // levels >= 1 above the dense tail (replicated in a sharded solve, latency-bound): the restricted residual
+    // R (b - A x) is evaluated as R b - (R A) x, one kernel instead of the A_out update + restriction, and the
+    // smoother skips its residual pass.  R A is formed explicitly (no symmetry assumption on a user-supplied A).
+    static const bool fused_restrict = !(getenv("FSB_FUSED_RESTRICT") && atoi(getenv("FSB_FUSED_RESTRICT")) == 0);  // tuning knob
+    if (fused_restrict && L.level_id >= 1 && N > kDenseTailMaxRows) {
+      double t1 = now_ms();
+      DCsr At, AtP;  // R A = (A^T P)^T: short rows on the left keep the product cheap (R has ~100 entries per row)
+      transpose_csr(ctx, L.A, At);
+      spgemm(ctx, At, L.P, AtP);
+      transpose_csr(ctx, AtP, L.RA);
+      times_ms["setup_RA_L" + std::to_string(L.level_id)] = now_ms() - t1;
+    }
     L.b.alloc(N, s); L.x.alloc(N, s); L.x2.alloc(N, s); L.r.alloc(N, s);
     L.bc.alloc(L.nnout, s); L.xc.alloc(L.nnout, s);
     LevelData nx;
@@ -271,13 +283,19 @@ void Solver::vcycle(int lev, const double* b_src, const int* gather, double* x_d
       pbc.p[q] = reinterpret_cast<double*>(dist.peer[q] + dist.off_bc);
     }
   }
-  // pre: x = w b/d, nu1 sweeps, r = b - A_in x - d x  (one kernel, matrix slab read once)
-  launch_smooth(ctx, L, b_src, gather, gather ? L.b.get() : nullptr, nullptr, w, prm.preInnerIters, L.x, nullptr, nullptr, L.r, done, D);
-  if (D) launch_halo_push(ctx, dist.nSendA, dist.sendA, dist.sendA_ptr, L.x, px, done);           // x across the cut
-  if (L.sAout.ready()) launch_spmv_sell(ctx, L.sAout, L.x, L.r, 3, nullptr, done, "residual_out", rr);
-  else launch_spmv(ctx, L.Aout, L.x, L.r, 3, nullptr, done, "residual_out", rr);   // r -= A_out x   (preAout_kernel)
-  if (D) launch_halo_push(ctx, dist.nSendR, dist.sendR, dist.sendR_ptr, L.r, pr, done);           // r rows the peers restrict
-  launch_spmv(ctx, L.R, L.r, L.bc, 0, nullptr, done, "restrict", rrc);            // bc = R r
+  if (!D && L.RA.nrows > 0) {
+    // pre: x = w b/d, nu1 sweeps; then bc = R (b - A x) = R b - (R A) x without forming the residual
+    launch_smooth(ctx, L, b_src, gather, gather ? L.b.get() : nullptr, nullptr, w, prm.preInnerIters, L.x, nullptr, nullptr, nullptr, done, false);
+    launch_restrict_fused(ctx, L.R, b_eff, L.RA, L.x, L.bc, done);
+  } else {
+    // pre: x = w b/d, nu1 sweeps, r = b - A_in x - d x  (one kernel, matrix slab read once)
+    launch_smooth(ctx, L, b_src, gather, gather ? L.b.get() : nullptr, nullptr, w, prm.preInnerIters, L.x, nullptr, nullptr, L.r, done, D);
+    if (D) launch_halo_push(ctx, dist.nSendA, dist.sendA, dist.sendA_ptr, L.x, px, done);           // x across the cut
+    if (L.sAout.ready()) launch_spmv_sell(ctx, L.sAout, L.x, L.r, 3, nullptr, done, "residual_out", rr);
+    else launch_spmv(ctx, L.Aout, L.x, L.r, 3, nullptr, done, "residual_out", rr);   // r -= A_out x   (preAout_kernel)
+    if (D) launch_halo_push(ctx, dist.nSendR, dist.sendR, dist.sendR_ptr, L.r, pr, done);           // r rows the peers restrict
+    launch_spmv(ctx, L.R, L.r, L.bc, 0, nullptr, done, "restrict", rrc);            // bc = R r
+  }
   if (D) launch_push_all(ctx, rrc.begin, rrc.end, L.bc, pbc, done);                               // all-gather of bc
   const bool next_is_coarsest = (lev + 1 == (int)levels.size() - 1);
   const int* ip = next_is_coarsest ? nullptr : levels[lev + 1].agg.ipermutation.get();

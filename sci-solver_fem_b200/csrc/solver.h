@@ -52,6 +52,7 @@ struct LevelData {
   DCsr A;             // permuted numbering (rows of a partition contiguous); coarsest: external numbering
   DBuf diag;
   DCsr P, R;          // P: rows internal(l), cols external(l+1); R = P^T
+  DCsr RA;            // R A, levels >= 1 above the dense tail: restricted residual as R b - (R A) x in one kernel
   Aggregation agg;
   IBuf pstart;        // first row of each partition (nparts+1)
   DCsr Aout;          // inter-partition entries (rows internal numbering, global columns)
