@@ -459,9 +459,10 @@ void dense_inverse(const Ctx& c, const DCsr& A, DBuf& Ainv) {
 // ---------------------------------------------------------------------------------------------
 // Partition split.  The reference splits the permuted matrix into A_in (intra-partition strict
 // upper triangle, packed 16|16 local coordinates, smoothedMG_amg_level.cu:24-43, 199-304) and
-// A_out (inter-partition entries).  Here: A_out as CSR over all rows, and — where rows are short
-// enough to live in registers — the intra-partition off-diagonal entries of BOTH triangles as one
-// column-major ELL slab per partition (16-bit local columns), so the smoother is atomic-free.
+// A_out (inter-partition entries).  Here: A_out as CSR over all rows, and the intra-partition
+// off-diagonal entries of BOTH triangles (atomic-free smoother) as length-sorted, warp-sliced ELL slabs
+// with 16-bit columns: register-resident on the fine level (one lane per row), shared-memory resident
+// with G lanes per row on coarser levels with many partitions; see "sorted, warp-sliced ELL slabs" below.
 // ---------------------------------------------------------------------------------------------
 namespace {
 

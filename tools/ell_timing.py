@@ -1,5 +1,5 @@
 """Phase timestamps (clock64) of one CTA of the fine-level ELL smoother: python tools/ell_timing.py [cta] [kind]
-kind 1: one-partition-per-CTA kernel (run with FSB_ELL_PERSIST=0), kind 2: persistent kernel (first 4 partitions of the CTA).
+kind 1: fine-level register-resident kernel (256-thread class), kind 3: shared-memory kernel of the coarser levels.
 Needs a library built with NVCC_EXTRA=-DFSB_DEBUG_STAMPS python sci-solver_fem_b200/build.py -f"""
 import ctypes as C, os, sys
 import numpy as np
