@@ -149,7 +149,7 @@ def algorithmic_bytes(kernel, n, nnz, nnzP=0, nc=0, nnz_in=None):
 
 
 # ----------------------------------------------------------------------------- reference arm / cpu baseline
-def run_oracle(N, steps, warmup, threads=None):
+def run_oracle(N, steps, warmup, threads=None, single_thread_solve=False):
     from oracle import oracle as orc
     if threads:
         orc.set_threads(threads)
@@ -167,8 +167,14 @@ def run_oracle(N, steps, warmup, threads=None):
         if i >= warmup:
             times.append(dt)
     err = float(np.linalg.norm(x - xstar) / np.linalg.norm(xstar))
+    nthreads = orc.lib().orc_max_threads()
+    t_single = None
+    if single_thread_solve:  # the same solve on ONE host thread (closest to the reference's serial host code)
+        orc.set_threads(1)
+        t0 = time.perf_counter(); o.solve(b); t_single = time.perf_counter() - t0
+        orc.set_threads(nthreads)
     return dict(n=len(verts), t_solve=float(np.mean(times)), iters=int(iters), relres=float(o.final_relres()), err=err,
-                t_pattern=t_pat, t_assemble=t_asm, t_setup=t_setup, threads=orc.lib().orc_max_threads())
+                t_pattern=t_pat, t_assemble=t_asm, t_setup=t_setup, threads=nthreads, t_solve_1thread=t_single)
 
 
 def reference_arm(args):
@@ -353,8 +359,9 @@ def ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            r = run_oracle(N, 1, 0)
+            r = run_oracle(N, 1, 0, single_thread_solve=True)
             cpu = {"value": r["n"] / r["t_solve"], "unit": UNIT, "cores": r["threads"], "kind": "port",
+                   "single_thread": {"value": r["n"] / r["t_solve_1thread"], "unit": UNIT, "solve_s": r["t_solve_1thread"]},
                    "sample": f"full workload, 1 complete PCG solve ({r['iters']} iterations, {r['t_solve']:.2f} s; setup {r['t_setup']:.1f} s excluded); "
                              "CPU oracle = restatement of the reference (no host solve and no offline CUDA build upstream)",
                    "iterations": r["iters"], "setup_s": r["t_setup"], "assemble_s": r["t_assemble"], "pattern_s": r["t_pattern"]}
