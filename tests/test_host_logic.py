@@ -133,3 +133,17 @@ def test_upstream_callers_compile_against_the_dropin_headers(tmp_path):
         r = subprocess.run(cmd, capture_output=True, text=True)
         assert r.returncode == 0, src + "\n" + r.stderr[-2000:]
 
+
+def test_bench_cpu_baseline_helper():
+    """bench.py's CPU arm: the oracle run returns the stage times, the iteration count and, on request, the
+    same solve on one host thread (what the bench line reports as cpu_baseline / cpu_baseline.single_thread)."""
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    r = bench.run_oracle(10, 1, 0, single_thread_solve=True)
+    assert r["n"] == 11 ** 3 and r["iters"] > 0 and r["relres"] <= 1e-8
+    assert r["t_solve"] > 0 and r["t_solve_1thread"] > 0 and r["threads"] >= 1
+    assert bench.run_oracle(10, 1, 0)["t_solve_1thread"] is None
+    assert bench.algorithmic_bytes("pre_smooth", 10, 100, nnz_in=60) == 12 * 60 + 4 * 11 + 240
+    assert bench.algorithmic_bytes("spmv_dot", 10, 100) == 12 * 100 + 4 * 11 + 160
+
