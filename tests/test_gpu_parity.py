@@ -332,6 +332,23 @@ def test_config3_matches_the_oracle_golden():
     assert rel(x, xstar) <= 2 * g["err_vs_exact"] + 1e-12
 
 
+def test_partitions_larger_than_512_rows():
+    """partitionMaxSize_ = 1000 (upstream's limit is 1024 rows per partition): the fine-level smoother then runs
+    its 1024-thread size class; aggregates / partitions stay bit-exact and the solve agrees with the oracle."""
+    v, t = kuhn(26)
+    prm = dict(PCG, partitionMaxSize=1000)
+    o, s, nl = _setup_pair(v, t, **prm)
+    sizes = np.diff(s.level_int(0, "pstart"))
+    assert sizes.max() > 512, sizes.max()
+    for name in ("permutation", "aggregateIdx", "partitionIdx"):
+        assert np.array_equal(s.level_int(0, name), o.level_int(0, name)), name
+    b = o.spmv(egg_carton(v))
+    xo, ito = o.solve(b)
+    xg = s.solve(np.zeros_like(b), b)
+    assert abs(s.iterations - ito) <= 2, (s.iterations, ito)
+    assert rel(xg, xo) <= 1e-6
+
+
 def test_metis_bottom_up_aggregator():
     """aggregatorType_ = 1 (CP::MetisBottomUp): oracle and CUDA path call the same METIS 5 entry point,
     so aggregates / partitions must again be bit-exact; partitionMaxSize_ packs fineSize*1000 + coarseSize."""
