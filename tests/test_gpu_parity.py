@@ -332,6 +332,23 @@ def test_config3_matches_the_oracle_golden():
     assert rel(x, xstar) <= 2 * g["err_vs_exact"] + 1e-12
 
 
+def test_pcg_parity_on_a_triangle_mesh():
+    """2-D path end to end (short rows: the 8-slot variant of the fine-level smoother): structured triangle grid,
+    assembled K + M, PCG against the oracle."""
+    v, t = fsb.meshio.grid_tri(96, 80)
+    o, s, nl = _setup_pair(v, t, **PCG)
+    assert nl >= 2
+    xstar = np.sin(2 * np.pi * v[:, 0]) * np.sin(2 * np.pi * v[:, 1])
+    b = o.spmv(xstar)
+    xo, ito = o.solve(b)
+    xg = s.solve(np.zeros_like(b), b)
+    assert abs(s.iterations - ito) <= 2, (s.iterations, ito)
+    assert rel(xg, xo) <= 1e-6
+    ho, hg = o.resid_history(), s.resid_history()
+    m = min(len(ho), len(hg))
+    assert np.allclose(hg[:m], ho[:m], rtol=1e-6)
+
+
 def test_partitions_larger_than_512_rows():
     """partitionMaxSize_ = 1000 (upstream's limit is 1024 rows per partition): the fine-level smoother then runs
     its 1024-thread size class; aggregates / partitions stay bit-exact and the solve agrees with the oracle."""
