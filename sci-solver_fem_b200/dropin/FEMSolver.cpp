@@ -4,7 +4,10 @@
 #include "FEMSolver.h"
 
 #include <algorithm>
+#include <cctype>
 #include <cmath>
+#include <cstdlib>
+#include <iterator>
 #include <cstdint>
 #include <cstring>
 #include <sstream>
@@ -80,32 +83,223 @@ TetMesh* TetMesh::read(const char* nodefilename, const char* elefilename, const 
 }
 
 // ASCII PLY with x y z first (TriMesh_io.cu:259, :874-878 use %lf)
-TriMesh* TriMesh::read(const char* filename) {
-  std::ifstream f(filename);
-  if (!f.is_open()) return NULL;
-  std::string tok, line;
-  std::getline(f, line);
-  if (line.substr(0, 3) != "ply") return NULL;
-  int nv = 0, nf = 0, nprop = 0;
-  bool in_vertex = false, ascii = false;
-  while (std::getline(f, line)) {
-    std::istringstream ss(line);
-    ss >> tok;
-    if (tok == "format") { ss >> tok; ascii = (tok == "ascii"); }
-    else if (tok == "element") { ss >> tok; in_vertex = (tok == "vertex"); if (tok == "vertex") ss >> nv; else if (tok == "face") ss >> nf; }
-    else if (tok == "property" && in_vertex) nprop++;
-    else if (tok == "end_header") break;
+// ---- triangle-mesh input.  TriMesh::read upstream recognises the format from the first bytes of the file
+// (TriMesh_io.cu:160-256).  Covered: PLY (ascii, binary little/big endian; any scalar property types, the
+// vertex_indices list with any integer count/index types, other elements skipped), OBJ, OFF, old-style SM.
+// Polygons are cut into triangles by upstream's rule (:1239-1270).  Not covered: 3DS, VVD, RAY, PLY strips/grids.
+namespace {
+
+struct PlyProp { bool list; std::string name; int size, csize; char kind, ckind; };  // kind: 'i' signed, 'u' unsigned, 'f' float
+struct PlyElem { std::string name; long count; std::vector<PlyProp> props; };
+
+bool ply_type(const std::string& t, int& size, char& kind) {
+  static const struct { const char* n; int s; char k; } T[] = {
+      {"char", 1, 'i'}, {"int8", 1, 'i'}, {"uchar", 1, 'u'}, {"uint8", 1, 'u'}, {"short", 2, 'i'}, {"int16", 2, 'i'},
+      {"ushort", 2, 'u'}, {"uint16", 2, 'u'}, {"int", 4, 'i'}, {"int32", 4, 'i'}, {"uint", 4, 'u'}, {"uint32", 4, 'u'},
+      {"float", 4, 'f'}, {"float32", 4, 'f'}, {"double", 8, 'f'}, {"float64", 8, 'f'}};
+  for (const auto& e : T)
+    if (t == e.n) { size = e.s; kind = e.k; return true; }
+  return false;
+}
+
+// one binary scalar of the given type at p (byte-swapped when the file's endianness is not the host's)
+double bin_scalar(const unsigned char* p, int size, char kind, bool swap) {
+  unsigned char b[8];
+  for (int i = 0; i < size; i++) b[i] = p[swap ? size - 1 - i : i];
+  if (kind == 'f') {
+    if (size == 4) { float v; std::memcpy(&v, b, 4); return v; }
+    double v; std::memcpy(&v, b, 8); return v;
   }
-  if (!ascii || nprop < 3) return NULL;
-  TriMesh* m = new TriMesh();
+  if (size == 1) return kind == 'i' ? (double)(signed char)b[0] : (double)b[0];
+  if (size == 2) { if (kind == 'i') { short v; std::memcpy(&v, b, 2); return v; } unsigned short v; std::memcpy(&v, b, 2); return v; }
+  if (kind == 'i') { int v; std::memcpy(&v, b, 4); return v; }
+  unsigned v; std::memcpy(&v, b, 4); return v;
+}
+
+void tessellate(const std::vector<point>& verts, const std::vector<int>& poly, std::vector<TriMesh::Face>& out) {
+  auto push = [&](int a, int b, int c) { TriMesh::Face f; f[0] = a; f[1] = b; f[2] = c; out.push_back(f); };
+  const size_t k = poly.size();
+  if (k < 3) return;
+  if (k == 3) { push(poly[0], poly[1], poly[2]); return; }
+  if (k == 4) {  // along the shorter diagonal
+    auto d2 = [&](int a, int b) { double s = 0; for (int j = 0; j < 3; j++) { double d = verts[a][j] - verts[b][j]; s += d * d; } return s; };
+    const int i = d2(poly[0], poly[2]) < d2(poly[1], poly[3]) ? 0 : 1;
+    push(poly[i], poly[(i + 1) % 4], poly[(i + 2) % 4]);
+    push(poly[i], poly[(i + 2) % 4], poly[(i + 3) % 4]);
+    return;
+  }
+  for (size_t i = 2; i < k; i++) push(poly[0], poly[i - 1], poly[i]);
+}
+
+bool finish(TriMesh* m, const std::vector<std::vector<int> >& polys) {
+  const int nv = (int)m->vertices.size();
+  for (const auto& p : polys) {
+    for (int i : p)
+      if (i < 0 || i >= nv) return false;
+    tessellate(m->vertices, p, m->faces);
+  }
+  return !(m->vertices.empty() && m->faces.empty());
+}
+
+bool parse_ply(const std::string& data, TriMesh* m) {
+  const size_t end = data.find("end_header");
+  if (end == std::string::npos) return false;
+  const size_t body0 = data.find('\n', end);
+  if (body0 == std::string::npos) return false;
+  std::istringstream hs(data.substr(0, end));
+  std::string line, fmt;
+  std::vector<PlyElem> elems;
+  while (std::getline(hs, line)) {
+    std::istringstream ls(line);
+    std::string w;
+    if (!(ls >> w)) continue;
+    if (w == "format") ls >> fmt;
+    else if (w == "element") { PlyElem e; ls >> e.name >> e.count; elems.push_back(e); }
+    else if (w == "property" && !elems.empty()) {
+      PlyProp pr;
+      std::string t;
+      ls >> t;
+      pr.list = (t == "list");
+      if (pr.list) {
+        std::string ct, it;
+        ls >> ct >> it >> pr.name;
+        if (!ply_type(ct, pr.csize, pr.ckind) || !ply_type(it, pr.size, pr.kind)) return false;
+      } else {
+        ls >> pr.name;
+        pr.csize = 0; pr.ckind = 'u';
+        if (!ply_type(t, pr.size, pr.kind)) return false;
+      }
+      elems.back().props.push_back(pr);
+    }
+  }
+  const bool ascii = (fmt == "ascii");
+  if (!ascii && fmt != "binary_little_endian" && fmt != "binary_big_endian") return false;
+  const unsigned short probe = 1;
+  const bool host_le = *reinterpret_cast<const unsigned char*>(&probe) == 1;
+  const bool swap = !ascii && ((fmt == "binary_little_endian") != host_le);
+  std::vector<std::vector<int> > polys;
+  std::istringstream as;
+  if (ascii) as.str(data.substr(body0 + 1));
+  const unsigned char* p = reinterpret_cast<const unsigned char*>(data.data()) + body0 + 1;
+  const unsigned char* pend = reinterpret_cast<const unsigned char*>(data.data()) + data.size();
+  auto next = [&](int size, char kind, double& v) -> bool {
+    if (ascii) return (bool)(as >> v);
+    if (p + size > pend) return false;
+    v = bin_scalar(p, size, kind, swap);
+    p += size;
+    return true;
+  };
+  for (const PlyElem& e : elems) {
+    const bool is_vertex = (e.name == "vertex"), is_face = (e.name == "face");
+    if (is_vertex) m->vertices.resize(e.count);
+    for (long r = 0; r < e.count; r++) {
+      for (const PlyProp& pr : e.props) {
+        double v;
+        if (!pr.list) {
+          if (!next(pr.size, pr.kind, v)) return false;
+          if (is_vertex) {
+            if (pr.name == "x") m->vertices[r][0] = v;
+            else if (pr.name == "y") m->vertices[r][1] = v;
+            else if (pr.name == "z") m->vertices[r][2] = v;
+          }
+        } else {
+          if (!next(pr.csize, pr.ckind, v)) return false;
+          const long k = (long)v;
+          std::vector<int> poly;
+          for (long j = 0; j < k; j++) {
+            if (!next(pr.size, pr.kind, v)) return false;
+            poly.push_back((int)v);
+          }
+          if (is_face && (pr.name == "vertex_indices" || pr.name == "vertex_index")) polys.push_back(poly);
+        }
+      }
+    }
+  }
+  return finish(m, polys);
+}
+
+// whitespace-separated tokens of a text file with '#' comments removed
+std::vector<std::string> text_tokens(const std::string& data) {
+  std::vector<std::string> toks;
+  std::istringstream ds(data);
+  std::string line, w;
+  while (std::getline(ds, line)) {
+    const size_t h = line.find('#');
+    if (h != std::string::npos) line.erase(h);
+    std::istringstream ls(line);
+    while (ls >> w) toks.push_back(w);
+  }
+  return toks;
+}
+
+bool parse_obj(const std::string& data, TriMesh* m) {
+  std::vector<std::vector<int> > polys;
+  std::istringstream ds(data);
+  std::string line;
+  while (std::getline(ds, line)) {
+    std::istringstream ls(line);
+    std::string w;
+    if (!(ls >> w) || w[0] == '#') continue;
+    if (w == "v") {
+      point q;
+      if (!(ls >> q[0] >> q[1] >> q[2])) return false;
+      m->vertices.push_back(q);
+    } else if (w == "f" || w == "t") {
+      std::vector<int> poly;
+      while (ls >> w) {  // a/b/c groups: the first integer is the vertex; 1-based, negative = relative
+        char* endp = NULL;
+        const long i = std::strtol(w.c_str(), &endp, 10);
+        if (endp == w.c_str()) break;
+        poly.push_back(i < 0 ? (int)(i + (long)m->vertices.size()) : (int)(i - 1));
+      }
+      polys.push_back(poly);
+    }
+  }
+  return finish(m, polys);
+}
+
+bool parse_counted(const std::vector<std::string>& t, size_t pos, bool off_style, TriMesh* m) {
+  // OFF: nverts nfaces [nedges] | vertices | k i0..ik-1 per face.   SM: nverts | vertices | nfaces | 3 indices per face
+  auto num = [&](size_t i, double& v) { if (i >= t.size()) return false; char* e = NULL; v = std::strtod(t[i].c_str(), &e); return e != t[i].c_str(); };
+  double v;
+  if (!num(pos++, v)) return false;
+  const long nv = (long)v;
+  long nf = 0;
+  if (off_style) { if (!num(pos++, v)) return false; nf = (long)v; pos++; }
   m->vertices.resize(nv);
-  for (int i = 0; i < nv; i++) {
-    for (int j = 0; j < nprop; j++) { double v; if (!(f >> v)) { delete m; return NULL; } if (j < 3) m->vertices[i][j] = v; }
+  for (long i = 0; i < nv; i++)
+    for (int j = 0; j < 3; j++) { if (!num(pos++, v)) return false; m->vertices[i][j] = v; }
+  if (!off_style) { if (!num(pos++, v)) return finish(m, {}); nf = (long)v; }
+  std::vector<std::vector<int> > polys;
+  for (long f = 0; f < nf; f++) {
+    long k = 3;
+    if (off_style) { if (!num(pos++, v)) return false; k = (long)v; }
+    std::vector<int> poly;
+    for (long j = 0; j < k; j++) { if (!num(pos++, v)) return false; poly.push_back((int)v); }
+    polys.push_back(poly);
   }
-  m->faces.resize(nf);
-  for (int i = 0; i < nf; i++) {
-    int k; if (!(f >> k) || k != 3) { delete m; return NULL; }
-    f >> m->faces[i][0] >> m->faces[i][1] >> m->faces[i][2];
+  return finish(m, polys);
+}
+
+}  // namespace
+
+TriMesh* TriMesh::read(const char* filename) {
+  if (!filename || !*filename) return NULL;
+  std::ifstream f(filename, std::ios::binary);
+  if (!f.is_open()) { perror("fopen"); return NULL; }
+  std::string data((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+  TriMesh* m = new TriMesh();
+  bool ok = false;
+  if (data.empty()) std::cerr << "Can't read header" << std::endl;
+  else if (data.compare(0, 3, "ply") == 0) ok = parse_ply(data, m);
+  else if (data.compare(0, 3, "OFF") == 0) { std::vector<std::string> t = text_tokens(data); ok = parse_counted(t, 1, true, m); }
+  else if (std::strchr("#vufgso", data[0])) ok = parse_obj(data, m);
+  else if (std::isdigit((unsigned char)data[0])) ok = parse_counted(text_tokens(data), 0, false, m);
+  else std::cerr << "Unknown file type" << std::endl;
+  if (!ok) {
+    std::cerr << "\nError reading file [" << filename << "]" << std::endl;
+    delete m;
+    return NULL;
   }
   return m;
 }

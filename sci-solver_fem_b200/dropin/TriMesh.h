@@ -1,8 +1,9 @@
 // tetmesh.h / TriMesh.h stand-ins: the data model the solve path consumes (vertices, tets/faces,
-// matlabels, neighbors) and the two input formats the shipped fixtures use.
+// matlabels, neighbors) and the input formats: TetGen .node/.ele; PLY (ascii / binary), OBJ, OFF, SM.
 // Reference: src/core/include/tetmesh.h, src/core/cuda/tetmesh.cu:112-170 (need_neighbors),
 // :251-376 (TetMesh::read); src/core/include/TriMesh.h, aggmis/cuda/TriMesh_connectivity.cu:96-131,
-// TriMesh_io.cu:146,259 (ASCII PLY).  Curvature / FIM / other-format baggage is out of scope.
+// TriMesh_io.cu:146-256 (format detection), :1239-1270 (tessellation).  Curvature / FIM members and the
+// exotic formats (3DS, VVD, RAY, PLY strips) are out of scope.
 #ifndef __FSB_MESHES_H__
 #define __FSB_MESHES_H__
 #include <string>
@@ -49,6 +50,6 @@ class TriMesh {
   void set_verbose(bool v) { verbose = v; }
   void need_neighbors();
   void need_meshquality() {}
-  static TriMesh* read(const char* filename);  // ASCII PLY; returns NULL on failure (TriMesh_io.cu:146-155)
+  static TriMesh* read(const char* filename);  // format by the first bytes; returns NULL on failure (TriMesh_io.cu:146-155)
 };
 #endif

@@ -142,7 +142,7 @@ class FEMSolver:
                 v, t, lab = meshio.read_node_ele(fname)
                 self._set_mesh(v, t, lab)
             else:
-                v, f = meshio.read_ply_ascii(fname)
+                v, f = meshio.read_trimesh(fname)
                 self._set_mesh(v, f, None)
             self.getMatrixFromMesh()
 

@@ -134,38 +134,202 @@ def write_node_ele(base: str, verts, tets, labels=None):
 
 
 # ----------------------------------------------------------------------------- PLY
-def read_ply_ascii(path: str):
-    """ASCII PLY with x y z first per vertex and `n i j k` faces (%lf parse, TriMesh_io.cu:874-878)."""
-    with open(path) as f:
-        assert f.readline().strip() == "ply"
-        nv = nf = 0
-        nprop = 0
-        in_vertex = False
-        while True:
-            ln = f.readline().strip()
-            if ln.startswith("format"):
-                assert "ascii" in ln, "only ASCII PLY is supported"
-            elif ln.startswith("element vertex"):
-                nv = int(ln.split()[2]); in_vertex = True
-            elif ln.startswith("element face"):
-                nf = int(ln.split()[2]); in_vertex = False
-            elif ln.startswith("element"):
-                in_vertex = False
-            elif ln.startswith("property") and in_vertex:
-                nprop += 1
-            elif ln == "end_header":
-                break
-        toks = f.read().split()
-    verts = np.array(toks[: nv * nprop], dtype=np.float64).reshape(nv, nprop)[:, :3].copy()
-    rest = toks[nv * nprop:]
-    tris = np.zeros((nf, 3), dtype=np.int32)
-    p = 0
-    for i in range(nf):
-        k = int(rest[p])
-        assert k == 3, "only triangles"
-        tris[i] = [int(rest[p + 1]), int(rest[p + 2]), int(rest[p + 3])]
-        p += 1 + k
+# ------------------------------------------------------------------------------------- triangle meshes
+# TriMesh::read (aggmis/cuda/TriMesh_io.cu:146-256) recognises the format from the first bytes of the file.
+# Covered here: PLY (ascii, binary little/big endian; any scalar property types, the vertex_indices list with
+# any integer count/index types; other elements are skipped), OBJ, OFF and old-style SM.  Polygons are cut into
+# triangles by upstream's rule (tess, :1239-1270).  Not covered: 3DS, VVD, RAY, PLY triangle strips / range grids.
+_PLY_TYPES = {"char": "i1", "int8": "i1", "uchar": "u1", "uint8": "u1", "short": "i2", "int16": "i2", "ushort": "u2",
+              "uint16": "u2", "int": "i4", "int32": "i4", "uint": "u4", "uint32": "u4", "float": "f4", "float32": "f4",
+              "double": "f8", "float64": "f8"}
+
+
+def tessellate(verts, face):
+    """Triangles of one polygon (vertex index list): 3 -> itself; 4 -> split along the shorter diagonal
+    (0-2 if strictly shorter, else 1-3); 5 and more -> fan around the first vertex; fewer than 3 -> nothing."""
+    k = len(face)
+    if k < 3:
+        return []
+    if k == 3:
+        return [tuple(face)]
+    if k == 4:
+        p = [np.asarray(verts[i], dtype=np.float64) for i in face]
+        d02 = float(np.sum((p[0] - p[2]) ** 2))
+        d13 = float(np.sum((p[1] - p[3]) ** 2))
+        i = 0 if d02 < d13 else 1
+        return [(face[i], face[(i + 1) % 4], face[(i + 2) % 4]), (face[i], face[(i + 2) % 4], face[(i + 3) % 4])]
+    return [(face[0], face[i - 1], face[i]) for i in range(2, k)]
+
+
+def _finish_trimesh(verts, polys):
+    verts = np.ascontiguousarray(verts, dtype=np.float64).reshape(-1, 3)
+    tris = [t for f in polys for t in tessellate(verts, f)]
+    tris = np.asarray(tris, dtype=np.int32).reshape(-1, 3)
+    if len(verts) == 0 and len(tris) == 0:
+        raise ValueError("empty mesh")
+    if len(tris) and (tris.min() < 0 or tris.max() >= len(verts)):
+        raise ValueError("face index out of range")
     return verts, tris
+
+
+def read_ply(path: str):
+    """PLY, ascii or binary (either endianness)."""
+    with open(path, "rb") as f:
+        data = f.read()
+    end = data.find(b"end_header")
+    if not data.startswith(b"ply") or end < 0:
+        raise ValueError("not a PLY file")
+    nl = data.find(b"\n", end)
+    header = data[:end].decode("ascii", "replace").splitlines()
+    body = data[nl + 1:]
+    fmt, elements = None, []          # elements: [name, count, [(kind, name, types...)]]
+    for ln in header[1:]:
+        t = ln.split()
+        if not t or t[0] in ("comment", "obj_info"):
+            continue
+        if t[0] == "format":
+            fmt = t[1]
+        elif t[0] == "element":
+            elements.append([t[1], int(t[2]), []])
+        elif t[0] == "property" and elements:
+            if t[1] == "list":
+                elements[-1][2].append(("list", t[4], _PLY_TYPES[t[2]], _PLY_TYPES[t[3]]))
+            else:
+                elements[-1][2].append(("scalar", t[2], _PLY_TYPES[t[1]]))
+    if fmt not in ("ascii", "binary_little_endian", "binary_big_endian"):
+        raise ValueError("unknown PLY format")
+    verts, polys = np.zeros((0, 3)), []
+    if fmt == "ascii":
+        toks = body.split()
+        pos = 0
+        for name, count, props in elements:
+            rows = []
+            for _ in range(count):
+                row = {}
+                for pr in props:
+                    if pr[0] == "scalar":
+                        row[pr[1]] = float(toks[pos]); pos += 1
+                    else:
+                        k = int(float(toks[pos])); pos += 1
+                        row[pr[1]] = [int(float(x)) for x in toks[pos:pos + k]]; pos += k
+                rows.append(row)
+            if name == "vertex":
+                verts = np.array([[r["x"], r["y"], r["z"]] for r in rows], dtype=np.float64).reshape(-1, 3)
+            elif name == "face":
+                key = "vertex_indices" if (rows and "vertex_indices" in rows[0]) else "vertex_index"
+                polys = [r[key] for r in rows]
+    else:
+        e = "<" if fmt == "binary_little_endian" else ">"
+        mv = memoryview(body)
+        pos = 0
+        for name, count, props in elements:
+            if all(pr[0] == "scalar" for pr in props):
+                dt = np.dtype([(pr[1], e + pr[2]) for pr in props])
+                arr = np.frombuffer(mv, dtype=dt, count=count, offset=pos)
+                pos += dt.itemsize * count
+                if name == "vertex":
+                    verts = np.stack([arr["x"], arr["y"], arr["z"]], axis=1).astype(np.float64)
+                continue
+            rows = []
+            for _ in range(count):
+                row = {}
+                for pr in props:
+                    if pr[0] == "scalar":
+                        dt = np.dtype(e + pr[2])
+                        row[pr[1]] = np.frombuffer(mv, dtype=dt, count=1, offset=pos)[0]; pos += dt.itemsize
+                    else:
+                        ct, it = np.dtype(e + pr[2]), np.dtype(e + pr[3])
+                        k = int(np.frombuffer(mv, dtype=ct, count=1, offset=pos)[0]); pos += ct.itemsize
+                        row[pr[1]] = [int(x) for x in np.frombuffer(mv, dtype=it, count=k, offset=pos)]; pos += it.itemsize * k
+                rows.append(row)
+            if name == "face":
+                key = "vertex_indices" if (rows and "vertex_indices" in rows[0]) else "vertex_index"
+                polys = [r[key] for r in rows]
+    return _finish_trimesh(verts, polys)
+
+
+def read_obj(path: str):
+    """Wavefront OBJ: `v x y z` and `f a b c ...` (also `t`), 1-based, negative = relative to the vertices read so far;
+    only the first integer of an `a/b/c` group counts (TriMesh_io.cu:651-689)."""
+    verts, polys = [], []
+    with open(path) as f:
+        for ln in f:
+            t = ln.split()
+            if not t or t[0].startswith("#"):
+                continue
+            if t[0] == "v" and len(t) >= 4:
+                verts.append([float(t[1]), float(t[2]), float(t[3])])
+            elif t[0] in ("f", "t"):
+                face = []
+                for g in t[1:]:
+                    try:
+                        i = int(g.split("/")[0])
+                    except ValueError:
+                        break
+                    face.append(i + len(verts) if i < 0 else i - 1)
+                polys.append(face)
+    return _finish_trimesh(np.array(verts, dtype=np.float64).reshape(-1, 3), polys)
+
+
+def _number_tokens(path, skip_first_word=None):
+    toks = []
+    with open(path) as f:
+        for ln in f:
+            ln = ln.split("#")[0]
+            toks.extend(ln.split())
+    if skip_first_word and toks and toks[0] == skip_first_word:
+        toks = toks[1:]
+    return toks
+
+
+def read_off(path: str):
+    """OFF: `OFF`, `nverts nfaces [nedges]`, the vertices, then `k i0 .. ik-1` per face (TriMesh_io.cu:692-707)."""
+    t = _number_tokens(path, "OFF")
+    nv, nf = int(t[0]), int(t[1])
+    pos = 3
+    verts = np.array(t[pos:pos + 3 * nv], dtype=np.float64).reshape(nv, 3)
+    pos += 3 * nv
+    polys = []
+    for _ in range(nf):
+        k = int(t[pos]); pos += 1
+        polys.append([int(x) for x in t[pos:pos + k]]); pos += k
+    return _finish_trimesh(verts, polys)
+
+
+def read_sm(path: str):
+    """Old-style SM: `nverts`, the vertices, `nfaces`, three indices per face (TriMesh_io.cu:710-731)."""
+    t = _number_tokens(path)
+    nv = int(t[0])
+    verts = np.array(t[1:1 + 3 * nv], dtype=np.float64).reshape(nv, 3)
+    pos = 1 + 3 * nv
+    polys = []
+    if pos < len(t):
+        nf = int(t[pos]); pos += 1
+        polys = [[int(x) for x in t[pos + 3 * i:pos + 3 * i + 3]] for i in range(nf)]
+    return _finish_trimesh(verts, polys)
+
+
+def read_trimesh(path: str):
+    """Format by the first bytes, as TriMesh::read_helper does (TriMesh_io.cu:160-256)."""
+    with open(path, "rb") as f:
+        head = f.read(4)
+    if not head:
+        raise ValueError("Can't read header")
+    c = head[:1]
+    if head[:3] == b"ply":
+        return read_ply(path)
+    if head[:3] == b"OFF":
+        return read_off(path)
+    if c in (b"#", b"v", b"u", b"f", b"g", b"s", b"o"):
+        return read_obj(path)
+    if c.isdigit():
+        return read_sm(path)
+    raise ValueError("Unknown file type")
+
+
+def read_ply_ascii(path: str):
+    """Kept name of the first reader (ASCII PLY fixtures of the reference); any PLY flavour is accepted now."""
+    return read_ply(path)
 
 
 def write_ply_ascii(path: str, verts, tris):

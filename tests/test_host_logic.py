@@ -147,3 +147,102 @@ def test_bench_cpu_baseline_helper():
     assert bench.algorithmic_bytes("pre_smooth", 10, 100, nnz_in=60) == 12 * 60 + 4 * 11 + 240
     assert bench.algorithmic_bytes("spmv_dot", 10, 100) == 12 * 100 + 4 * 11 + 160
 
+
+def _mesh_with_polygons():
+    """Small surface with triangles, two quads (one per diagonal choice) and a pentagon."""
+    verts = np.array([[0, 0, 0], [1, 0, 0], [0.8, 0.8, 0], [0, 1, 0], [2, 0, 0.25], [2.5, 1, 0], [1, 2, 0], [0, 2, 0.5], [-1, 1, 0], [3, 2.5, 1]],
+                     dtype=np.float64)
+    polys = [[0, 1, 2, 3], [1, 4, 5, 2], [3, 2, 6], [3, 6, 7, 8, 0], [4, 9, 5]]
+    return verts, polys
+
+
+def _write_mesh_files(d, verts, polys):
+    """The same mesh as PLY (ascii / binary LE / binary BE with extra properties and a leading element), OBJ, OFF, SM."""
+    import struct
+    files = {}
+    nv, nf = len(verts), len(polys)
+    hdr = ("ply\nformat %s 1.0\ncomment test\nelement extra 2\nproperty int a\nelement vertex %d\nproperty float x\nproperty float y\n"
+           "property float z\nproperty uchar red\nproperty double w\nelement face %d\nproperty list uchar int vertex_indices\n"
+           "property float q\nend_header\n")
+    with open(os.path.join(d, "a.ply"), "w") as f:
+        f.write(hdr % ("ascii", nv, nf))
+        f.write("7\n9\n")
+        for v in verts:
+            f.write("%.9g %.9g %.9g 200 1.5\n" % tuple(v))
+        for p in polys:
+            f.write("%d %s 0.5\n" % (len(p), " ".join(map(str, p))))
+    files["ply_ascii"] = os.path.join(d, "a.ply")
+    for tag, e, name in (("le", "<", "binary_little_endian"), ("be", ">", "binary_big_endian")):
+        path = os.path.join(d, "b_%s.ply" % tag)
+        with open(path, "wb") as f:
+            f.write((hdr % (name, nv, nf)).encode())
+            f.write(struct.pack(e + "ii", 7, 9))
+            for v in verts:
+                f.write(struct.pack(e + "fffBd", v[0], v[1], v[2], 200, 1.5))
+            for p in polys:
+                f.write(struct.pack(e + "B%dif" % len(p), len(p), *p, 0.5))
+        files["ply_" + tag] = path
+    with open(os.path.join(d, "m.obj"), "w") as f:
+        f.write("# comment\n")
+        for v in verts:
+            f.write("v %.9g %.9g %.9g\n" % tuple(v))
+        for k, p in enumerate(polys):
+            if k % 2 == 0:
+                f.write("f " + " ".join("%d/%d/%d" % (i + 1, i + 1, i + 1) for i in p) + "\n")
+            else:
+                f.write("f " + " ".join(str(i - nv) for i in p) + "\n")     # negative = relative to the end
+    files["obj"] = os.path.join(d, "m.obj")
+    with open(os.path.join(d, "m.off"), "w") as f:
+        f.write("OFF\n# comment\n%d %d 0\n" % (nv, nf))
+        for v in verts:
+            f.write("%.9g %.9g %.9g\n" % tuple(v))
+        for p in polys:
+            f.write("%d %s\n" % (len(p), " ".join(map(str, p))))
+    files["off"] = os.path.join(d, "m.off")
+    return files
+
+
+def test_triangle_mesh_formats_python_and_dropin_agree(tmp_path):
+    """TriMesh::read's format detection and polygon tessellation (TriMesh_io.cu:160-256, 1239-1270) for PLY (ascii and
+    both binary byte orders), OBJ, OFF and SM: the Python readers and the drop-in's C++ readers must return the same
+    mesh, and that mesh must be the hand-tessellated one."""
+    import subprocess
+    verts, polys = _mesh_with_polygons()
+    v32 = verts.astype(np.float32).astype(np.float64)
+    expect = []
+    for p in polys:
+        expect += meshio.tessellate(verts, p)
+    # the two quads exercise both diagonal choices, the pentagon the fan
+    assert expect[:2] == [(0, 1, 2), (0, 2, 3)] and expect[2:4] == [(4, 5, 2), (4, 2, 1)] and len(expect) == 2 + 2 + 1 + 3 + 1
+    files = _write_mesh_files(str(tmp_path), verts, polys)
+    tri_only = [list(t) for t in expect]
+    with open(os.path.join(str(tmp_path), "m.sm"), "w") as f:     # SM has no polygons: write the triangles
+        f.write("%d\n" % len(verts))
+        for v in verts:
+            f.write("%.9g %.9g %.9g\n" % tuple(v))
+        f.write("%d\n" % len(tri_only))
+        for t in tri_only:
+            f.write("%d %d %d\n" % tuple(t))
+    files["sm"] = os.path.join(str(tmp_path), "m.sm")
+    exe = os.path.join(ROOT, "sci-solver_fem_b200", "dropin", "bin", "mesh_info")
+    have_exe = os.path.exists(exe)
+    for kind, path in files.items():
+        v, t = meshio.read_trimesh(path)
+        assert np.allclose(v, v32 if kind.startswith("ply_") and kind != "ply_ascii" else verts, rtol=0, atol=1e-6), kind
+        assert [tuple(x) for x in t.tolist()] == expect, kind
+        if have_exe:
+            r = subprocess.run([exe, path], capture_output=True, text=True)
+            assert r.returncode == 0, kind + r.stderr
+            out = r.stdout.split("\n")
+            assert int(out[0]) == len(v) and int(out[1]) == len(t), kind
+            cs = sum((i % 97 + 1) * (j + 1) * v[i, j] for i in range(len(v)) for j in range(3))
+            fs = sum((i % 89 + 1) * (j + 1) * int(t[i, j]) for i in range(len(t)) for j in range(3))
+            assert abs(float(out[2]) - cs) <= 1e-9 * max(1.0, abs(cs)), kind
+            assert int(out[3]) == fs, kind
+    with open(os.path.join(str(tmp_path), "bad.xyz"), "w") as f:
+        f.write("?? nothing\n")
+    with pytest.raises(ValueError):
+        meshio.read_trimesh(os.path.join(str(tmp_path), "bad.xyz"))
+    if have_exe:
+        assert subprocess.run([exe, os.path.join(str(tmp_path), "bad.xyz")], capture_output=True).returncode == 1
+
