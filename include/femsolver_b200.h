@@ -95,19 +95,28 @@ int fsb_precondition_device(fsb_solver* s, const double* r_dev, double* z_dev);
 
 /* stage 4 — sharded solve over the GPUs of one box (absent upstream; one process per GPU).
  * Every process builds the same mesh and calls fsb_setup (replicated, deterministic); then
- *   fsb_dist_prepare(rank, nranks)  splits the fine level into contiguous nnz-balanced partition ranges,
- *                                   builds the halo send lists and allocates the exchange arena;
+ *   fsb_dist_prepare(rank, nranks)  deals the partitions of the fine level — and of every coarser level that still
+ *                                   gives each GPU enough rows — out in contiguous nnz-balanced ranges, builds
+ *                                   the push lists of every exchange and allocates the exchange arena;
  *   fsb_dist_handle                 returns the 64-byte CUDA IPC handle of that arena (all-gather it, e.g.
  *                                   with torch.distributed / MPI);
  *   fsb_dist_connect(handles)       maps the peers' arenas (nranks x 64 bytes, rank order).
  * After that fsb_solve / fsb_solve_device with solverType = 1 run sharded; all processes must call them
- * together.  fsb_setup or fsb_dist_disconnect ends the sharded mode. */
+ * together.  fsb_solve_device reads b / x0 at this GPU's rows and leaves the FULL solution in x on every
+ * GPU; fsb_solve (host buffers) moves only the slice [user_lo, user_hi) of b, x0 and x over PCIe (the
+ * range of user-numbered rows that covers this GPU's rows, fsb_dist_info) — x outside it is untouched.
+ * fsb_setup or fsb_dist_disconnect ends the sharded mode. */
 int fsb_dist_prepare(fsb_solver* s, int rank, int nranks);
 int fsb_dist_handle(fsb_solver* s, void* handle64, long long* arena_bytes);
 int fsb_dist_connect(fsb_solver* s, const void* handles);
 int fsb_dist_disconnect(fsb_solver* s);
 /* first partition / first fine row / first coarse row of every rank (nranks+1 entries each); returns nranks */
 int fsb_dist_ranges(const fsb_solver* s, int* part_begin, int* row_begin, int* coarse_begin);
+/* the same for sharded level `level` (rows in that level's permuted numbering) */
+int fsb_dist_level_ranges(const fsb_solver* s, int level, int* part_begin, int* row_begin, int* coarse_begin);
+/* number of sharded levels, the host-copy slice, and per sharded level the number of values this GPU pushes per
+ * exchange (4 entries per level: operator halo, residual halo, down, up; halo_values may be NULL); returns nranks */
+int fsb_dist_info(const fsb_solver* s, int* sharded_levels, int* user_lo, int* user_hi, long long* halo_values);
 /* host-only helper: contiguous split of weighted partitions over nranks (out_begin has nranks+1 entries) */
 void fsb_split_by_weight(int nparts, const long long* weights, int nranks, int* out_begin);
 

@@ -19,6 +19,8 @@ template <typename F>
 int guarded(fsb_solver* s, F&& f) {
   if (!s || !s->impl) return FSB_ERR_INVALID;
   try {
+    // every entry point runs on the solver's own device, whatever the caller's current device is
+    if (cudaSetDevice(s->impl->ctx.device) != cudaSuccess) { cudaGetLastError(); throw fsb::CudaError("cudaSetDevice failed for the solver's device"); }
     f(*s->impl);
     return FSB_OK;
   } catch (const std::invalid_argument& e) {
@@ -253,12 +255,31 @@ int fsb_dist_handle(fsb_solver* s, void* handle64, long long* arena_bytes) {
 int fsb_dist_connect(fsb_solver* s, const void* handles) { return guarded(s, [&](fsb::Solver& S) { S.dist_connect(handles); }); }
 int fsb_dist_disconnect(fsb_solver* s) { return guarded(s, [&](fsb::Solver& S) { S.dist_disconnect(); }); }
 int fsb_dist_ranges(const fsb_solver* s, int* part_begin, int* row_begin, int* coarse_begin) {
+  return fsb_dist_level_ranges(s, 0, part_begin, row_begin, coarse_begin);
+}
+int fsb_dist_level_ranges(const fsb_solver* s, int level, int* part_begin, int* row_begin, int* coarse_begin) {
   if (!s || !s->impl) return FSB_ERR_INVALID;
   const auto& d = s->impl->dist;
+  if (level < 0 || level >= (int)d.lev.size()) return FSB_ERR_INVALID;
+  const auto& L = d.lev[level];
   for (int r = 0; r <= d.nranks; r++) {
-    if (part_begin) part_begin[r] = d.pbeg[r];
-    if (row_begin) row_begin[r] = d.rbeg[r];
-    if (coarse_begin) coarse_begin[r] = d.abeg[r];
+    if (part_begin) part_begin[r] = L.pbeg[r];
+    if (row_begin) row_begin[r] = L.rbeg[r];
+    if (coarse_begin) coarse_begin[r] = L.abeg[r];
+  }
+  return d.nranks;
+}
+int fsb_dist_info(const fsb_solver* s, int* sharded_levels, int* user_lo, int* user_hi, long long* halo_values) {
+  if (!s || !s->impl) return FSB_ERR_INVALID;
+  const auto& d = s->impl->dist;
+  if (sharded_levels) *sharded_levels = d.nshard;
+  if (user_lo) *user_lo = d.user_lo;
+  if (user_hi) *user_hi = d.user_hi;
+  if (halo_values) {  // per sharded level: entries of the four push lists (operator columns, residual rows, down, up)
+    for (int l = 0; l < d.nshard; l++) {
+      halo_values[4 * l + 0] = d.lev[l].sendA.total; halo_values[4 * l + 1] = d.lev[l].sendR.total;
+      halo_values[4 * l + 2] = d.lev[l].sendDown.total; halo_values[4 * l + 3] = d.lev[l].sendUp.total;
+    }
   }
   return d.nranks;
 }

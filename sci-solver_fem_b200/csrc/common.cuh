@@ -29,18 +29,37 @@ struct CudaError : public std::runtime_error {
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Function attributes (opt-in dynamic shared memory) are per DEVICE: a process may hold solvers on several
+// devices, so "already set" is tracked per device ordinal.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool first(int device) {
+    if (device < 0 || device >= 64) return true;
+    if (done[device]) return false;
+    done[device] = true;
+    return true;
+  }
+};
+
 // Device-visible description of the GPU group of a sharded solve (one process per GPU; peers'
 // arenas are mapped through CUDA IPC and reached over NVLink).  nranks == 1: everything is local.
+// Exchanges are CHANNELS: a producer kernel stores its boundary values into the peers' copies of a
+// vector, fences, and publishes the channel's epoch into flag word [1 + chan][rank] of every destination
+// peer; it never waits.  A consumer waits (in its prologue) until the flag words of the peers it receives
+// from have reached its own epoch of that channel.  Row 0 of the flag table belongs to the all-reduce.
 constexpr int kMaxRanks = 8;
+constexpr int kMaxChan = 47;   // flag table: (1 + kMaxChan) rows of kMaxRanks words
 struct DistDev {
   int rank = 0, nranks = 1;
-  unsigned long long* my_flags = nullptr;             // [kMaxRanks] written by the peers
-  unsigned long long* peer_flags[kMaxRanks] = {};     // the same array in every peer's arena
+  unsigned long long* my_flags = nullptr;             // [(1 + kMaxChan) * kMaxRanks] written by the peers
+  unsigned long long* peer_flags[kMaxRanks] = {};     // the same table in every peer's arena
   double* my_red = nullptr;                           // [2][kMaxRanks] all-reduce slots (parity double-buffered)
   double* peer_red[kMaxRanks] = {};
-  unsigned long long* epoch = nullptr;                // local exchange counter
-  int* error = nullptr;                               // set when a peer wait times out
+  unsigned long long* epoch = nullptr;                // [1 + kMaxChan] local counters: [0] all-reduce, [1 + c] channel c
+  int* error = nullptr;                               // set when a peer wait times out; every later wait returns at once
 };
+// a channel as seen by one kernel launch: id, peers it signals (producer) / waits for (consumer)
+struct Chan { int id = -1; unsigned mask = 0; };
 
 // Optional per-launch timing (CUDA events around every solve-phase kernel; used by bench.py's
 // roofline pass, never inside a timed region).

@@ -69,20 +69,29 @@ __device__ __forceinline__ double final_sum(const double* partials, int n, doubl
 }
 
 // ------------------------------------------------------------------ cross-GPU exchange (NVLink peer memory)
-// One CTA per GPU meets its peers: thread q publishes to peer q (value first, system fence, then the
-// epoch flag) and waits for peer q's flag.  Epochs increase monotonically and every GPU executes the
-// same sequence of exchanges, so no reset is ever needed; a wait that exceeds ~30 s raises the error
-// flag instead of hanging the GPU.
+// Flag words are epochs that only grow, and every GPU executes the same sequence of exchanges, so no
+// reset is ever needed.  A wait that exceeds ~10 s raises the error flag; once it is set every later
+// wait returns immediately (the PCG update kernel turns it into `done`, the host reports it).
+__device__ __forceinline__ void spin_until(const DistDev& d, volatile unsigned long long* f, unsigned long long ep) {
+  if (*(volatile int*)d.error) return;
+  const long long t0 = clock64();
+  unsigned spins = 0;
+  while (*f < ep) {
+    if ((++spins & 1023u) == 0) {
+      if (*(volatile int*)d.error) break;
+      if (clock64() - t0 > 20000000000ll) { *(volatile int*)d.error = 1; __threadfence_system(); break; }  // ~10 s: never hang the GPU
+    }
+  }
+}
+
+// all-ranks barrier of the all-reduce: thread q publishes to peer q (value first, system fence, then the
+// epoch) and waits for peer q's word.
 __device__ __forceinline__ void cross_signal_wait(const DistDev& d, unsigned long long ep) {
   const int t = threadIdx.x;
   if (t < d.nranks) {
     __threadfence_system();
     *(reinterpret_cast<volatile unsigned long long*>(d.peer_flags[t]) + d.rank) = ep;
-    volatile unsigned long long* f = reinterpret_cast<volatile unsigned long long*>(d.my_flags) + t;
-    const long long t0 = clock64();
-    while (*f < ep) {
-      if (clock64() - t0 > 60000000000ll) { *d.error = 1; break; }  // ~30 s: never hang the GPU
-    }
+    spin_until(d, reinterpret_cast<volatile unsigned long long*>(d.my_flags) + t, ep);
     __threadfence_system();
   }
   __syncthreads();
@@ -94,7 +103,7 @@ __device__ __forceinline__ double cross_sum(const DistDev& d, double local) {
   if (d.nranks == 1) return local;  // uniform
   __shared__ double s_val;
   __shared__ unsigned long long s_ep;
-  if (threadIdx.x == 0) { s_val = local; s_ep = ++(*d.epoch); }
+  if (threadIdx.x == 0) { s_val = local; s_ep = ++d.epoch[0]; }
   __syncthreads();
   const unsigned long long ep = s_ep;
   const int par = (int)(ep & 1ull) * kMaxRanks;
@@ -103,6 +112,31 @@ __device__ __forceinline__ double cross_sum(const DistDev& d, double local) {
   double tot = 0.0;
   if (threadIdx.x == 0) for (int q = 0; q < d.nranks; q++) tot += *(reinterpret_cast<volatile double*>(d.my_red) + par + q);
   return tot;
+}
+
+// producer side of a channel, called by the last CTA of a push kernel after all CTAs have fenced their
+// peer stores: bump the channel's epoch and publish it to the destination peers.  Never waits.
+__device__ __forceinline__ void chan_signal(const DistDev& d, Chan ch) {
+  __shared__ unsigned long long s_cep;
+  if (threadIdx.x == 0) s_cep = ++d.epoch[1 + ch.id];
+  __syncthreads();
+  if (threadIdx.x < d.nranks && threadIdx.x != d.rank && (ch.mask >> threadIdx.x & 1u)) {
+    __threadfence_system();
+    *(reinterpret_cast<volatile unsigned long long*>(d.peer_flags[threadIdx.x]) + (1 + ch.id) * kMaxRanks + d.rank) = s_cep;
+  }
+}
+
+// consumer side: every CTA that is about to read values pushed through channel `ch` calls this first.
+// The expected epoch is this GPU's own count of the channel (its own push precedes the consumer in stream
+// order and all GPUs run the same sequence).  Waits only for the peers in ch.mask (those that send to this GPU).
+__device__ __forceinline__ void chan_wait(const DistDev& d, Chan ch) {
+  if (ch.id < 0) return;  // uniform
+  if (threadIdx.x < d.nranks && threadIdx.x != d.rank && (ch.mask >> threadIdx.x & 1u)) {
+    const unsigned long long ep = *(reinterpret_cast<volatile unsigned long long*>(d.epoch) + 1 + ch.id);
+    spin_until(d, reinterpret_cast<volatile unsigned long long*>(d.my_flags) + (1 + ch.id) * kMaxRanks + threadIdx.x, ep);
+    __threadfence_system();
+  }
+  __syncthreads();
 }
 
 // Programmatic dependent launch: every kernel of the solve starts with griddepcontrol.wait
@@ -131,8 +165,9 @@ inline cudaLaunchConfig_t pdl_config(dim3 grid, dim3 block, size_t smem, cudaStr
 
 
 // pushes owned boundary values into the peers' copies of a vector: entry k of `list` goes to the peer
-// whose segment of list_ptr contains k.  The last CTA closes the exchange with a cross-GPU barrier.
-__global__ void __launch_bounds__(256) halo_push_kernel(DistDev d, int total, const int* __restrict__ list, const int* __restrict__ list_ptr,
+// whose segment of list_ptr contains k (same index in the peer's copy).  The last CTA publishes the
+// channel epoch to the destination peers; nobody waits here — the consumer kernel does (chan_wait).
+__global__ void __launch_bounds__(256) halo_push_kernel(DistDev d, Chan ch, int total, const int* __restrict__ list, const int* __restrict__ list_ptr,
                                                         const double* __restrict__ src, PeerPtrs dst, unsigned int* ticket,
                                                         const int* __restrict__ done) {
   pdl_wait();
@@ -148,16 +183,11 @@ __global__ void __launch_bounds__(256) halo_push_kernel(DistDev d, int total, co
   __syncthreads();
   if (threadIdx.x == 0) s_last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1);
   __syncthreads();
-  if (s_last) {
-    __shared__ unsigned long long s_ep;
-    if (threadIdx.x == 0) s_ep = ++(*d.epoch);
-    __syncthreads();
-    cross_signal_wait(d, s_ep);
-  }
+  if (s_last) chan_signal(d, ch);
 }
 
 // all-gather by peer stores: the owned slice [begin, end) of a vector is written into every peer's copy
-__global__ void __launch_bounds__(256) push_all_kernel(DistDev d, int begin, int end, const double* __restrict__ src, PeerPtrs dst,
+__global__ void __launch_bounds__(256) push_all_kernel(DistDev d, Chan ch, int begin, int end, const double* __restrict__ src, PeerPtrs dst,
                                                        unsigned int* ticket, const int* __restrict__ done) {
   pdl_wait();
   __shared__ int s_last;
@@ -170,12 +200,14 @@ __global__ void __launch_bounds__(256) push_all_kernel(DistDev d, int begin, int
   __syncthreads();
   if (threadIdx.x == 0) s_last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1);
   __syncthreads();
-  if (s_last) {
-    __shared__ unsigned long long s_ep;
-    if (threadIdx.x == 0) s_ep = ++(*d.epoch);
-    __syncthreads();
-    cross_signal_wait(d, s_ep);
-  }
+  if (s_last) chan_signal(d, ch);
+}
+
+// stand-alone consumer wait for kernels that have no wait hook of their own (smoothers, dense GEMV, gathers)
+__global__ void __launch_bounds__(32) chan_wait_kernel(DistDev d, Chan ch, const int* __restrict__ done) {
+  pdl_wait();
+  if (done && *done) return;
+  chan_wait(d, ch);
 }
 
 // ------------------------------------------------------------------ SpMV family (CSR-stream)
@@ -257,22 +289,25 @@ __global__ void __launch_bounds__(SPMV_ROWS) csr_stream_kernel(int n, const int*
 }
 
 template <int MODE>
-__global__ void spmv_vector_kernel(int row_begin, int n, const int* __restrict__ ptr, const int* __restrict__ col, const double* __restrict__ val,
-                                   const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ b,
-                                   const int* __restrict__ done);
+__global__ void spmv_vector_kernel(DistDev dist, Chan wch, int row_begin, int n, const int* __restrict__ ptr, const int* __restrict__ col,
+                                   const double* __restrict__ val, const double* __restrict__ x, double* __restrict__ y,
+                                   const double* __restrict__ b, const int* __restrict__ done);
 
 template <int MODE, bool DOT>
 void spmv_dispatch(const Ctx& c, const DCsr& A, const double* x, double* y, const double* b, double* partials, PcgScalars* sc,
-                   const int* done, const char* name, RowRange rr = RowRange()) {
+                   const int* done, const char* name, RowRange rr = RowRange(), Chan wch = Chan()) {
   int n = A.nrows;
   if (n == 0) return;
   g_launch_counter++;
   ProfScope ps(c, name);
   const bool ranged = rr.end >= 0;
   if (ranged && DOT) throw std::runtime_error("row-ranged CSR dot is not implemented (use the SELL copy)");
+  if (wch.id >= 0 && !ranged) throw std::runtime_error("a channel wait needs the row-ranged (sharded) SpMV");
   if (!DOT && (ranged || (double)A.nnz > 32.0 * n || n < 32768)) {  // long rows, a small operator or a row range: one warp per row
     const int r0 = ranged ? rr.begin : 0, r1 = ranged ? rr.end : n;
-    if (r1 > r0) FSB_LAUNCH((spmv_vector_kernel<MODE>), cdiv((long long)(r1 - r0) * 32, 256), 256, 0, c.stream, r0, r1, A.ptr, A.col, A.val, x, y, b, done);
+    // an empty range still launches one CTA when it has to consume a channel (the epoch bookkeeping is per launch)
+    if (r1 > r0 || wch.id >= 0)
+      FSB_LAUNCH((spmv_vector_kernel<MODE>), std::max(1, cdiv((long long)(r1 - r0) * 32, 256)), 256, 0, c.stream, c.dist, wch, r0, r1, A.ptr, A.col, A.val, x, y, b, done);
   } else
     FSB_LAUNCH((csr_stream_kernel<MODE, DOT>), cdiv(n, SPMV_ROWS), SPMV_ROWS, 0, c.stream, n, A.ptr, A.col, A.val, x, y, b, partials, sc, done);
   FSB_CHECK_LAUNCH();
@@ -282,7 +317,7 @@ void spmv_dispatch(const Ctx& c, const DCsr& A, const double* x, double* y, cons
 // request per warp for col and one for val; four steps are kept in flight together with their x
 // gathers.  The row sum runs in column order (same rounding sequence as a sequential CSR loop).
 template <int MODE, bool DOT>
-__global__ void __launch_bounds__(256) sell_spmv_kernel(DistDev dist, int row_begin, int row_end, int list_begin, int list_end,
+__global__ void __launch_bounds__(256) sell_spmv_kernel(DistDev dist, Chan wch, int row_begin, int row_end, int list_begin, int list_end,
                                                         const int* __restrict__ rowmap, int n, const long long* __restrict__ sptr,
                                                         const int* __restrict__ col, const double* __restrict__ val,
                                                         const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ b,
@@ -292,6 +327,7 @@ __global__ void __launch_bounds__(256) sell_spmv_kernel(DistDev dist, int row_be
   __shared__ double s_warp[32];
   __shared__ int s_flag;
   if (done && *done) return;
+  chan_wait(dist, wch);  // sharded solve: the halo values of x have arrived (no-op otherwise)
   // list position i (rows may be length-sorted inside windows: rowmap); owned rows are [row_begin, row_end).
   // The grid may be smaller than the list (fused dot: fewer partial sums and tickets): grid-stride over 256-row chunks.
   const int lane = threadIdx.x & 31;
@@ -352,7 +388,7 @@ __global__ void __launch_bounds__(256) sell_spmv_kernel(DistDev dist, int row_be
 
 template <int MODE, bool DOT>
 void sell_dispatch(const Ctx& c, const Sell& A, const double* x, double* y, const double* b, double* partials, PcgScalars* sc,
-                   const int* done, const char* name, RowRange rr = RowRange()) {
+                   const int* done, const char* name, RowRange rr = RowRange(), Chan wch = Chan()) {
   if (A.nrows == 0) return;
   const int r0 = rr.end >= 0 ? rr.begin : 0, r1 = rr.end >= 0 ? rr.end : A.nrows;
   g_launch_counter++;
@@ -360,11 +396,11 @@ void sell_dispatch(const Ctx& c, const Sell& A, const double* x, double* y, cons
   // list positions that can hold the owned rows: whole sort windows when the rows are length-sorted
   const int gran = A.window > 0 ? A.window : 32;
   const int l0 = r0 / gran * gran, l1 = std::min(A.nrows, (r1 + gran - 1) / gran * gran);
-  if (l1 <= l0) return;
+  if (l1 <= l0 && !DOT && wch.id < 0) return;  // (an empty owned range still takes part in the all-reduce / consumes its channel)
   static const int dot_ctas_per_sm = getenv("FSB_DOT_CTAS") ? atoi(getenv("FSB_DOT_CTAS")) : 12;  // tuning knob
-  int blocks = cdiv(l1 - l0, 256);
+  int blocks = std::max(1, cdiv(std::max(0, l1 - l0), 256));
   if (DOT) blocks = std::min(blocks, c.num_sms * dot_ctas_per_sm);
-  FSB_LAUNCH((sell_spmv_kernel<MODE, DOT>), blocks, 256, 0, c.stream, c.dist, r0, r1, l0, l1, A.rowmap.size() ? A.rowmap.get() : nullptr, A.nrows,
+  FSB_LAUNCH((sell_spmv_kernel<MODE, DOT>), blocks, 256, 0, c.stream, c.dist, wch, r0, r1, l0, l1, A.rowmap.size() ? A.rowmap.get() : nullptr, A.nrows,
                                                                        A.sptr, A.col, A.val, x, y, b, partials, sc, done);
   FSB_CHECK_LAUNCH();
 }
@@ -869,11 +905,13 @@ __global__ void __launch_bounds__(BLOCK) smooth_cluster_kernel(int C, int G, int
 
 // warp-per-row SpMV for long rows (restriction operators, coarse operators)
 template <int MODE>
-__global__ void __launch_bounds__(256) spmv_vector_kernel(int row_begin, int n, const int* __restrict__ ptr, const int* __restrict__ col,
-                                                          const double* __restrict__ val, const double* __restrict__ x,
-                                                          double* __restrict__ y, const double* __restrict__ b, const int* __restrict__ done) {
+__global__ void __launch_bounds__(256) spmv_vector_kernel(DistDev dist, Chan wch, int row_begin, int n, const int* __restrict__ ptr,
+                                                          const int* __restrict__ col, const double* __restrict__ val,
+                                                          const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ b,
+                                                          const int* __restrict__ done) {
   pdl_wait();
   if (done && *done) return;
+  chan_wait(dist, wch);  // sharded solve: the halo values this kernel gathers have arrived (no-op otherwise)
   const int row = row_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (row >= n) return;
   double s = 0.0;
@@ -1007,10 +1045,11 @@ __global__ void __launch_bounds__(128) coarse_gemv_row_kernel(int n, const doubl
 }
 
 // ------------------------------------------------------------------ PCG vector kernels
-__global__ void cg_init_kernel(PcgScalars* sc, double tol, int maxit) {
+__global__ void cg_init_kernel(PcgScalars* sc, double tol, int maxit, int hist_cap) {
   pdl_wait();
   sc->rz_old = sc->rz_new = sc->py = sc->alpha = sc->beta = sc->rr = sc->bnorm = 0.0;
-  sc->tol = tol; sc->done = 0; sc->niter = 0; sc->maxit = maxit; sc->hist_len = 0;
+  // maxit <= 0: the reference's while (niter < maxiters) loop applies no update at all (cgcycle.cu:34)
+  sc->tol = tol; sc->done = maxit <= 0 ? 1 : 0; sc->niter = 0; sc->maxit = maxit; sc->hist_len = 0; sc->hist_cap = hist_cap; sc->err = 0;
   for (int i = 0; i < 4; i++) sc->ticket[i] = 0;
 }
 
@@ -1030,7 +1069,7 @@ __global__ void __launch_bounds__(256) dot_kernel(DistDev dist, int n, const dou
   double bs = block_sum(v, s_warp);
   if (publish_partial(bs, partials, &sc->ticket[1], &s_flag)) {
     double tot = final_sum(partials, gridDim.x, s_warp);
-    if (WHICH != 0) tot = cross_sum(dist, tot);  // bnorm is computed from the full (replicated) b on every GPU
+    tot = cross_sum(dist, tot);  // all-reduce over the GPUs of a sharded solve (no-op on one GPU)
     if (threadIdx.x == 0) {
       if (WHICH == 0) sc->bnorm = sqrt(tot);
       else if (WHICH == 1) sc->rz_old = tot;
@@ -1073,9 +1112,11 @@ __global__ void __launch_bounds__(256) cg_update_kernel(DistDev dist, int n, dou
     if (threadIdx.x == 0) {
       sc->rr = tot;
       double rel = sqrt(tot) / sc->bnorm;
-      hist[sc->hist_len++] = rel;
+      if (sc->hist_len < sc->hist_cap) hist[sc->hist_len++] = rel;
       if (rel <= sc->tol) sc->done = 1;                 // cgcycle.cu:47
       else { sc->niter++; if (sc->niter >= sc->maxit) sc->done = 1; }  // :35, :50
+      // a peer that never arrived at an exchange (sharded solve): stop iterating, the host reports it
+      if (dist.nranks > 1 && *(volatile int*)dist.error) { sc->done = 1; sc->err = 1; }
     }
   }
 }
@@ -1108,35 +1149,41 @@ inline int vec_blocks(const Ctx& c, int n, bool reduces = false) {
 
 }  // namespace
 
-void launch_spmv(const Ctx& c, const DCsr& A, const double* x, double* y, int mode, const double* b, const int* done, const char* name, RowRange rr) {
-  if (mode == 0) spmv_dispatch<0, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr);
-  else if (mode == 1) spmv_dispatch<1, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr);
-  else if (mode == 2) spmv_dispatch<2, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr);
-  else spmv_dispatch<3, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr);
+void launch_spmv(const Ctx& c, const DCsr& A, const double* x, double* y, int mode, const double* b, const int* done, const char* name, RowRange rr, Chan wch) {
+  if (mode == 0) spmv_dispatch<0, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr, wch);
+  else if (mode == 1) spmv_dispatch<1, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr, wch);
+  else if (mode == 2) spmv_dispatch<2, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr, wch);
+  else spmv_dispatch<3, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr, wch);
 }
 
-void launch_spmv_sell(const Ctx& c, const Sell& A, const double* x, double* y, int mode, const double* b, const int* done, const char* name, RowRange rr) {
-  if (mode == 0) sell_dispatch<0, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr);
-  else if (mode == 1) sell_dispatch<1, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr);
-  else if (mode == 2) sell_dispatch<2, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr);
-  else sell_dispatch<3, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr);
+void launch_spmv_sell(const Ctx& c, const Sell& A, const double* x, double* y, int mode, const double* b, const int* done, const char* name, RowRange rr, Chan wch) {
+  if (mode == 0) sell_dispatch<0, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr, wch);
+  else if (mode == 1) sell_dispatch<1, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr, wch);
+  else if (mode == 2) sell_dispatch<2, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr, wch);
+  else sell_dispatch<3, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr, wch);
 }
-void launch_spmv_dot_sell(const Ctx& c, const Sell& A, const double* x, double* y, double* partials, PcgScalars* sc, RowRange rr) {
-  sell_dispatch<0, true>(c, A, x, y, nullptr, partials, sc, &sc->done, "spmv_dot", rr);
+void launch_spmv_dot_sell(const Ctx& c, const Sell& A, const double* x, double* y, double* partials, PcgScalars* sc, RowRange rr, Chan wch) {
+  sell_dispatch<0, true>(c, A, x, y, nullptr, partials, sc, &sc->done, "spmv_dot", rr, wch);
 }
 
-void launch_halo_push(const Ctx& c, int total, const int* list, const int* list_ptr, const double* src, const PeerPtrs& dst, const int* done) {
+void launch_halo_push(const Ctx& c, Chan ch, int total, const int* list, const int* list_ptr, const double* src, const PeerPtrs& dst, const int* done) {
   g_launch_counter++;
   ProfScope ps(c, "halo_push");
-  int blocks = std::max(1, std::min(cdiv(total, 256), c.num_sms * 4));
-  FSB_LAUNCH((halo_push_kernel), blocks, 256, 0, c.stream, c.dist, total, list, list_ptr, src, dst, c.dist_ticket, done);
+  int blocks = std::max(1, std::min(cdiv(total, 256), c.num_sms * 2));
+  FSB_LAUNCH((halo_push_kernel), blocks, 256, 0, c.stream, c.dist, ch, total, list, list_ptr, src, dst, c.dist_ticket, done);
   FSB_CHECK_LAUNCH();
 }
-void launch_push_all(const Ctx& c, int begin, int end, const double* src, const PeerPtrs& dst, const int* done) {
+void launch_push_all(const Ctx& c, Chan ch, int begin, int end, const double* src, const PeerPtrs& dst, const int* done) {
   g_launch_counter++;
   ProfScope ps(c, "push_all");
   int blocks = std::max(1, std::min(cdiv(end - begin, 256), c.num_sms * 4));
-  FSB_LAUNCH((push_all_kernel), blocks, 256, 0, c.stream, c.dist, begin, end, src, dst, c.dist_ticket, done);
+  FSB_LAUNCH((push_all_kernel), blocks, 256, 0, c.stream, c.dist, ch, begin, end, src, dst, c.dist_ticket, done);
+  FSB_CHECK_LAUNCH();
+}
+void launch_chan_wait(const Ctx& c, Chan ch, const int* done) {
+  g_launch_counter++;
+  ProfScope ps(c, "chan_wait");
+  FSB_LAUNCH((chan_wait_kernel), 1, 32, 0, c.stream, c.dist, ch, done);
   FSB_CHECK_LAUNCH();
 }
 
@@ -1149,7 +1196,9 @@ void launch_smooth(const Ctx& c, const LevelData& L, const double* b_src, const 
   g_launch_counter++;
   ProfScope ps(c, x_in ? "post_smooth" : "pre_smooth");
   cudaStream_t s = c.stream;
-  if (owned_only && !L.use_ell) throw std::runtime_error("sharded smoothing needs the ELL path on the sharded level");
+  // sharded level: this GPU smooths its own contiguous range of partitions only
+  const int p0 = owned_only ? L.ownP0 : 0, pn = owned_only ? L.ownPn : L.nparts;
+  if (pn <= 0) return;
   const int* nl = owned_only ? L.nlistOwn : L.nlist;
   const DevBuf<EllDesc>* pl = owned_only ? L.plistOwn : L.plist;
   static const bool serial = getenv("FSB_ELL_SERIAL") && atoi(getenv("FSB_ELL_SERIAL")) != 0;  // tuning knob: size classes one after the other
@@ -1185,33 +1234,30 @@ void launch_smooth(const Ctx& c, const LevelData& L, const double* b_src, const 
 #undef FSB_ELL_LAUNCH1
 #undef FSB_ELL_TAIL
   else if (L.use_sellg) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.first(c.device)) {
       FSB_CUDA(cudaFuncSetAttribute(smooth_sellg_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       FSB_CUDA(cudaFuncSetAttribute(smooth_sellg_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      attr_set = true;
     }
     // more partitions than SMs: two 512-thread CTAs per SM, each with half of the shared memory; else one 1024-thread CTA
     static const char* env_two = getenv("FSB_SELLG_TWO");  // tuning knob
-    const bool two = env_two ? atoi(env_two) != 0 : L.nparts > c.num_sms;
+    const bool two = env_two ? atoi(env_two) != 0 : pn > c.num_sms;
     const int npad = (L.maxPartRows + 15) & ~15;
     const size_t fixed = (size_t)(2 * (2 * npad + 8) + 3 * npad) * 8 + 16;
     const size_t limit = (two ? 113 : 226) * 1024 - 1024;
     int smemSlots = (int)std::min<long long>(L.sellgMaxSlots, (long long)((limit - fixed) / 10) & ~31LL);
     if (smemSlots < 0) smemSlots = 0;
     const size_t smem = fixed + (size_t)smemSlots * 10;
-#define FSB_SELLG_ARGS L.sellgDesc, L.ellG, npad, smemSlots, L.ellwptr, L.ellval, L.ellcol, L.ellrow, L.diag, b_src, gather, b_int, x_in, w, nsweeps, x_out, scatter, x_ext, r_out, done
-    if (two) FSB_LAUNCH((smooth_sellg_kernel<512>), L.nparts, 512, smem, s, FSB_SELLG_ARGS);
-    else FSB_LAUNCH((smooth_sellg_kernel<1024>), L.nparts, 1024, smem, s, FSB_SELLG_ARGS);
+#define FSB_SELLG_ARGS L.sellgDesc.get() + p0, L.ellG, npad, smemSlots, L.ellwptr, L.ellval, L.ellcol, L.ellrow, L.diag, b_src, gather, b_int, x_in, w, nsweeps, x_out, scatter, x_ext, r_out, done
+    if (two) FSB_LAUNCH((smooth_sellg_kernel<512>), pn, 512, smem, s, FSB_SELLG_ARGS);
+    else FSB_LAUNCH((smooth_sellg_kernel<1024>), pn, 1024, smem, s, FSB_SELLG_ARGS);
 #undef FSB_SELLG_ARGS
   } else if (L.smemBytes > 0) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.first(c.device))
       FSB_CUDA(cudaFuncSetAttribute(smooth_cluster_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      attr_set = true;
-    }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(L.nparts * L.clusterC); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = L.smemBytes; cfg.stream = s;
+    cfg.gridDim = dim3(pn * L.clusterC); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = L.smemBytes; cfg.stream = s;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = L.clusterC; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -1219,10 +1265,10 @@ void launch_smooth(const Ctx& c, const LevelData& L, const double* b_src, const 
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl_config(dim3(1), dim3(1), 0, s).numAttrs ? 2 : 1;
     FSB_CUDA(cudaLaunchKernelEx(&cfg, smooth_cluster_kernel<512>, L.clusterC, L.coopG, L.maxChunkNnz, L.maxPartRows, L.maxChunkRows,
-                                (const int*)L.pstart.get(), (const int*)L.A.ptr.get(), (const int*)L.A.col.get(), (const double*)L.A.val.get(),
+                                (const int*)L.pstart.get() + p0, (const int*)L.A.ptr.get(), (const int*)L.A.col.get(), (const double*)L.A.val.get(),
                                 (const double*)L.diag.get(), b_src, gather, b_int, x_in, w, nsweeps, x_out, scatter, x_ext, r_out, done));
   } else
-    FSB_LAUNCH((smooth_coop_kernel<512>), L.nparts, 512, 0, s, L.coopG, L.pstart, L.A.ptr, L.A.col, L.A.val, L.diag, b_src, gather, b_int, x_in, w,
+    FSB_LAUNCH((smooth_coop_kernel<512>), pn, 512, 0, s, L.coopG, L.pstart.get() + p0, L.A.ptr, L.A.col, L.A.val, L.diag, b_src, gather, b_int, x_in, w,
                                                     nsweeps, x_out, scatter, x_ext, r_out, done);
   FSB_CHECK_LAUNCH();
 }
@@ -1250,8 +1296,8 @@ void launch_coarse_solve(const Ctx& c, int n, const double* Ainv, const double* 
   FSB_CHECK_LAUNCH();
 }
 
-void launch_cg_init(const Ctx& c, PcgScalars* sc, double tol, int maxit) {
-  FSB_LAUNCH((cg_init_kernel), 1, 1, 0, c.stream, sc, tol, maxit);
+void launch_cg_init(const Ctx& c, PcgScalars* sc, double tol, int maxit, int hist_cap) {
+  FSB_LAUNCH((cg_init_kernel), 1, 1, 0, c.stream, sc, tol, maxit, hist_cap);
   FSB_CHECK_LAUNCH();
 }
 

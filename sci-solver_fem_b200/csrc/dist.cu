@@ -1,16 +1,26 @@
 // dist.cu — stage 4: sharding the PCG solve over the GPUs of one box (absent upstream, F9).
 //
 // Design: one process per GPU.  Setup is REPLICATED (every GPU assembles the mesh and builds the
-// identical, deterministic hierarchy — no setup communication at all); the solve is SHARDED on the
-// fine level: the reference's partitions (<= 1024-row blocks whose rows are contiguous) are dealt out
-// in contiguous, nnz-balanced ranges, i.e. a GPU is a super-partition in the reference's own
-// A_in / A_out sense.  Every GPU keeps full-length vectors but computes only its rows; the values a
-// peer needs (operator columns across the cut, restriction rows across the cut) are PUSHED into the
-// peer's copy by plain stores through NVLink peer mappings (CUDA IPC), followed by a flag-based
-// cross-GPU barrier executed by the last CTA of the push kernel.  Dot products are all-reduced the same
-// way inside the reduction kernels (cycle.cu: cross_sum).  Coarse levels (>= 1) are small and are
-// computed redundantly on every GPU after an all-gather (push_all) of the restricted residual.
+// identical, deterministic hierarchy — no setup communication at all); the solve is SHARDED level by
+// level: on every level that is large enough the reference's partitions (<= 1024-row blocks whose rows
+// are contiguous in the level's permuted numbering) are dealt out in contiguous, nnz-balanced ranges, i.e.
+// a GPU is a super-partition in the reference's own A_in / A_out sense (smoothedMG_amg_level.cu:199-304).
+// Every GPU keeps full-length vectors but computes only its rows.  What a peer needs —
+//   * operator columns across the cut (x after pre-smoothing, x after the coarse correction, the PCG
+//     direction p),
+//   * residual rows its restriction rows reference,
+//   * restricted-residual entries of rows it owns on the next level ("down"), coarse corrections its
+//     prolongator rows reference ("up"),
+// is PUSHED into the peer's copy by plain stores through NVLink peer mappings (CUDA IPC) by a small
+// producer kernel that then publishes a per-channel epoch flag to exactly the peers it wrote to and
+// never waits; the consumer kernel waits in its prologue for exactly the peers it receives from
+// (cycle.cu: chan_signal / chan_wait).  Dot products are all-reduced inside the reduction kernels
+// (cycle.cu: cross_sum).  The levels below the sharded ones are small and are computed redundantly on
+// every GPU after an all-gather of the restricted residual — the coarse grid is agglomerated onto
+// every GPU instead of onto one, so the way back up needs no communication.
 #include <algorithm>
+#include <climits>
+#include <cstring>
 #include <numeric>
 
 #include "kernels.h"
@@ -45,41 +55,103 @@ __device__ __forceinline__ int owner_of(const Ranges& rg, int i) {
   return q;
 }
 
-// flags[q * nown + (j - myb)] = 1 when a row owned by q != me references my row j
-__global__ void mark_needed_kernel(int nrows, const int* __restrict__ ptr, const int* __restrict__ col, Ranges rowOwner, Ranges colOwner,
-                                   int me, int myb, int mye, int* __restrict__ flags) {
+// Generic "who needs which of my values" marking.  Row i (owner by rowOwner) references the entries
+// col[ptr[i] .. ptr[i+1]) (ptr == null: the single entry col[i]); an entry j is first mapped through
+// colmap when given (e.g. external -> internal numbering); it is MINE when it falls into [myb, mye).
+// flags[q * nown + (j - myb)] = 1 when a row owned by q != me references my value j.
+__global__ void mark_needed_kernel(int nrows, const int* __restrict__ ptr, const int* __restrict__ col, const int* __restrict__ colmap,
+                                   Ranges rowOwner, int me, int myb, int mye, int* __restrict__ flags) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nrows) return;
   int q = owner_of(rowOwner, i);
   if (q == me) return;
   int nown = mye - myb;
-  for (int e = ptr[i]; e < ptr[i + 1]; e++) {
+  const int e0 = ptr ? ptr[i] : i, e1 = ptr ? ptr[i + 1] : i + 1;
+  for (int e = e0; e < e1; e++) {
     int j = col[e];
+    if (colmap) j = colmap[j];
     if (j >= myb && j < mye) flags[(size_t)q * nown + (j - myb)] = 1;
   }
-  (void)colOwner;
 }
-__global__ void fill_list_kernel(long long total, int nown, int myb, const int* __restrict__ flags, const int* __restrict__ pos, int* __restrict__ list) {
+// the other direction: which peers own values that MY rows [r0, r1) reference -> bit mask
+__global__ void mark_sources_kernel(int r0, int r1, const int* __restrict__ ptr, const int* __restrict__ col, const int* __restrict__ colmap,
+                                    Ranges colOwner, int me, unsigned* __restrict__ mask) {
+  int i = r0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= r1) return;
+  unsigned m = 0;
+  const int e0 = ptr ? ptr[i] : i, e1 = ptr ? ptr[i + 1] : i + 1;
+  for (int e = e0; e < e1; e++) {
+    int j = col[e];
+    if (colmap) j = colmap[j];
+    int q = owner_of(colOwner, j);
+    if (q != me) m |= 1u << q;
+  }
+  if (m) atomicOr(mask, m);
+}
+__global__ void fill_list_kernel(long long total, int nown, int myb, const int* __restrict__ flags, const int* __restrict__ pos,
+                                 const int* __restrict__ valmap, int* __restrict__ list) {
   long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (k < total && flags[k]) list[pos[k] - 1] = myb + (int)(k % nown);
-}
-
-void build_send_list(const Ctx& c, int nranks, int nown, int myb, IBuf& flags, IBuf& list, IBuf& list_ptr, int& total) {
-  cudaStream_t s = c.stream;
-  size_t m = (size_t)nranks * nown;
-  IBuf pos(m, s);
-  inclusive_scan_i32(flags, pos, m, s);
-  std::vector<int> ptr_h(nranks + 1, 0);
-  for (int q = 0; q < nranks; q++) ptr_h[q + 1] = nown > 0 ? pos.read((size_t)(q + 1) * nown - 1) : 0;
-  total = ptr_h[nranks];
-  list.alloc(std::max(1, total), s);
-  fill_list_kernel<<<cdiv((long long)m, 256), 256, 0, s>>>((long long)m, nown, myb, flags, pos, list);
-  list_ptr.alloc(nranks + 1, s);
-  list_ptr.from_host(ptr_h.data(), nranks + 1);
-  FSB_CUDA(cudaStreamSynchronize(s));
+  if (k < total && flags[k]) {
+    const int j = myb + (int)(k % nown);
+    list[pos[k] - 1] = valmap ? valmap[j] : j;
+  }
 }
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// One exchange: `nrows` consumer rows (owner by rowOwner) reference values (col / colmap) of which
+// [myb, mye) are mine; the list stores valmap[j] (or j) = index into the exchanged vector.
+void build_push_list(const Ctx& c, int nranks, int me, int nrows, const int* ptr, const int* col, const int* colmap, const Ranges& rowOwner,
+                     const Ranges& colOwner, int myb, int mye, const int* valmap, Solver::PushList& out) {
+  cudaStream_t s = c.stream;
+  const int nown = std::max(mye - myb, 0);
+  out.total = 0; out.dst_mask = 0; out.src_mask = 0;
+  std::vector<int> ptr_h(nranks + 1, 0);
+  if (nown > 0 && nrows > 0) {
+    const size_t m = (size_t)nranks * nown;
+    IBuf flags(m, s), pos(m, s);
+    flags.zero();
+    mark_needed_kernel<<<cdiv(nrows, 256), 256, 0, s>>>(nrows, ptr, col, colmap, rowOwner, me, myb, mye, flags);
+    inclusive_scan_i32(flags, pos, m, s);
+    for (int q = 0; q < nranks; q++) ptr_h[q + 1] = pos.read((size_t)(q + 1) * nown - 1);
+    out.total = ptr_h[nranks];
+    out.idx.alloc(std::max(1, out.total), s);
+    fill_list_kernel<<<cdiv((long long)m, 256), 256, 0, s>>>((long long)m, nown, myb, flags, pos, valmap, out.idx);
+    FSB_CUDA(cudaStreamSynchronize(s));
+  } else {
+    out.idx.alloc(1, s);
+  }
+  for (int q = 0; q < nranks; q++) if (ptr_h[q + 1] > ptr_h[q]) out.dst_mask |= 1u << q;
+  out.ptr.alloc(nranks + 1, s);
+  out.ptr.from_host(ptr_h.data(), nranks + 1);
+  // who sends to me: the owners of the values my own consumer rows reference
+  const int r0 = rowOwner.b[me], r1 = rowOwner.b[me + 1];
+  DevBuf<unsigned> mask(1, s);
+  mask.zero();
+  if (r1 > r0) mark_sources_kernel<<<cdiv(r1 - r0, 256), 256, 0, s>>>(r0, r1, ptr, col, colmap, colOwner, me, mask);
+  FSB_CHECK_LAUNCH();
+  out.src_mask = mask.read(0);
+  FSB_CUDA(cudaStreamSynchronize(s));
+}
+
+Ranges make_ranges(const int* b, int nranks) {
+  Ranges r;
+  r.n = nranks;
+  for (int q = 0; q <= nranks; q++) r.b[q] = b[q];
+  for (int q = nranks + 1; q <= kMaxRanks; q++) r.b[q] = b[nranks];
+  return r;
+}
+
+__global__ void minmax_gather_kernel(int r0, int r1, const int* __restrict__ idx, int* __restrict__ lohi) {
+  int lo = INT_MAX, hi = INT_MIN;
+  for (int i = r0 + blockIdx.x * blockDim.x + threadIdx.x; i < r1; i += gridDim.x * blockDim.x) {
+    const int v = idx[i];
+    lo = min(lo, v); hi = max(hi, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+  if ((threadIdx.x & 31) == 0 && lo <= hi) { atomicMin(&lohi[0], lo); atomicMax(&lohi[1], hi); }
+}
 
 }  // namespace
 
@@ -93,15 +165,19 @@ void Solver::dist_disconnect() {
   if (dist.arena) {
     // the vectors that were views into the arena become ordinary buffers again on the next solve
     cg_p.release(); cg_x.release();
-    if (!levels.empty()) {
-      LevelData& L0 = levels[0];
-      cudaStream_t s = ctx.stream;
-      L0.x.release(); L0.r.release(); L0.bc.release();
-      L0.x.alloc(L0.n, s); L0.r.alloc(L0.n, s); L0.bc.alloc(std::max(1, L0.nnout), s);
+    cudaStream_t s = ctx.stream;
+    for (int l = 0; l < dist.nshard && l < (int)levels.size(); l++) {
+      LevelData& L = levels[l];
+      L.x.release(); L.r.release(); L.bc.release(); L.xc.release();
+      L.x.alloc(L.n, s); L.r.alloc(L.n, s); L.bc.alloc(std::max(1, L.nnout), s); L.xc.alloc(std::max(1, L.nnout), s);
+      L.ownP0 = 0; L.ownPn = 0;
     }
+    FSB_CUDA(cudaStreamSynchronize(s));
     cudaFree(dist.arena);
     dist.arena = nullptr;
   }
+  dist.lev.clear();
+  dist.nshard = 0;
   dist.connected = false;
   dist.nranks = 1; dist.rank = 0;
   ctx.dist = DistDev();
@@ -111,63 +187,113 @@ void Solver::dist_disconnect() {
 void Solver::dist_prepare(int rank, int nranks) {
   if (!has_setup) throw std::runtime_error("dist_prepare before setup");
   if (nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks) throw std::invalid_argument("bad rank / nranks (at most 8 GPUs of one box)");
+  FSB_CUDA(cudaSetDevice(ctx.device));
   dist_disconnect();
   dist.rank = rank; dist.nranks = nranks;
   if (nranks == 1) return;
   if (levels.size() < 2 || !levels[0].use_ell || !levels[0].sA.ready() || !levels[0].sAout.ready() || !levels[0].sP.ready())
     throw std::runtime_error("sharded solve needs a fine level with >= 32768 rows on the ELL/SELL path");
   cudaStream_t s = ctx.stream;
-  LevelData& L0 = levels[0];
-  const int np = L0.nparts, n = L0.n, n1 = L0.nnout;
-  // 1. nnz-balanced contiguous ranges of partitions
-  std::vector<int> ps = L0.pstart.to_vector(), pidx = L0.agg.partitionIdx.to_vector();
-  std::vector<int> rowptr = L0.A.ptr.to_vector();
-  std::vector<long long> w(np);
-  for (int p = 0; p < np; p++) w[p] = rowptr[ps[p + 1]] - rowptr[ps[p]];
-  split_by_weight(np, w.data(), nranks, dist.pbeg);
-  for (int r = 0; r <= nranks; r++) { dist.rbeg[r] = ps[dist.pbeg[r]]; dist.abeg[r] = pidx[dist.pbeg[r]]; }
-  const int myb = dist.rbeg[rank], mye = dist.rbeg[rank + 1], nown = mye - myb;
-  // 2. owned partition lists of the smoother's size classes
-  {
-    std::vector<EllDesc> lists[kEllClasses];
-    for (int p = dist.pbeg[rank]; p < dist.pbeg[rank + 1]; p++) lists[ell_class(ps[p + 1] - ps[p])].push_back(L0.ellDescHost[p]);
-    for (int q = 0; q < kEllClasses; q++) {
-      L0.nlistOwn[q] = (int)lists[q].size();
-      L0.plistOwn[q].alloc(std::max<size_t>(1, lists[q].size()), s);
-      if (!lists[q].empty()) L0.plistOwn[q].from_host(lists[q].data(), lists[q].size());
+  // which levels are sharded: the fine level always; a coarser one while every GPU still gets enough rows to fill it
+  // and the level is a regular smoothing level (above the dense tail / the coarsest level)
+  static const int min_rows_per_rank = getenv("FSB_SHARD_MINROWS") ? atoi(getenv("FSB_SHARD_MINROWS")) : 16384;  // tuning knob
+  static const int max_shard_levels = getenv("FSB_SHARD_LEVELS") ? atoi(getenv("FSB_SHARD_LEVELS")) : 4;        // tuning knob
+  const int last_smoothing = (tail_level_ >= 0 ? tail_level_ : (int)levels.size() - 1) - 1;
+  int nshard = 1;
+  while (nshard <= last_smoothing && nshard < max_shard_levels && levels[nshard].nparts >= nranks &&
+         (long long)levels[nshard].n >= (long long)min_rows_per_rank * nranks && kChanLevel0 + kChanPerLevel * (nshard + 1) <= kMaxChan)
+    nshard++;
+  dist.nshard = nshard;
+  dist.lev.clear();
+  dist.lev.resize(nshard);
+  // 1. nnz-balanced contiguous ranges of partitions on every sharded level
+  std::vector<std::vector<int>> ps(nshard);
+  for (int l = 0; l < nshard; l++) {
+    LevelData& L = levels[l];
+    DistLevel& D = dist.lev[l];
+    const int np = L.nparts;
+    ps[l] = L.pstart.to_vector();
+    std::vector<int> pidx = L.agg.partitionIdx.to_vector(), rowptr = L.A.ptr.to_vector();
+    std::vector<long long> w(np);
+    for (int p = 0; p < np; p++) w[p] = rowptr[ps[l][p + 1]] - rowptr[ps[l][p]];
+    split_by_weight(np, w.data(), nranks, D.pbeg);
+    for (int r = 0; r <= nranks; r++) { D.rbeg[r] = ps[l][D.pbeg[r]]; D.abeg[r] = pidx[D.pbeg[r]]; }
+    L.ownP0 = D.pbeg[rank]; L.ownPn = D.pbeg[rank + 1] - D.pbeg[rank];
+    if (L.use_ell) {  // owned partition lists of the register-resident smoother's size classes
+      std::vector<EllDesc> lists[kEllClasses];
+      for (int p = D.pbeg[rank]; p < D.pbeg[rank + 1]; p++) lists[ell_class(ps[l][p + 1] - ps[l][p])].push_back(L.ellDescHost[p]);
+      for (int q = 0; q < kEllClasses; q++) {
+        L.nlistOwn[q] = (int)lists[q].size();
+        L.plistOwn[q].alloc(std::max<size_t>(1, lists[q].size()), s);
+        if (!lists[q].empty()) L.plistOwn[q].from_host(lists[q].data(), lists[q].size());
+      }
     }
   }
-  // 3. send lists: my rows that a peer's operator rows (A) / restriction rows (R) reference
-  Ranges rowsR, aggsR;
-  rowsR.n = aggsR.n = nranks;
-  for (int r = 0; r <= nranks; r++) { rowsR.b[r] = dist.rbeg[r]; aggsR.b[r] = dist.abeg[r]; }
-  {
-    IBuf flags((size_t)nranks * std::max(nown, 1), s);
-    flags.zero();
-    mark_needed_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, L0.A.ptr, L0.A.col, rowsR, rowsR, rank, myb, mye, flags);
-    build_send_list(ctx, nranks, nown, myb, flags, dist.sendA, dist.sendA_ptr, dist.nSendA);
-    flags.zero();
-    mark_needed_kernel<<<cdiv(n1, 256), 256, 0, s>>>(n1, L0.R.ptr, L0.R.col, aggsR, rowsR, rank, myb, mye, flags);
-    build_send_list(ctx, nranks, nown, myb, flags, dist.sendR, dist.sendR_ptr, dist.nSendR);
+  // 2. push lists
+  for (int l = 0; l < nshard; l++) {
+    LevelData& L = levels[l];
+    DistLevel& D = dist.lev[l];
+    const Ranges rows = make_ranges(D.rbeg, nranks), aggs = make_ranges(D.abeg, nranks);
+    const int myb = D.rbeg[rank], mye = D.rbeg[rank + 1];
+    // my rows that a peer's operator rows reference
+    build_push_list(ctx, nranks, rank, L.n, L.A.ptr, L.A.col, nullptr, rows, rows, myb, mye, nullptr, D.sendA);
+    // my rows that a peer's restriction rows reference (rows of R = next level's external numbering)
+    build_push_list(ctx, nranks, rank, L.nnout, L.R.ptr, L.R.col, nullptr, aggs, rows, myb, mye, nullptr, D.sendR);
+    if (l + 1 < nshard) {
+      LevelData& Ln = levels[l + 1];
+      DistLevel& Dn = dist.lev[l + 1];
+      const Ranges rowsN = make_ranges(Dn.rbeg, nranks);
+      // down: internal row i of the next level reads bc[ipermutation[i]]; I computed the entries of my aggregates
+      build_push_list(ctx, nranks, rank, Ln.n, nullptr, Ln.agg.ipermutation, nullptr, rowsN, aggs, D.abeg[rank], D.abeg[rank + 1], nullptr, D.sendDown);
+      // up: a prolongator row (owner by this level's rows) references xc[e], e external on the next level; mine when
+      // permutation[e] is one of my next-level rows; the pushed index is e = ipermutation[internal]
+      build_push_list(ctx, nranks, rank, L.n, L.P.ptr, L.P.col, Ln.agg.permutation, rows, rowsN, Dn.rbeg[rank], Dn.rbeg[rank + 1], Ln.agg.ipermutation,
+                      D.sendUp);
+    }
   }
-  // 4. arena (identical layout on every rank): flags | reduction slots | p | x | r | bc | cg_x
+  // 3. user-numbering range that covers my fine rows (host-buffer solves move only this slice over PCIe)
+  {
+    LevelData& L0 = levels[0];
+    IBuf lohi(2, s);
+    const int init[2] = {INT_MAX, INT_MIN};
+    lohi.from_host(init, 2);
+    const int r0 = dist.lev[0].rbeg[rank], r1 = dist.lev[0].rbeg[rank + 1];
+    if (r1 > r0 && !prm.refLevel0NoPerm) {
+      minmax_gather_kernel<<<std::min(cdiv(r1 - r0, 256), 4 * ctx.num_sms), 256, 0, s>>>(r0, r1, L0.agg.ipermutation, lohi);
+      FSB_CHECK_LAUNCH();
+      std::vector<int> r = lohi.to_vector();
+      dist.user_lo = r[0]; dist.user_hi = r[1] + 1;
+    } else { dist.user_lo = r0; dist.user_hi = r1; }
+  }
+  // 4. arena (identical layout on every rank): flag table | reduction slots | p | cg_x | per sharded level x, r, bc, xc
   size_t off = 0;
-  dist.off_flags = off; off = align_up(off + kMaxRanks * sizeof(unsigned long long), 256);
+  dist.off_flags = off; off = align_up(off + (size_t)(1 + kMaxChan) * kMaxRanks * sizeof(unsigned long long), 256);
   dist.off_red = off; off = align_up(off + 2 * kMaxRanks * sizeof(double), 256);
+  const int n = levels[0].n;
   dist.off_p = off; off = align_up(off + (size_t)n * 8, 256);
-  dist.off_x = off; off = align_up(off + (size_t)n * 8, 256);
-  dist.off_r = off; off = align_up(off + (size_t)n * 8, 256);
-  dist.off_bc = off; off = align_up(off + (size_t)std::max(n1, 1) * 8, 256);
   dist.off_cgx = off; off = align_up(off + (size_t)n * 8, 256);
+  for (int l = 0; l < nshard; l++) {
+    DistLevel& D = dist.lev[l];
+    const size_t nl = (size_t)levels[l].n, nc = (size_t)std::max(levels[l].nnout, 1);
+    D.off_x = off; off = align_up(off + nl * 8, 256);
+    D.off_r = off; off = align_up(off + nl * 8, 256);
+    D.off_bc = off; off = align_up(off + nc * 8, 256);
+    D.off_xc = off; off = align_up(off + nc * 8, 256);
+  }
   dist.arena_bytes = off;
   FSB_CUDA(cudaMalloc((void**)&dist.arena, dist.arena_bytes));
   FSB_CUDA(cudaMemsetAsync(dist.arena, 0, dist.arena_bytes, s));
   cg_p.view(reinterpret_cast<double*>(dist.arena + dist.off_p), n, s);
   cg_x.view(reinterpret_cast<double*>(dist.arena + dist.off_cgx), n, s);
-  L0.x.view(reinterpret_cast<double*>(dist.arena + dist.off_x), n, s);
-  L0.r.view(reinterpret_cast<double*>(dist.arena + dist.off_r), n, s);
-  L0.bc.view(reinterpret_cast<double*>(dist.arena + dist.off_bc), n1, s);
-  dist.epoch.alloc(1, s); dist.epoch.zero();
+  for (int l = 0; l < nshard; l++) {
+    LevelData& L = levels[l];
+    DistLevel& D = dist.lev[l];
+    L.x.view(reinterpret_cast<double*>(dist.arena + D.off_x), L.n, s);
+    L.r.view(reinterpret_cast<double*>(dist.arena + D.off_r), L.n, s);
+    L.bc.view(reinterpret_cast<double*>(dist.arena + D.off_bc), L.nnout, s);
+    L.xc.view(reinterpret_cast<double*>(dist.arena + D.off_xc), L.nnout, s);
+  }
+  dist.epoch.alloc(1 + kMaxChan, s); dist.epoch.zero();
   dist.error.alloc(1, s); dist.error.zero();
   dist.ticket.alloc(1, s); dist.ticket.zero();
   FSB_CUDA(cudaStreamSynchronize(s));
@@ -184,6 +310,7 @@ void Solver::dist_get_handle(void* handle64, long long* bytes) {
 
 void Solver::dist_connect(const void* handles) {
   if (!dist.arena) throw std::runtime_error("dist_connect before dist_prepare");
+  FSB_CUDA(cudaSetDevice(ctx.device));
   const char* hb = static_cast<const char*>(handles);
   for (int q = 0; q < dist.nranks; q++) {
     if (q == dist.rank) { dist.peer[q] = dist.arena; continue; }

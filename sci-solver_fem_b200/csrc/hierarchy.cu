@@ -427,9 +427,9 @@ void spgemm(const Ctx& c, const DCsr& A, const DCsr& B, DCsr& C) {
   // rows with few products: one thread each; rows with many (long A-rows, e.g. R * (A P)): one warp each
   const bool long_rows = (double)A.nnz > 64.0 * n;
   if (long_rows) {
-    static bool attr_set = false;
+    static PerDeviceOnce attr_once;
     const size_t smem = (size_t)((WG_SMEM_PER_WARP + 15) & ~15) * WG_WARPS;
-    if (!attr_set) { FSB_CUDA(cudaFuncSetAttribute(spgemm_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+    if (attr_once.first(c.device)) FSB_CUDA(cudaFuncSetAttribute(spgemm_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     spgemm_warp_kernel<<<cdiv(n, WG_WARPS), 32 * WG_WARPS, smem, s>>>(n, A.ptr, A.col, A.val, B.ptr, B.col, B.val, sbase, scol, sval, count);
     // rows it could not take (very long A-rows / too many distinct columns): thread-per-row kernel, restricted to them
     spgemm_rows<<<cdiv(n, 64), 64, 0, s>>>(n, A.ptr, A.col, A.val, B.ptr, B.col, B.val, sbase, scol, sval, count, 1);

@@ -6,14 +6,18 @@ namespace fsb {
 
 // y = A x (mode 0), y = b - A x (1), y += A x (2), y -= A x (3); CSR-stream kernel. `name` tags the profile.
 void launch_spmv(const Ctx& c, const DCsr& A, const double* x, double* y, int mode, const double* b, const int* done, const char* name,
-                 RowRange rr = RowRange());
+                 RowRange rr = RowRange(), Chan wch = Chan());
 // same operation on the SELL-32 copy of an operator (thread per row, coalesced, no staging)
 void launch_spmv_sell(const Ctx& c, const Sell& A, const double* x, double* y, int mode, const double* b, const int* done, const char* name,
-                      RowRange rr = RowRange());
-void launch_spmv_dot_sell(const Ctx& c, const Sell& A, const double* x, double* y, double* partials, PcgScalars* sc, RowRange rr = RowRange());
-// multi-GPU exchanges over NVLink peer memory (each ends with a cross-GPU barrier in its last CTA)
-void launch_halo_push(const Ctx& c, int total, const int* list, const int* list_ptr, const double* src, const PeerPtrs& dst, const int* done);
-void launch_push_all(const Ctx& c, int begin, int end, const double* src, const PeerPtrs& dst, const int* done);
+                      RowRange rr = RowRange(), Chan wch = Chan());
+void launch_spmv_dot_sell(const Ctx& c, const Sell& A, const double* x, double* y, double* partials, PcgScalars* sc, RowRange rr = RowRange(),
+                          Chan wch = Chan());
+// multi-GPU exchanges over NVLink peer memory: the producer stores into the peers' copies and publishes the
+// channel epoch (never waits); the consumer kernel waits for the peers it receives from (wch), or a
+// stand-alone wait kernel does when the consumer has no hook
+void launch_halo_push(const Ctx& c, Chan ch, int total, const int* list, const int* list_ptr, const double* src, const PeerPtrs& dst, const int* done);
+void launch_push_all(const Ctx& c, Chan ch, int begin, int end, const double* src, const PeerPtrs& dst, const int* done);
+void launch_chan_wait(const Ctx& c, Chan ch, const int* done);
 // y = A x and the dot product x.y folded into the same pass; the last CTA finishes
 // py and alpha = rz_old / py in device memory.
 void launch_spmv_dot(const Ctx& c, const DCsr& A, const double* x, double* y, double* partials, PcgScalars* sc);
@@ -31,7 +35,7 @@ void launch_restrict_fused(const Ctx& c, const DCsr& R, const double* b, const D
 void launch_coarse_solve(const Ctx& c, int n, const double* Ainv, const double* b, double* x, const int* done);
 
 // PCG vector kernels (device-resident scalars)
-void launch_cg_init(const Ctx& c, PcgScalars* sc, double tol, int maxit);
+void launch_cg_init(const Ctx& c, PcgScalars* sc, double tol, int maxit, int hist_cap);
 void launch_dot(const Ctx& c, int n, const double* a, const double* b, double* partials, PcgScalars* sc, int which);  // which: 0 bnorm, 1 rz(first), 2 rz(new)+beta
 void launch_cg_update(const Ctx& c, int n, double* x, double* r, const double* p, const double* y, double* partials, PcgScalars* sc, double* hist);
 void launch_cg_pdir(const Ctx& c, int n, double* p, const double* z, const PcgScalars* sc, int first);

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <chrono>
+#include <climits>
 #include <cstring>
 
 #include "kernels.h"
@@ -72,8 +73,23 @@ void Solver::toc(const char* name) {
 }
 
 // ----------------------------------------------------------------------------- stage 1
+// smallest / largest vertex index of the element list (a malformed .ele file must not reach the pattern kernels)
+__global__ static void index_range_kernel(long long m, const int* __restrict__ e, int* __restrict__ lohi) {
+  int lo = INT_MAX, hi = INT_MIN;
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < m; k += (long long)gridDim.x * blockDim.x) {
+    const int v = e[k];
+    lo = min(lo, v); hi = max(hi, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+  if ((threadIdx.x & 31) == 0 && lo <= hi) { atomicMin(&lohi[0], lo); atomicMax(&lohi[1], hi); }
+}
+
 void Solver::set_mesh(int nv, const double* xyz, int ne, int npe, const int* elems, const int* labels, bool on_device) {
   if (npe != 3 && npe != 4) throw std::invalid_argument("npe must be 3 (triangles) or 4 (tetrahedra)");
+  if (nv <= 0 || ne < 0 || !xyz || (ne > 0 && !elems)) throw std::invalid_argument("empty mesh");
+  // capacity of the 32-bit contribution ids / entry counts of the pattern stage (pattern.cu)
+  if ((long long)ne * npe * npe + nv >= 0xffffffffLL) throw std::invalid_argument("mesh too large: elements x slots must stay below 2^32");
   FSB_CUDA(cudaSetDevice(ctx.device));
   cudaStream_t s = ctx.stream;
   mesh.nv = nv; mesh.ne = ne; mesh.npe = npe;
@@ -86,6 +102,19 @@ void Solver::set_mesh(int nv, const double* xyz, int ne, int npe, const int* ele
     mesh.labels.alloc(ne, s);
     FSB_CUDA(cudaMemcpyAsync(mesh.labels.get(), labels, sizeof(int) * ne, k, s));
   } else mesh.labels.release();
+  if (ne > 0) {
+    IBuf lohi(2, s);
+    const int init[2] = {INT_MAX, INT_MIN};
+    lohi.from_host(init, 2);
+    const long long m = (long long)ne * npe;
+    index_range_kernel<<<std::min(cdiv(m, 1024), 4 * ctx.num_sms), 256, 0, s>>>(m, mesh.elems, lohi);
+    FSB_CHECK_LAUNCH();
+    std::vector<int> r = lohi.to_vector();
+    if (r[0] < 0 || r[1] >= nv) {
+      mesh.nv = mesh.ne = 0; mesh.xyz.release(); mesh.elems.release(); mesh.labels.release();
+      throw std::invalid_argument("element vertex index out of range [0, " + std::to_string(nv) + "): " + std::to_string(r[0] < 0 ? r[0] : r[1]));
+    }
+  }
   FSB_CUDA(cudaStreamSynchronize(s));
   has_setup = false;
 }
@@ -259,6 +288,12 @@ void Solver::vcycle(int lev, const double* b_src, const int* gather, double* x_d
   LevelData& L = levels[lev];
   const int* done = cg_active_ ? &scal.get()->done : nullptr;
   profiler.cur_level = lev;
+  // sharded solve: this level is computed redundantly on every GPU, but its right-hand side was restricted by the
+  // sharded level above and all-gathered -> wait for every peer's slice first
+  if (lev > 0 && sharded(lev - 1) && !sharded(lev)) {
+    Chan w; w.id = kChanLevel0 + kChanPerLevel * (lev - 1) + kDown; w.mask = (1u << dist.nranks) - 1u;
+    launch_chan_wait(ctx, w, done);
+  }
   if (lev == (int)levels.size() - 1) {  // coarsest: direct solve (amg_level.cu:25-31)
     launch_coarse_solve(ctx, L.n, Ainv, b_src, x_dst, done);
     return;
@@ -269,19 +304,17 @@ void Solver::vcycle(int lev, const double* b_src, const int* gather, double* x_d
   }
   const double w = prm.smootherWeight;
   const double* b_eff = gather ? L.b.get() : b_src;
-  // sharded solve: this GPU owns a contiguous range of level-0 partitions (dist.cu); levels >= 1 are replicated
-  const bool D = dist.connected && dist.nranks > 1 && cg_active_ && lev == 0;
+  // sharded solve: this GPU owns a contiguous range of the level's partitions (dist.cu)
+  const bool D = sharded(lev);
+  const bool Dn = D && sharded(lev + 1);
   RowRange rr, rrc;
-  PeerPtrs px = {}, pr = {}, pbc = {};
+  const DistLevel* DL = D ? &dist.lev[lev] : nullptr;
   if (D) {
     if (prm.postRelaxes != 1) throw std::invalid_argument("the sharded solve supports postRelaxes_ == 1");
-    rr.begin = dist.rbeg[dist.rank]; rr.end = dist.rbeg[dist.rank + 1];
-    rrc.begin = dist.abeg[dist.rank]; rrc.end = dist.abeg[dist.rank + 1];
-    for (int q = 0; q < dist.nranks; q++) {
-      px.p[q] = reinterpret_cast<double*>(dist.peer[q] + dist.off_x);
-      pr.p[q] = reinterpret_cast<double*>(dist.peer[q] + dist.off_r);
-      pbc.p[q] = reinterpret_cast<double*>(dist.peer[q] + dist.off_bc);
-    }
+    rr.begin = DL->rbeg[dist.rank]; rr.end = DL->rbeg[dist.rank + 1];
+    rrc.begin = DL->abeg[dist.rank]; rrc.end = DL->abeg[dist.rank + 1];
+    // the right-hand side of a sharded level > 0 arrives through the parent's "down" channel
+    if (lev > 0) launch_chan_wait(ctx, chan_from(lev - 1, kDown, dist.lev[lev - 1].sendDown), done);
   }
   if (!D && L.RA.nrows > 0) {
     // pre: x = w b/d, nu1 sweeps; then bc = R (b - A x) = R b - (R A) x without forming the residual
@@ -290,26 +323,48 @@ void Solver::vcycle(int lev, const double* b_src, const int* gather, double* x_d
   } else {
     // pre: x = w b/d, nu1 sweeps, r = b - A_in x - d x  (one kernel, matrix slab read once)
     launch_smooth(ctx, L, b_src, gather, gather ? L.b.get() : nullptr, nullptr, w, prm.preInnerIters, L.x, nullptr, nullptr, L.r, done, D);
-    if (D) launch_halo_push(ctx, dist.nSendA, dist.sendA, dist.sendA_ptr, L.x, px, done);           // x across the cut
-    if (L.sAout.ready()) launch_spmv_sell(ctx, L.sAout, L.x, L.r, 3, nullptr, done, "residual_out", rr);
-    else launch_spmv(ctx, L.Aout, L.x, L.r, 3, nullptr, done, "residual_out", rr);   // r -= A_out x   (preAout_kernel)
-    if (D) launch_halo_push(ctx, dist.nSendR, dist.sendR, dist.sendR_ptr, L.r, pr, done);           // r rows the peers restrict
-    launch_spmv(ctx, L.R, L.r, L.bc, 0, nullptr, done, "restrict", rrc);            // bc = R r
+    Chan wx, wr;
+    if (D) {  // x across the cut
+      launch_halo_push(ctx, chan_to(lev, kXPre, DL->sendA), DL->sendA.total, DL->sendA.idx, DL->sendA.ptr, L.x, peers_at(DL->off_x), done);
+      wx = chan_from(lev, kXPre, DL->sendA);
+    }
+    if (L.sAout.ready()) launch_spmv_sell(ctx, L.sAout, L.x, L.r, 3, nullptr, done, "residual_out", rr, wx);
+    else launch_spmv(ctx, L.Aout, L.x, L.r, 3, nullptr, done, "residual_out", rr, wx);   // r -= A_out x   (preAout_kernel)
+    if (D) {  // r rows the peers restrict
+      launch_halo_push(ctx, chan_to(lev, kRes, DL->sendR), DL->sendR.total, DL->sendR.idx, DL->sendR.ptr, L.r, peers_at(DL->off_r), done);
+      wr = chan_from(lev, kRes, DL->sendR);
+    }
+    launch_spmv(ctx, L.R, L.r, L.bc, 0, nullptr, done, "restrict", rrc, wr);            // bc = R r
   }
-  if (D) launch_push_all(ctx, rrc.begin, rrc.end, L.bc, pbc, done);                               // all-gather of bc
+  if (D) {
+    if (Dn) launch_halo_push(ctx, chan_to(lev, kDown, DL->sendDown), DL->sendDown.total, DL->sendDown.idx, DL->sendDown.ptr, L.bc, peers_at(DL->off_bc), done);
+    else {  // the next level is replicated: all-gather of bc
+      Chan ch; ch.id = kChanLevel0 + kChanPerLevel * lev + kDown; ch.mask = (1u << dist.nranks) - 1u;
+      launch_push_all(ctx, ch, rrc.begin, rrc.end, L.bc, peers_at(DL->off_bc), done);
+    }
+  }
   const bool next_is_coarsest = (lev + 1 == (int)levels.size() - 1);
   const int* ip = next_is_coarsest ? nullptr : levels[lev + 1].agg.ipermutation.get();
   vcycle(lev + 1, L.bc, ip, L.xc, ip, nullptr);
   profiler.cur_level = lev;
-  if (L.sP.ready()) launch_spmv_sell(ctx, L.sP, L.xc, L.x, 2, nullptr, done, "prolong_add", rr);
-  else launch_spmv(ctx, L.P, L.xc, L.x, 2, nullptr, done, "prolong_add", rr);      // x += P xc
+  Chan wup;
+  if (Dn) {  // coarse corrections of the next level's rows I own that the peers' prolongator rows reference
+    launch_halo_push(ctx, chan_to(lev, kUp, DL->sendUp), DL->sendUp.total, DL->sendUp.idx, DL->sendUp.ptr, L.xc, peers_at(DL->off_xc), done);
+    wup = chan_from(lev, kUp, DL->sendUp);
+  }
+  if (L.sP.ready()) launch_spmv_sell(ctx, L.sP, L.xc, L.x, 2, nullptr, done, "prolong_add", rr, wup);
+  else launch_spmv(ctx, L.P, L.xc, L.x, 2, nullptr, done, "prolong_add", rr, wup);      // x += P xc
   double* xin = L.x;
   double* xtmp = L.x2;
   for (int rel = 0; rel < prm.postRelaxes; rel++) {
     bool lastpass = (rel == prm.postRelaxes - 1);
-    if (D) launch_halo_push(ctx, dist.nSendA, dist.sendA, dist.sendA_ptr, xin, px, done);
-    if (L.sAout.ready()) launch_spmv_sell(ctx, L.sAout, xin, L.r, 1, b_eff, done, "bprime", rr);
-    else launch_spmv(ctx, L.Aout, xin, L.r, 1, b_eff, done, "bprime", rr);         // b' = b - A_out x (x frozen for this pass)
+    Chan wx;
+    if (D) {
+      launch_halo_push(ctx, chan_to(lev, kXPost, DL->sendA), DL->sendA.total, DL->sendA.idx, DL->sendA.ptr, xin, peers_at(DL->off_x), done);
+      wx = chan_from(lev, kXPost, DL->sendA);
+    }
+    if (L.sAout.ready()) launch_spmv_sell(ctx, L.sAout, xin, L.r, 1, b_eff, done, "bprime", rr, wx);
+    else launch_spmv(ctx, L.Aout, xin, L.r, 1, b_eff, done, "bprime", rr, wx);         // b' = b - A_out x (x frozen for this pass)
     if (lastpass) launch_smooth(ctx, L, L.r, nullptr, nullptr, xin, w, prm.postInnerIters, scatter ? nullptr : x_dst, scatter, scatter ? x_dst : nullptr, nullptr, done, D);
     else { launch_smooth(ctx, L, L.r, nullptr, nullptr, xin, w, prm.postInnerIters, xtmp, nullptr, nullptr, nullptr, done, D); std::swap(xin, xtmp); }
   }
@@ -347,20 +402,21 @@ void Solver::precondition(const double* r, double* z) {
 void Solver::enqueue_pcg_iteration() {
   const int n = levels[0].n;
   PcgScalars* sc = scal.get();
-  const bool D = dist.connected && dist.nranks > 1;
-  const int rb = D ? dist.rbeg[dist.rank] : 0, re = D ? dist.rbeg[dist.rank + 1] : n, nown = re - rb;
+  const bool D = sharded(0);
+  const int rb = D ? dist.lev[0].rbeg[dist.rank] : 0, re = D ? dist.lev[0].rbeg[dist.rank + 1] : n, nown = re - rb;
   RowRange rr;
-  if (D) { rr.begin = rb; rr.end = re; }
-  if (levels[0].sA.ready()) launch_spmv_dot_sell(ctx, levels[0].sA, cg_p, cg_y, partials, sc, rr);
+  Chan wp;
+  if (D) { rr.begin = rb; rr.end = re; wp.id = kChanP; wp.mask = dist.lev[0].sendA.src_mask; }
+  if (levels[0].sA.ready()) launch_spmv_dot_sell(ctx, levels[0].sA, cg_p, cg_y, partials, sc, rr, wp);
   else launch_spmv_dot(ctx, levels[0].A, cg_p, cg_y, partials, sc);          // y = A p, alpha = rz / (p.y)
   launch_cg_update(ctx, nown, cg_x.get() + rb, cg_r.get() + rb, cg_p.get() + rb, cg_y.get() + rb, partials, sc, hist);  // x += alpha p, r -= alpha y, ||r||, test
   vcycle(0, cg_r, nullptr, cg_z, nullptr, nullptr);                          // z = M^-1 r
   launch_dot(ctx, nown, cg_r.get() + rb, cg_z.get() + rb, partials, sc, 2);  // rz_new, beta
   launch_cg_pdir(ctx, nown, cg_p.get() + rb, cg_z.get() + rb, sc, 0);        // p = z + beta p
-  if (D) {
-    PeerPtrs pp = {};
-    for (int q = 0; q < dist.nranks; q++) pp.p[q] = reinterpret_cast<double*>(dist.peer[q] + dist.off_p);
-    launch_halo_push(ctx, dist.nSendA, dist.sendA, dist.sendA_ptr, cg_p, pp, &sc->done);  // p across the cut for the next SpMV
+  if (D) {  // p across the cut for the next SpMV
+    const PushList& pl = dist.lev[0].sendA;
+    Chan ch; ch.id = kChanP; ch.mask = pl.dst_mask;
+    launch_halo_push(ctx, ch, pl.total, pl.idx, pl.ptr, cg_p, peers_at(dist.off_p), &sc->done);
   }
 }
 
@@ -375,38 +431,52 @@ void Solver::pcg(const double* b_user, double* x_user) {
   ensure(cg_b, n); ensure(cg_x, n); ensure(cg_r, n); ensure(cg_z, n); ensure(cg_p, n); ensure(cg_y, n);
   size_t npart = std::max<size_t>((size_t)cdiv((long long)n * 32, 256), (size_t)ctx.num_sms * 8) + 1;
   ensure(partials, npart);
-  ensure(hist, (size_t)prm.maxIters + 2);
+  const int hist_cap = std::max(2, std::min(prm.maxIters, 1 << 20) + 2);  // maxIters_ used as 'infinite' must not size an allocation
+  ensure(hist, (size_t)hist_cap);
   if (scal.size() != 1) scal.alloc(1, s);
   PcgScalars* sc = scal.get();
   cg_active_ = true;
-  GraphKey key = {cg_b.get(), cg_x.get(), cg_r.get(), cg_z.get(), cg_p.get(), cg_y.get(), partials.get(), hist.get(), (void*)sc,
-                  prm.preInnerIters, prm.postInnerIters, prm.postRelaxes, prm.smootherWeight};
+  GraphKey key;
+  memset(&key, 0, sizeof key);  // the struct has padding and is compared bytewise
+  {
+    void* ptrs[9] = {cg_b.get(), cg_x.get(), cg_r.get(), cg_z.get(), cg_p.get(), cg_y.get(), partials.get(), hist.get(), (void*)sc};
+    memcpy(key.p, ptrs, sizeof ptrs);
+    key.pre = prm.preInnerIters; key.post = prm.postInnerIters; key.relaxes = prm.postRelaxes; key.w = prm.smootherWeight;
+  }
   if (iter_graph_ && memcmp(&key, &graph_key_, sizeof(GraphKey)) != 0) destroy_graph();
   graph_key_ = key;
-  launch_cg_init(ctx, sc, prm.tolerance, prm.maxIters);
-  if (permute) {  // the whole iteration lives in the level-0 permuted numbering
-    launch_gather(ctx, n, L0.agg.ipermutation, b_user, cg_b);
-    launch_gather(ctx, n, L0.agg.ipermutation, x_user, cg_x);
+  launch_cg_init(ctx, sc, prm.tolerance, prm.maxIters, hist_cap);
+  const bool D = sharded(0);
+  const int rb = D ? dist.lev[0].rbeg[dist.rank] : 0, re = D ? dist.lev[0].rbeg[dist.rank + 1] : n, nown = re - rb;
+  // the whole iteration lives in the level-0 permuted numbering; a sharded solve touches its own rows only
+  if (permute) {
+    launch_gather(ctx, nown, L0.agg.ipermutation.get() + rb, b_user, cg_b.get() + rb);
+    launch_gather(ctx, nown, L0.agg.ipermutation.get() + rb, x_user, cg_x.get() + rb);
   } else {
-    cg_b.from_device(b_user, n); cg_x.from_device(x_user, n);
+    FSB_CUDA(cudaMemcpyAsync(cg_b.get() + rb, b_user + rb, sizeof(double) * nown, cudaMemcpyDeviceToDevice, s));
+    FSB_CUDA(cudaMemcpyAsync(cg_x.get() + rb, x_user + rb, sizeof(double) * nown, cudaMemcpyDeviceToDevice, s));
   }
-  const bool D = dist.connected && dist.nranks > 1;
-  const int rb = D ? dist.rbeg[dist.rank] : 0, re = D ? dist.rbeg[dist.rank + 1] : n, nown = re - rb;
+  // bnorm first: its all-reduce is also the barrier that separates this solve's first peer stores from the
+  // peers' last reads of the previous solve (final scatter of the all-gathered solution)
+  launch_dot(ctx, nown, cg_b.get() + rb, cg_b.get() + rb, partials, sc, 0);
   RowRange rr;
-  PeerPtrs pp = {}, pcx = {};
+  Chan wx0;
   if (D) {
     rr.begin = rb; rr.end = re;
-    for (int q = 0; q < dist.nranks; q++) {
-      pp.p[q] = reinterpret_cast<double*>(dist.peer[q] + dist.off_p);
-      pcx.p[q] = reinterpret_cast<double*>(dist.peer[q] + dist.off_cgx);
-    }
+    const PushList& pl = dist.lev[0].sendA;
+    Chan ch; ch.id = kChanX0; ch.mask = pl.dst_mask;
+    launch_halo_push(ctx, ch, pl.total, pl.idx, pl.ptr, cg_x, peers_at(dist.off_cgx), nullptr);  // initial guess across the cut
+    wx0.id = kChanX0; wx0.mask = pl.src_mask;
   }
-  launch_dot(ctx, n, cg_b, cg_b, partials, sc, 0);                 // bnorm (full b on every GPU)
-  if (L0.sA.ready()) launch_spmv_sell(ctx, L0.sA, cg_x, cg_r, 1, cg_b, nullptr, "residual", rr);
+  if (L0.sA.ready()) launch_spmv_sell(ctx, L0.sA, cg_x, cg_r, 1, cg_b, nullptr, "residual", rr, wx0);
   else launch_spmv(ctx, L0.A, cg_x, cg_r, 1, cg_b, nullptr, "residual"); // r = b - A x
   vcycle(0, cg_r, nullptr, cg_z, nullptr, nullptr);                // z = M^-1 r
   launch_cg_pdir(ctx, nown, cg_p.get() + rb, cg_z.get() + rb, sc, 1);  // p = z
-  if (D) launch_halo_push(ctx, dist.nSendA, dist.sendA, dist.sendA_ptr, cg_p, pp, nullptr);
+  if (D) {
+    const PushList& pl = dist.lev[0].sendA;
+    Chan ch; ch.id = kChanP; ch.mask = pl.dst_mask;
+    launch_halo_push(ctx, ch, pl.total, pl.idx, pl.ptr, cg_p, peers_at(dist.off_p), nullptr);
+  }
   launch_dot(ctx, nown, cg_r.get() + rb, cg_z.get() + rb, partials, sc, 1);  // rz_old
   FSB_CUDA(cudaStreamSynchronize(s));
 
@@ -456,9 +526,12 @@ void Solver::pcg(const double* b_user, double* x_user) {
   if (h.hist_len) hist.to_host(resid_history.data(), h.hist_len);
   final_relres = h.hist_len ? resid_history.back() : -1;
   if (D) {
-    launch_push_all(ctx, rb, re, cg_x, pcx, nullptr);              // every GPU ends up with the full solution
-    int err = dist.error.read(0);
-    if (err) throw std::runtime_error("sharded solve: a peer did not arrive at an exchange (timeout)");
+    if (h.err || dist.error.read(0)) throw std::runtime_error("sharded solve: a peer did not arrive at an exchange (timeout)");
+    // every GPU ends up with the full solution
+    Chan ch; ch.id = kChanXAll; ch.mask = (1u << dist.nranks) - 1u;
+    launch_push_all(ctx, ch, rb, re, cg_x, peers_at(dist.off_cgx), nullptr);
+    launch_chan_wait(ctx, ch, nullptr);
+    if (dist.error.read(0)) throw std::runtime_error("sharded solve: a peer did not arrive at the final exchange (timeout)");
   }
   if (permute) launch_scatter(ctx, n, L0.agg.ipermutation, cg_x, x_user);
   else FSB_CUDA(cudaMemcpyAsync(x_user, cg_x.get(), sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
@@ -477,9 +550,14 @@ void Solver::solve(const double* b, double* x, bool on_device) {
   DBuf bd, xd;
   const double* bp = b;
   double* xp = x;
+  // sharded PCG with host buffers: only the user-numbering slice that covers this GPU's rows crosses PCIe
+  // (b and the initial guess in, the solution out); x outside [user_lo, user_hi) is left untouched on the host
+  const bool slice = !on_device && dist.connected && dist.nranks > 1 && prm.solverType == 1;
+  const int lo = slice ? dist.user_lo : 0, hi = slice ? dist.user_hi : n;
   if (!on_device) {
     bd.alloc(n, s); xd.alloc(n, s);
-    bd.from_host(b, n); xd.from_host(x, n);
+    FSB_CUDA(cudaMemcpyAsync(bd.get() + lo, b + lo, sizeof(double) * (hi - lo), cudaMemcpyHostToDevice, s));
+    FSB_CUDA(cudaMemcpyAsync(xd.get() + lo, x + lo, sizeof(double) * (hi - lo), cudaMemcpyHostToDevice, s));
     bp = bd; xp = xd;
   }
   tic("solve");
@@ -499,7 +577,10 @@ void Solver::solve(const double* b, double* x, bool on_device) {
   toc("solve");
   launches = g_launch_counter;
   profiler.on = false;
-  if (!on_device) xd.to_host(x, n);
+  if (!on_device) {
+    FSB_CUDA(cudaMemcpyAsync(x + lo, xd.get() + lo, sizeof(double) * (hi - lo), cudaMemcpyDeviceToHost, s));
+    FSB_CUDA(cudaStreamSynchronize(s));
+  }
 }
 
 std::string Solver::profile_report() {

@@ -28,6 +28,7 @@ struct Params {
 struct PcgScalars {
   double rz_old, rz_new, py, alpha, beta, rr, bnorm, tol;
   int done, niter, maxit, hist_len;
+  int hist_cap, err;
   unsigned int ticket[4];
 };
 
@@ -68,6 +69,7 @@ struct LevelData {
   int nlist[kEllClasses] = {0, 0, 0};
   DevBuf<EllDesc> plistOwn[kEllClasses];  // the same lists restricted to this GPU's partitions (sharded solve)
   int nlistOwn[kEllClasses] = {0, 0, 0};
+  int ownP0 = 0, ownPn = 0;               // this GPU's partition range of a sharded level (dist.cu)
   std::vector<EllDesc> ellDescHost;       // one descriptor per partition (host copy, used to build the lists)
   // sorted, warp-sliced ELL slabs (hierarchy.cu: split_partitions)
   bool use_sellg = false;          // sorted slabs with ellG lanes per row, shared-memory resident (smooth_sellg_kernel)
@@ -117,28 +119,51 @@ class Solver {
   void precondition(const double* r, double* z);   // one V-cycle, z = M^-1 r
   long long launches = 0;              // kernels launched by the last solve()
   // ---- stage 4: sharded solve over the GPUs of one box (one process per GPU, replicated setup) ----
-  // dist_prepare(): after setup(); splits level-0 partitions over the ranks, builds the halo send lists and
-  // allocates the IPC arena.  dist_connect(): maps the peers' arenas.  Then solve() (PCG) runs sharded.
+  // dist_prepare(): after setup(); deals the partitions of every level that is large enough out to the ranks
+  // (contiguous, nnz-balanced ranges), builds the push lists of every exchange and allocates the IPC arena.
+  // dist_connect(): maps the peers' arenas.  Then solve() (PCG) runs sharded.
   void dist_prepare(int rank, int nranks);
   void dist_get_handle(void* handle64, long long* bytes);
   void dist_connect(const void* handles /* nranks x 64 bytes */);
   void dist_disconnect();
+  // values of my rows that peers need, grouped by destination peer (same index in the peer's copy of the vector)
+  struct PushList {
+    IBuf idx, ptr;               // entries / nranks+1 segment offsets
+    int total = 0;
+    unsigned dst_mask = 0;       // peers with a non-empty segment
+    unsigned src_mask = 0;       // peers whose lists send to me
+  };
+  // channel ids: 0 p halo, 1 x0 halo (initial residual), 2 final all-gather of x, then 5 per sharded level
+  enum { kChanP = 0, kChanX0 = 1, kChanXAll = 2, kChanLevel0 = 3, kChanPerLevel = 5 };
+  enum { kXPre = 0, kRes = 1, kDown = 2, kUp = 3, kXPost = 4 };
+  struct DistLevel {
+    int pbeg[kMaxRanks + 1] = {};  // partition ranges
+    int rbeg[kMaxRanks + 1] = {};  // row ranges (internal numbering of the level)
+    int abeg[kMaxRanks + 1] = {};  // row ranges of the next level in ITS external numbering = aggregates of the owned partitions
+    PushList sendA;                // operator columns across the cut (x after pre-smoothing / after the coarse correction, p, x0)
+    PushList sendR;                // residual rows the peers' restriction rows reference
+    PushList sendDown;             // restricted residual entries a peer owns on the next (sharded) level
+    PushList sendUp;               // coarse corrections of my next-level rows that a peer's prolongator rows reference
+    size_t off_x = 0, off_r = 0, off_bc = 0, off_xc = 0;
+  };
   struct DistHost {
     int rank = 0, nranks = 1;
     bool connected = false;
-    int pbeg[kMaxRanks + 1] = {};  // level-0 partition ranges
-    int rbeg[kMaxRanks + 1] = {};  // level-0 row ranges
-    int abeg[kMaxRanks + 1] = {};  // level-1 (external) row ranges = aggregates of the owned partitions
+    int nshard = 0;                // levels 0 .. nshard-1 are sharded, the rest is computed redundantly on every GPU
+    std::vector<DistLevel> lev;
+    int user_lo = 0, user_hi = 0;  // user-numbering range that covers this GPU's fine rows (host-buffer solves copy only this slice)
     char* arena = nullptr;
     size_t arena_bytes = 0;
-    size_t off_flags = 0, off_red = 0, off_p = 0, off_x = 0, off_r = 0, off_bc = 0, off_cgx = 0;
+    size_t off_flags = 0, off_red = 0, off_p = 0, off_cgx = 0;
     char* peer[kMaxRanks] = {};
-    IBuf sendA, sendA_ptr, sendR, sendR_ptr;  // boundary rows each peer needs (operator columns / restriction rows)
-    int nSendA = 0, nSendR = 0;
     DevBuf<unsigned long long> epoch;
     IBuf error;
     DevBuf<unsigned int> ticket;
   } dist;
+  bool sharded(int lev) const { return dist.connected && dist.nranks > 1 && cg_active_ && lev < dist.nshard; }
+  Chan chan_to(int lev, int which, const PushList& pl) const { Chan c; c.id = kChanLevel0 + kChanPerLevel * lev + which; c.mask = pl.dst_mask; return c; }
+  Chan chan_from(int lev, int which, const PushList& pl) const { Chan c; c.id = kChanLevel0 + kChanPerLevel * lev + which; c.mask = pl.src_mask; return c; }
+  PeerPtrs peers_at(size_t off) const { PeerPtrs p = {}; for (int q = 0; q < dist.nranks; q++) p.p[q] = reinterpret_cast<double*>(dist.peer[q] + off); return p; }
   std::string profile_report();        // "name level launches total_ms" lines of the last profiled solve
   Profiler profiler;
 

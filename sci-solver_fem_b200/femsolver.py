@@ -59,6 +59,7 @@ def load_library():
         "fsb_profile_report": (ci, [vp, vp, ci]),
         "fsb_dist_prepare": (ci, [vp, ci, ci]), "fsb_dist_handle": (ci, [vp, vp, C.POINTER(cll)]),
         "fsb_dist_connect": (ci, [vp, vp]), "fsb_dist_disconnect": (ci, [vp]), "fsb_dist_ranges": (ci, [vp, vp, vp, vp]),
+        "fsb_dist_level_ranges": (ci, [vp, ci, vp, vp, vp]), "fsb_dist_info": (ci, [vp, vp, vp, vp, vp]),
         "fsb_split_by_weight": (None, [ci, vp, ci, vp]),
         "fsb_tet_mass_integrals": (None, [vp]), "fsb_tri_quadrature": (None, [vp, vp, vp, vp]),
     }
@@ -76,7 +77,7 @@ EXPORTED_SYMBOLS = (
     "fsb_get_matrix_csr fsb_set_matrix_values fsb_set_matrix_csr fsb_setup fsb_num_levels fsb_level_rows fsb_level_nnz "
     "fsb_level_int fsb_level_val fsb_solve fsb_solve_device fsb_solve_fem fsb_resid_history fsb_spmv_fine_device "
     "fsb_precondition_device fsb_time_ms fsb_last_launches fsb_stream fsb_tet_mass_integrals fsb_tri_quadrature "
-    "fsb_profile_report fsb_dist_prepare fsb_dist_handle fsb_dist_connect fsb_dist_disconnect fsb_dist_ranges "
+    "fsb_profile_report fsb_dist_prepare fsb_dist_handle fsb_dist_connect fsb_dist_disconnect fsb_dist_ranges fsb_dist_level_ranges fsb_dist_info "
     "fsb_split_by_weight fsb_apply_matrix_device").split()
 
 
@@ -340,10 +341,20 @@ class FEMSolver:
     def dist_disconnect(self):
         self._check(self._L.fsb_dist_disconnect(self._h))
 
-    def dist_ranges(self):
+    def dist_ranges(self, level: int = 0):
         pb, rb, ab = (np.zeros(9, dtype=np.int32) for _ in range(3))
-        n = self._L.fsb_dist_ranges(self._h, _p(pb), _p(rb), _p(ab))
+        n = self._L.fsb_dist_level_ranges(self._h, int(level), _p(pb), _p(rb), _p(ab))
+        if n < 0:
+            raise ValueError(f"level {level} is not sharded")
         return pb[: n + 1].copy(), rb[: n + 1].copy(), ab[: n + 1].copy()
+
+    def dist_info(self):
+        """{'sharded_levels', 'user_range' (host-copy slice of a sharded solve), 'halo_values' per sharded level}."""
+        ns, lo, hi = C.c_int(0), C.c_int(0), C.c_int(0)
+        hv = np.zeros(4 * 16, dtype=np.int64)
+        self._L.fsb_dist_info(self._h, C.byref(ns), C.byref(lo), C.byref(hi), _p(hv))
+        return {"sharded_levels": ns.value, "user_range": (lo.value, hi.value),
+                "halo_values": [dict(zip(("operator", "residual", "down", "up"), map(int, hv[4 * l: 4 * l + 4]))) for l in range(ns.value)]}
 
     def apply_matrix_device(self, x_ptr: int, y_ptr: int):
         """y = A x on the device (user ordering)."""

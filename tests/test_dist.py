@@ -17,10 +17,12 @@ def free_port():
         return s.getsockname()[1]
 
 
-def launch(nproc, args, timeout):
+def launch(nproc, args, timeout, env=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
            "--master-port", str(free_port()), WORKER] + args
-    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT, env=e)
 
 
 def test_host_plumbing_gloo_world2():
@@ -43,9 +45,27 @@ def test_split_by_weight_properties():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_sharded_solve_matches_single_gpu(world):
+@pytest.mark.parametrize("all_levels", [0, 1])
+def test_sharded_solve_matches_single_gpu(world, all_levels):
+    """all_levels=1 lowers the rows-per-GPU threshold so that every smoothing level of the small test mesh is
+    sharded (exercises the down / up exchanges and the owned-range variants of the coarse smoothers)."""
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
-    r = launch(world, ["gpu", "40"], 900)
+    # (the dense tail is switched off so that level 1 of the small mesh is a smoothing level that can be sharded)
+    env = {"FSB_SHARD_MINROWS": "1", "FSB_DENSE_TAIL": "0", "FSB_EXPECT_SHARDED_LEVELS": "2" if world == 2 else "1"} if all_levels else {}
+    r = launch(world, ["gpu", "40"], 900, env)
+    assert r.returncode == 0 and "GPU_DIST_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-6000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("all_levels", [0, 1])
+def test_sharded_solve_two_ranks_on_one_gpu(all_levels):
+    """The sharded code path on a ONE-GPU box: two processes time-slice cuda:0 and exchange through CUDA IPC
+    exactly as they would over NVLink (slow — every cross-rank wait costs a time slice — but it is the same
+    kernels, channels and push lists), compared with the single-GPU solve."""
+    env = {"FSB_DIST_SAME_GPU": "1"}
+    if all_levels:
+        env.update({"FSB_SHARD_MINROWS": "1", "FSB_DENSE_TAIL": "0", "FSB_EXPECT_SHARDED_LEVELS": "2"})
+    r = launch(2, ["gpu", "32"], 1200, env)
     assert r.returncode == 0 and "GPU_DIST_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-6000:]
