@@ -3,10 +3,12 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--cube N]
 
-Workload: Kuhn tet cube with `--cube` cells per side — on one GPU BASELINE.json configs[2] (default 118:
-1 685 159 DOF, 9 858 192 tets), on 2/4/8 GPUs configs[3] (default 255: 16 777 216 DOF, 99 488 250 tets;
-the line then also carries rank 0's single-GPU solve time of that same mesh) — operator K + M assembled on the
-GPU, AMG hierarchy built on the GPU (aggregation seed 0), right-hand side b = A x*, x* the egg-carton
+Workload: Kuhn tet cube with `--cube` cells per side.  The default at EVERY GPU count is BASELINE.json
+configs[3], the ~100 M-tet cube (N=255: 16 777 216 DOF, 99 488 250 tets) the metric's 1/2/4/8-GPU series is quoted
+on — it fits one B200 (25 GB), so the 1 -> 8 series is one mesh and the driver's scaling efficiency is
+like-for-like; on one GPU the line also carries a `secondary` block for configs[2] (N=118: 1 685 159 DOF,
+9 858 192 tets), and on N > 1 GPUs rank 0's single-GPU solve time of the same mesh.  Operator K + M assembled on
+the GPU, AMG hierarchy built on the GPU (aggregation seed 0), right-hand side b = A x*, x* the egg-carton
 sin(2 pi x) sin(2 pi y) sin(2 pi z), initial guess 0, FEMSolver defaults + solverType_=1 (PCG),
 tolerance_=1e-8, maxIters_=200.  One STEP = one complete PCG solve from the initial residual to
 ||r||/||b|| <= 1e-8.
@@ -19,9 +21,12 @@ tolerance_=1e-8, maxIters_=200.  One STEP = one complete PCG solve from the init
                 on this box's host cores, same workload, one full solve
 
 `--impl reference` times that CPU oracle alone (all host threads) and prints the same line shape.
+  parity    the solution against the committed oracle golden of the same cube (tests/golden/, iterations +-2,
+            residual history and solution samples to 1e-6) and, on N > 1 GPUs, against rank 0's single-GPU
+            solution of the same mesh; a failed check makes the process exit 3 after printing the line
 Under torchrun (N > 1) one cube is solved by all N GPUs together (strong scaling): setup is
-replicated on every GPU, the fine level of the solve is sharded in contiguous partition ranges, halo
-values and dot products travel over NVLink peer memory.
+replicated on every GPU, every level with enough rows per GPU is sharded in contiguous partition ranges,
+halo values and dot products travel over NVLink peer memory.
 """
 from __future__ import annotations
 
@@ -148,6 +153,18 @@ def algorithmic_bytes(kernel, n, nnz, nnzP=0, nc=0, nnz_in=None):
     return 0
 
 
+def setup_bytes(levels, nnzP, nnz_out):
+    """Compulsory traffic of the AMG setup: per smoothing level the operator is read for the
+    permutation and written back (24 nnz), split into slabs (10 B per in-partition entry) and A_out (12 B per entry),
+    P and R are written (24 nnz_P), and the Galerkin product reads A, P, R once and writes A_c (12 (nnz + 2 nnz_P + nnz_c))."""
+    tot = 0
+    for l in range(len(levels) - 1):
+        n, nnz = levels[l]
+        nnzc = levels[l + 1][1]
+        tot += 24 * nnz + 10 * (nnz - nnz_out[l]) + 12 * nnz_out[l] + 24 * nnzP[l] + 12 * (nnz + 2 * nnzP[l] + nnzc) + 16 * n
+    return tot
+
+
 # ----------------------------------------------------------------------------- reference arm / cpu baseline
 def run_oracle(N, steps, warmup, threads=None, single_thread_solve=False):
     from oracle import oracle as orc
@@ -181,15 +198,24 @@ def run_oracle(N, steps, warmup, threads=None, single_thread_solve=False):
                 t_pattern=t_pat, t_assemble=t_asm, t_setup=t_setup, threads=nthreads, t_solve_1thread=t_single)
 
 
+def host_threads():
+    """All the host threads this process may use — torchrun exports OMP_NUM_THREADS=1, which must not leak into the
+    CPU arm."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     N = args.cube
     steps, warmup = args.steps, args.warmup
-    if N > 160:  # bounded sample of the ~100M-tet workload: one complete solve (about 1.5 min of CPU work with the setup)
+    if N > 160:  # bounded sample of the ~100M-tet workload: one complete solve (setup excluded from the metric)
         steps, warmup = 1, 0
-    r = run_oracle(N, steps, warmup)
+    r = run_oracle(N, steps, warmup, threads=host_threads())
     value = r["n"] / r["t_solve"]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
@@ -207,30 +233,57 @@ def reference_arm(args):
     return 0
 
 
-# ----------------------------------------------------------------------------- our arm
-def ours(args):
-    import torch
-    import torch.distributed as dist
-    import sci_solver_fem_b200 as fsb
+# ----------------------------------------------------------------------------- parity
+def golden_for(N):
+    p = os.path.join(ROOT, "tests", "golden", f"oracle_cube{N}_pcg.json")
+    if not os.path.exists(p):
+        return None, None
+    return json.load(open(p)), os.path.relpath(p, ROOT)
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    N = args.cube
+
+def parity_block(N, x, iters, hist, levels, x_single=None, iters_single=None):
+    """Compares a solve of the bench workload with the committed oracle golden of the same cube and, for a sharded
+    solve, with the single-GPU solution of the same mesh.  Bars: iterations +-2, residual history 1e-6 relative
+    at equal iteration index, solution samples / norm 1e-6 (BASELINE.json north_star)."""
+    out = {"ok": True, "checks": []}
+    g, gpath = golden_for(N)
+    if g is not None:
+        ho, h = np.array(g["resid_history"]), np.array(hist)
+        m = min(len(h), len(ho))
+        hist_rel = float(np.max(np.abs(h[:m] / ho[:m] - 1))) if m else None
+        samp = float(np.max(np.abs(x[g["sample_idx"]] - np.array(g["x_samples"])) / np.maximum(np.abs(np.array(g["x_samples"])), 1e-9)))
+        nrm = float(abs(np.linalg.norm(x) - g["x_norm2"]) / g["x_norm2"])
+        ok = abs(iters - g["iterations"]) <= 2 and (hist_rel is None or hist_rel <= 1e-6) and samp <= 1e-6 and nrm <= 1e-6 \
+            and [int(r) for r, _ in levels] == g["levels"]
+        out["oracle_golden"] = {"file": gpath, "iterations": iters, "golden_iterations": g["iterations"], "iters_equal": iters == g["iterations"],
+                                "hist_max_rel": hist_rel, "samples_max_rel": samp, "x_norm_rel": nrm, "levels_equal": [int(r) for r, _ in levels] == g["levels"], "ok": bool(ok)}
+        out["ok"] = out["ok"] and bool(ok)
+        out["checks"].append("oracle_golden")
+    else:
+        out["oracle_golden"] = None
+    if x_single is not None:
+        rel = float(np.linalg.norm(x - x_single) / np.linalg.norm(x_single))
+        ok = rel <= 1e-6 and abs(iters - iters_single) <= 2
+        out["vs_single_gpu"] = {"rel_l2": rel, "iterations": iters, "single_gpu_iterations": iters_single, "iters_equal": iters == iters_single, "ok": bool(ok)}
+        out["ok"] = out["ok"] and bool(ok)
+        out["checks"].append("vs_single_gpu")
+    return out
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_case(N, args, primary, world, rank, local, torch, dist, fsb):
+    """Builds the cube-N problem on this rank's GPU, times the solve (device-resident and host-buffer paths), profiles
+    one solve and returns the pieces of the bench line."""
     verts, tets, xstar = build_problem(N)
     n = len(verts)
-
+    ne = len(tets)
     s = fsb.FEMSolver.from_arrays(verts, tets, None, device=local)
+    del tets
     s.solverType_, s.tolerance_, s.maxIters_, s.seed_ = 1, 1e-8, 200, 0
     t_pattern_cold = s.time_ms("pattern")   # first GPU work of the process: includes pool growth / module load
     t_pattern = t_assemble = t_setup = float("inf")
-    rebuilds = 3 if N <= 160 else 1
-    for _ in range(rebuilds):                # steady-state stage timings: best of 3 rebuilds (allocator pool warm)
+    rebuilds = 3 if N <= 160 else 2
+    for _ in range(rebuilds):                # steady-state stage timings: best of the rebuilds (allocator pool warm)
         s.getMatrixFromMesh()
         t_pattern, t_assemble = min(t_pattern, s.time_ms("pattern")), min(t_assemble, s.time_ms("assemble"))
     for _ in range(rebuilds):
@@ -250,7 +303,9 @@ def ours(args):
     x_dev = torch.zeros(n, dtype=torch.float64, device="cuda")
     stream = torch.cuda.ExternalStream(s._L.fsb_stream(s.handle))
     torch.cuda.synchronize()
-    ms_single = None
+    ms_single = x_single = it_single = None
+    dinfo = None
+    lo, hi = 0, n
     if world > 1:
         # the hierarchy is replicated, so every GPU can also solve the whole system alone: rank 0 times that
         # (same mesh, same build, same run) as the strong-scaling reference of this line
@@ -260,10 +315,12 @@ def ours(args):
                     x_dev.zero_()
                 s.solve_device(x_dev.data_ptr(), b_dev.data_ptr())
             ms_single = s.time_ms("solve")
+            x_single, it_single = x_dev.cpu().numpy(), s.iterations
         dist.barrier()
         s.dist_connect(rank, world, fsb.exchange_handles_torch)
-        pb, rb, ab = s.dist_ranges()
-        log(f"[rank {rank}] owns partitions [{pb[rank]},{pb[rank+1]}) rows [{rb[rank]},{rb[rank+1]})")
+        dinfo = s.dist_info()
+        lo, hi = dinfo["user_range"]
+        log(f"[rank {rank}] sharded levels {dinfo['sharded_levels']}, fine rows {[int(v) for v in s.dist_ranges(0)[1]]}, halo values {dinfo['halo_values']}, host slice [{lo},{hi})")
         dist.barrier()
 
     def barrier():
@@ -277,7 +334,7 @@ def ours(args):
         s.solve_device(x_dev.data_ptr(), b_dev.data_ptr())
 
     def solve_host():
-        x_host.zero_()
+        x_host[lo:hi].zero_()
         s.solve(x_host.numpy(), b_host.numpy())
 
     def timed(fn, steps, warmup):
@@ -301,14 +358,21 @@ def ours(args):
         return ms / steps, wall * 1e3 / steps
 
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and primary:
         sampler.start()
     ms_dev, wall_dev = timed(solve_device, args.steps, args.warmup)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if (rank == 0 and primary) else None
     iters, relres, launches = s.iterations, s.relres, s.last_launches()
+    hist = s.resid_history().copy()
     xg = x_dev.cpu().numpy()
     err = float(np.linalg.norm(xg - xstar) / np.linalg.norm(xstar))
+    parity = parity_block(N, xg, iters, hist, levels, x_single, it_single) if rank == 0 else None
     ms_e2e, wall_e2e = timed(solve_host, max(1, args.steps), min(args.warmup, 3))
+    if rank == 0 and parity is not None:  # the host-buffer path must deliver the same numbers (on its slice)
+        xh = x_host.numpy()
+        rel_h = float(np.linalg.norm(xh[lo:hi] - xg[lo:hi]) / np.linalg.norm(xg[lo:hi]))
+        parity["host_path_rel_l2"] = rel_h
+        parity["ok"] = bool(parity["ok"] and rel_h <= 1e-10)
     # solveFEM-equivalent (hierarchy rebuilt + solve, host buffers), for the record (single GPU only:
     # a rebuild ends the sharded mode)
     t_solvefem = float("nan")
@@ -323,81 +387,181 @@ def ours(args):
     prof = s.profile_report()
     s.profile_ = 0
     tot = sum(ms for (_, ms) in prof.values())
-    top = max(prof.items(), key=lambda kv: kv[1][1])
-    (kname, klev), (kcnt, kms) = top
-    ln, lnnz = levels[klev]
-    nnzP = nc = 0
-    if klev + 1 < len(levels):
-        nc = levels[klev + 1][0]
-        nnzP = int(s._L.fsb_level_int(s.handle, klev, b"P_col", None, 0))
-    kname_alg = "restrict" if (kname == "spmv" and klev < len(levels) - 1) else kname
-    own = 1.0
-    if world > 1 and klev == 0:  # the fine level is sharded: a launch touches this GPU's rows only
-        own = float(rb[rank + 1] - rb[rank]) / n
-    def nnz_in_of(lev):  # entries inside the partitions' diagonal blocks = nnz - nnz(A_out)
-        if lev >= len(levels) - 1:
-            return levels[lev][1]
-        ap = s.level_int(lev, "Aout_ptr")
-        return levels[lev][1] - int(ap[-1])
-    bytes_per_launch = algorithmic_bytes(kname_alg, ln, lnnz, nnzP, nc, nnz_in_of(klev)) * own
+    nlev = len(levels)
+    nnzP = [int(s._L.fsb_level_int(s.handle, l, b"P_col", None, 0)) for l in range(nlev - 1)]
+    nnz_out = [int(s.level_int(l, "Aout_ptr")[-1]) for l in range(nlev - 1)]
+    # fraction of a level's rows this GPU owns (sharded levels of a multi-GPU solve)
+    own = [1.0] * nlev
+    if world > 1:
+        for l in range(dinfo["sharded_levels"]):
+            rb = s.dist_ranges(l)[1]
+            own[l] = float(rb[rank + 1] - rb[rank]) / levels[l][0]
+
+    def kernel_bytes(kname, lev):
+        ln, lnnz = levels[lev]
+        nc = levels[lev + 1][0] if lev + 1 < nlev else 0
+        nP = nnzP[lev] if lev < nlev - 1 else 0
+        nin = lnnz - nnz_out[lev] if lev < nlev - 1 else lnnz   # entries inside the partitions' diagonal blocks
+        k = "restrict" if (kname == "spmv" and lev < nlev - 1) else kname
+        return algorithmic_bytes(k, ln, lnnz, nP, nc, nin) * own[lev]
+
+    # dominant kernel = the largest time share among the kernels with an HBM byte model (exchange kernels and
+    # waits measure peer latency, not HBM traffic)
+    modeled = {k: v for k, v in prof.items() if kernel_bytes(*k) > 0}
+    (kname, klev), (kcnt, kms) = max(modeled.items(), key=lambda kv: kv[1][1])
+    bytes_per_launch = kernel_bytes(kname, klev)
     peak, peak_src = measured_peaks()
     # DRAM traffic of the dominant kernel from the committed ncu --set full capture of the same workload
-    traffic = None
+    traffic, traffic_note = None, None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        if tj.get("cube") == N and world == 1:
-            traffic = tj.get("kernels", {}).get(f"{kname}@level{klev}")
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+        traffic = tj.get(f"cube{N}", {}).get(f"{kname}@level{klev}")
+        if traffic is not None and world > 1:
+            traffic, traffic_note = traffic * own[klev], "single-GPU ncu capture scaled by this GPU's share of the level's rows (ncu cannot attach to a multi-rank run)"
     except Exception:
         pass
+    if traffic is None:
+        traffic_note = "no ncu --set full capture of this kernel on this cube under profiles/"
     achieved = bytes_per_launch / (kms / kcnt * 1e-3) / 1e9
-    kernels = {f"{k}@L{l}": {"launches": c, "ms": round(ms, 4), "share": round(ms / tot, 4)} for (k, l), (c, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1])[:8]}
+    kernels = {f"{k}@L{l}": {"launches": c, "ms": round(ms, 4), "share": round(ms / tot, 4)} for (k, l), (c, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1])[:12]}
     # per-kernel achieved GB/s on the fine level (SpMV + smoother % of HBM peak is part of the metric)
     fine = {}
-    nnz_in0 = nnz_in_of(0)
-    for k in ("spmv_dot", "pre_smooth", "residual", "post_smooth", "cg_update", "dot", "cg_pdir"):
+    for k in ("spmv_dot", "pre_smooth", "residual_out", "restrict", "prolong_add", "bprime", "residual", "post_smooth", "cg_update", "dot", "cg_pdir"):
         if (k, 0) in prof:
             c, ms = prof[(k, 0)]
-            gbs = algorithmic_bytes(k, levels[0][0], levels[0][1], nnz_in=nnz_in0) * (own if world > 1 else 1.0) / (ms / c * 1e-3) / 1e9
+            kb = kernel_bytes(k, 0) if k not in ("residual_out", "bprime") else (12 * nnz_out[0] + 28 * levels[0][0]) * own[0]
+            gbs = kb / (ms / c * 1e-3) / 1e9
             fine[k] = {"us": round(ms / c * 1e3, 2), "GBps": round(gbs, 1), "frac_of_peak": round(gbs / peak, 4)}
+    # whole-iteration roofline: algorithmic bytes of every modeled kernel of one iteration / time of one iteration
+    it_bytes = sum(kernel_bytes(k, l) * c for (k, l), (c, ms) in prof.items()) + sum((12 * nnz_out[l] + 28 * levels[l][0]) * own[l] * prof[(k, l)][0]
+                                                                                      for l in range(nlev - 1) for k in ("residual_out", "bprime") if (k, l) in prof)
+    stages = {
+        "assemble": {"bytes": 84 * ne + 24 * n + 8 * nnz, "ms": t_assemble},
+        "pattern": {"bytes": 16 * ne + 64 * ne + 4 * (n + 1) + 4 * nnz, "ms": t_pattern},
+        "setup": {"bytes": setup_bytes(levels, nnzP, nnz_out), "ms": t_setup},
+        "solve": {"bytes": it_bytes, "ms": ms_dev, "note": "sum of the modeled kernels' algorithmic bytes of one solve on this GPU / device time of the solve"},
+    }
+    for st in stages.values():
+        st["GBps"] = st["bytes"] / (st["ms"] * 1e-3) / 1e9
+        st["frac_of_peak"] = st["GBps"] / peak
+    out = dict(N=N, n=n, ne=ne, nnz=nnz, levels=levels, ms_dev=ms_dev, wall_dev=wall_dev, ms_e2e=ms_e2e, iters=iters, relres=relres, err=err,
+               launches=launches, t_pattern=t_pattern, t_pattern_cold=t_pattern_cold, t_assemble=t_assemble, t_setup=t_setup, t_solvefem=t_solvefem,
+               ms_single=ms_single, dinfo=dinfo, lo=lo, hi=hi, clocks=clocks, parity=parity,
+               roofline={"bound": "hbm", "kernel": f"{kname}@level{klev}", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src, "bytes_per_launch": bytes_per_launch,
+                         "us_per_launch": kms / kcnt * 1e3, "share_of_step": kms / tot, "fine_level_kernels": fine, "top_kernels": kernels},
+               stages=stages)
+    if rank == 0 and world == 1 and args.scipy_check and N <= 160:
+        out["scipy"] = scipy_sanity(s, b_host.numpy(), xg)
+    if world > 1:
+        s.dist_disconnect()
+    del s
+    torch.cuda.empty_cache()
+    return out
+
+
+def scipy_sanity(s, b, x_ours):
+    """Independent ground truth: SciPy CG + Jacobi on the same CSR, to 1e-8."""
+    try:
+        import scipy.sparse as sp
+        import scipy.sparse.linalg as spla
+        ptr, col, val = s.matrix_csr()
+        A = sp.csr_matrix((val, col, ptr))
+        dinv = 1.0 / A.diagonal()
+        M = spla.LinearOperator(A.shape, matvec=lambda v: dinv * v)
+        cnt = [0]
+        t0 = time.perf_counter()
+        x, info = spla.cg(A, b, rtol=1e-8, atol=0.0, maxiter=3000, M=M, callback=lambda xk: cnt.__setitem__(0, cnt[0] + 1))
+        dt = time.perf_counter() - t0
+        return {"solver": "scipy.sparse.linalg.cg + Jacobi, rtol 1e-8", "iterations": cnt[0], "info": int(info), "seconds": dt,
+                "dofs_per_s": A.shape[0] / dt, "relres": float(np.linalg.norm(b - A @ x) / np.linalg.norm(b)),
+                "rel_l2_vs_ours": float(np.linalg.norm(x - x_ours) / np.linalg.norm(x_ours))}
+    except Exception as e:
+        return {"error": str(e)}
+
+
+def ours(args):
+    import torch
+    import torch.distributed as dist
+    import sci_solver_fem_b200 as fsb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    N = args.cube
+    r = run_case(N, args, True, world, rank, local, torch, dist, fsb)
+    secondary = None
+    if world == 1 and N != 118 and not args.no_secondary:
+        q = run_case(118, args, False, world, rank, local, torch, dist, fsb)
+        secondary = {"workload": workload_name(118) + " (BASELINE configs[2])", "value": q["n"] / (q["ms_dev"] * 1e-3), "unit": UNIT, "ms_per_step": q["ms_dev"],
+                     "e2e": {"value": q["n"] / (q["ms_e2e"] * 1e-3), "ms_per_step": q["ms_e2e"]}, "iterations": q["iters"], "relres": q["relres"],
+                     "rel_l2_err_vs_exact": q["err"], "levels": q["levels"], "pattern_ms": q["t_pattern"], "assemble_ms": q["t_assemble"], "setup_ms": q["t_setup"],
+                     "solveFEM_host_ms": q["t_solvefem"] * 1e3, "dofs_per_s_incl_assembly_and_setup": q["n"] / ((q["t_pattern"] + q["t_assemble"] + q["t_setup"] + q["ms_dev"]) * 1e-3),
+                     "roofline": q["roofline"], "roofline_stages": q["stages"], "parity": q["parity"], "scipy_cg_jacobi": q.get("scipy")}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        Nc = N if N <= 160 else 118   # bounded sample: the ~10 M-tet cube of the same family when the workload is the ~100 M-tet one
         try:
-            r = run_oracle(N, 1, 0, single_thread_solve=True)
-            cpu = {"value": r["n"] / r["t_solve"], "unit": UNIT, "cores": r["threads"], "kind": "port",
-                   "single_thread": ({"value": r["n"] / r["t_solve_1thread"], "unit": UNIT, "solve_s": r["t_solve_1thread"]}
-                                     if r.get("t_solve_1thread") else None),
-                   "sample": f"full workload, 1 complete PCG solve ({r['iters']} iterations, {r['t_solve']:.2f} s; setup {r['t_setup']:.1f} s excluded); "
-                             "CPU oracle = restatement of the reference (no host solve and no offline CUDA build upstream)",
-                   "iterations": r["iters"], "setup_s": r["t_setup"], "assemble_s": r["t_assemble"], "pattern_s": r["t_pattern"]}
+            c = run_oracle(Nc, 1, 0, threads=host_threads(), single_thread_solve=True)
+            cpu = {"value": c["n"] / c["t_solve"], "unit": UNIT, "cores": c["threads"], "kind": "port",
+                   "single_thread": ({"value": c["n"] / c["t_solve_1thread"], "unit": UNIT, "solve_s": c["t_solve_1thread"]}
+                                     if c.get("t_solve_1thread") else None),
+                   "sample": (f"Kuhn cube N={Nc} ({c['n']} DOF" + ("" if Nc == N else f", the same family at 1/{round(r['n'] / c['n'])} of the workload's DOFs") +
+                              f"), 1 complete PCG solve ({c['iters']} iterations, {c['t_solve']:.2f} s; setup {c['t_setup']:.1f} s excluded); "
+                              "CPU oracle = restatement of the reference (no host solve and no offline CUDA build upstream)"),
+                   "iterations": c["iters"], "setup_s": c["t_setup"], "assemble_s": c["t_assemble"], "pattern_s": c["t_pattern"]}
         except Exception as e:  # the bench line must still be printed
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"oracle failed: {e}"}
 
+    rc = 0
     if rank == 0:
+        n, ms_dev = r["n"], r["ms_dev"]
+        if world == 1:
+            par = "single GPU"
+        else:
+            d = r["dinfo"]
+            par = (f"{world} GPUs: replicated setup; levels 0..{d['sharded_levels'] - 1} sharded in contiguous partition ranges, the rest replicated after an "
+                   "all-gather; NVLink peer-memory pushes with per-neighbour epoch flags (producers never wait, consumers wait in their prologue), in-kernel all-reduce")
         line = {
             "metric": METRIC, "value": n / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(N), "parallelism": "single GPU" if world == 1 else f"{world} GPUs: replicated setup, fine level sharded in contiguous partition ranges, NVLink peer-memory halo pushes + in-kernel all-reduce",
-                       "l2_policy": "inputs larger than L2 (hierarchy + vectors ~%.0f MB per solve pass)" % ((12 * nnz + 40 * n) / 1e6),
-                       "iterations": iters, "relres": relres, "rel_l2_err_vs_exact": err, "levels": levels,
-                       "pattern_ms": t_pattern, "pattern_cold_ms": t_pattern_cold, "assemble_ms": t_assemble, "setup_ms": t_setup, "solveFEM_host_ms": None if t_solvefem != t_solvefem else t_solvefem * 1e3,
-                       "wall_ms_per_step": wall_dev,
-                       "single_gpu_same_mesh_ms": ms_single,
-                       "speedup_vs_single_gpu_same_mesh": (ms_single / ms_dev) if ms_single else None,
-                       "dofs_per_s_incl_assembly_and_setup": n / ((t_pattern + t_assemble + t_setup + ms_dev) * 1e-3)},
-            "e2e": {"value": n / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 8 * n,
-                    "ms_per_step": ms_e2e, "call": "fsb_solve (host b/x0 in pinned memory -> x)"},
-            "gpu_launches": int(launches) * args.steps,
-            "roofline": {"bound": "hbm", "kernel": f"{kname}@level{klev}", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": bytes_per_launch, "us_per_launch": kms / kcnt * 1e3,
-                         "share_of_step": kms / tot, "fine_level_kernels": fine, "top_kernels": kernels},
+            "config": {"workload": workload_name(N), "parallelism": par,
+                       "l2_policy": "inputs larger than L2 (hierarchy + vectors ~%.0f MB per solve pass)" % ((12 * r["nnz"] + 40 * n) / 1e6),
+                       "iterations": r["iters"], "relres": r["relres"], "rel_l2_err_vs_exact": r["err"], "levels": r["levels"],
+                       "pattern_ms": r["t_pattern"], "pattern_cold_ms": r["t_pattern_cold"], "assemble_ms": r["t_assemble"], "setup_ms": r["t_setup"],
+                       "solveFEM_host_ms": None if r["t_solvefem"] != r["t_solvefem"] else r["t_solvefem"] * 1e3,
+                       "wall_ms_per_step": r["wall_dev"],
+                       "single_gpu_same_mesh_ms": r["ms_single"],
+                       "speedup_vs_single_gpu_same_mesh": (r["ms_single"] / ms_dev) if r["ms_single"] else None,
+                       "sharding": r["dinfo"],
+                       "dofs_per_s_incl_assembly_and_setup": n / ((r["t_pattern"] + r["t_assemble"] + r["t_setup"] + ms_dev) * 1e-3)},
+            "e2e": {"value": n / (r["ms_e2e"] * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 16 * (r["hi"] - r["lo"]), "d2h_bytes_per_step": 8 * (r["hi"] - r["lo"]),
+                    "ms_per_step": r["ms_e2e"], "call": "fsb_solve (host b/x0 in pinned memory -> x)" + ("" if world == 1 else "; every rank moves the user-numbering slice that covers its rows")},
+            "gpu_launches": int(r["launches"]) * args.steps,
+            "roofline": r["roofline"],
+            "roofline_stages": r["stages"],
+            "parity": r["parity"],
+            "secondary": secondary,
             "cpu_baseline": cpu,
-            "clocks": clocks,
+            "clocks": r["clocks"],
         }
         emit(line)
+        if r["parity"] is not None and not r["parity"]["ok"]:
+            log("PARITY FAILED:", json.dumps(r["parity"]))
+            rc = 3
+        if secondary and secondary["parity"] is not None and not secondary["parity"]["ok"]:
+            log("PARITY FAILED (secondary):", json.dumps(secondary["parity"]))
+            rc = 3
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
-    return 0
+    return rc
 
 
 def main():
@@ -406,12 +570,12 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cube", type=int, default=None,
-                    help="cells per side; default 118 (BASELINE configs[2], ~10M tets) on one GPU, 255 (configs[3], ~100M tets) on 2/4/8 GPUs")
+    ap.add_argument("--cube", type=int, default=255,
+                    help="cells per side; default 255 (BASELINE configs[3], ~100M tets: the mesh of the 1/2/4/8-GPU series); 118 = configs[2]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the configs[2] (N=118) block of a single-GPU run")
+    ap.add_argument("--no-scipy", dest="scipy_check", action="store_false", help="skip the SciPy CG sanity solve of the secondary block")
     args = ap.parse_args()
-    if args.cube is None:
-        args.cube = 118 if args.gpus <= 1 and int(os.environ.get("WORLD_SIZE", "1")) <= 1 else 255
     if args.impl == "reference":
         return reference_arm(args)
     return ours(args)

@@ -166,12 +166,28 @@ inline cudaLaunchConfig_t pdl_config(dim3 grid, dim3 block, size_t smem, cudaStr
 
 // pushes owned boundary values into the peers' copies of a vector: entry k of `list` goes to the peer
 // whose segment of list_ptr contains k (same index in the peer's copy).  The last CTA publishes the
-// channel epoch to the destination peers; nobody waits here — the consumer kernel does (chan_wait).
-__global__ void __launch_bounds__(256) halo_push_kernel(DistDev d, Chan ch, int total, const int* __restrict__ list, const int* __restrict__ list_ptr,
-                                                        const double* __restrict__ src, PeerPtrs dst, unsigned int* ticket,
-                                                        const int* __restrict__ done) {
-  pdl_wait();
+// channel epoch to the destination peers (sig.mask) and then waits for the peers this GPU receives from
+// (wt.mask) — a neighbour-only handshake instead of an all-ranks barrier; when the kernel has finished, the
+// halo values of this exchange are in place for the consumer kernel that follows in the stream.
+// One system-scope fence per CTA (thread 0, after the CTA barrier: fences are cumulative) — a fence per
+// thread costs a round trip to the system coherence point each.
+__device__ __forceinline__ void push_epilogue(const DistDev& d, Chan sig, Chan wt, unsigned int* ticket) {
   __shared__ int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    s_last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    chan_signal(d, sig);
+    chan_wait(d, wt);
+  }
+}
+__global__ void __launch_bounds__(256) halo_push_kernel(DistDev d, Chan sig, Chan wt, int total, const int* __restrict__ list,
+                                                        const int* __restrict__ list_ptr, const double* __restrict__ src, PeerPtrs dst,
+                                                        unsigned int* ticket, const int* __restrict__ done) {
+  pdl_wait();
   if (done && *done) return;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
     int q = 0;
@@ -179,28 +195,19 @@ __global__ void __launch_bounds__(256) halo_push_kernel(DistDev d, Chan ch, int 
     const int j = list[k];
     dst.p[q][j] = src[j];
   }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1);
-  __syncthreads();
-  if (s_last) chan_signal(d, ch);
+  push_epilogue(d, sig, wt, ticket);
 }
 
 // all-gather by peer stores: the owned slice [begin, end) of a vector is written into every peer's copy
-__global__ void __launch_bounds__(256) push_all_kernel(DistDev d, Chan ch, int begin, int end, const double* __restrict__ src, PeerPtrs dst,
+__global__ void __launch_bounds__(256) push_all_kernel(DistDev d, Chan sig, Chan wt, int begin, int end, const double* __restrict__ src, PeerPtrs dst,
                                                        unsigned int* ticket, const int* __restrict__ done) {
   pdl_wait();
-  __shared__ int s_last;
   if (done && *done) return;
   for (int j = begin + blockIdx.x * blockDim.x + threadIdx.x; j < end; j += gridDim.x * blockDim.x) {
     const double v = src[j];
     for (int q = 0; q < d.nranks; q++) if (q != d.rank) dst.p[q][j] = v;
   }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1);
-  __syncthreads();
-  if (s_last) chan_signal(d, ch);
+  push_epilogue(d, sig, wt, ticket);
 }
 
 // stand-alone consumer wait for kernels that have no wait hook of their own (smoothers, dense GEMV, gathers)
@@ -1166,18 +1173,18 @@ void launch_spmv_dot_sell(const Ctx& c, const Sell& A, const double* x, double* 
   sell_dispatch<0, true>(c, A, x, y, nullptr, partials, sc, &sc->done, "spmv_dot", rr, wch);
 }
 
-void launch_halo_push(const Ctx& c, Chan ch, int total, const int* list, const int* list_ptr, const double* src, const PeerPtrs& dst, const int* done) {
+void launch_halo_push(const Ctx& c, Chan sig, Chan wt, int total, const int* list, const int* list_ptr, const double* src, const PeerPtrs& dst, const int* done) {
   g_launch_counter++;
   ProfScope ps(c, "halo_push");
-  int blocks = std::max(1, std::min(cdiv(total, 256), c.num_sms * 2));
-  FSB_LAUNCH((halo_push_kernel), blocks, 256, 0, c.stream, c.dist, ch, total, list, list_ptr, src, dst, c.dist_ticket, done);
+  int blocks = std::max(1, std::min(cdiv(total, 512), c.num_sms));
+  FSB_LAUNCH((halo_push_kernel), blocks, 256, 0, c.stream, c.dist, sig, wt, total, list, list_ptr, src, dst, c.dist_ticket, done);
   FSB_CHECK_LAUNCH();
 }
-void launch_push_all(const Ctx& c, Chan ch, int begin, int end, const double* src, const PeerPtrs& dst, const int* done) {
+void launch_push_all(const Ctx& c, Chan sig, Chan wt, int begin, int end, const double* src, const PeerPtrs& dst, const int* done) {
   g_launch_counter++;
   ProfScope ps(c, "push_all");
-  int blocks = std::max(1, std::min(cdiv(end - begin, 256), c.num_sms * 4));
-  FSB_LAUNCH((push_all_kernel), blocks, 256, 0, c.stream, c.dist, ch, begin, end, src, dst, c.dist_ticket, done);
+  int blocks = std::max(1, std::min(cdiv(end - begin, 512), c.num_sms * 2));
+  FSB_LAUNCH((push_all_kernel), blocks, 256, 0, c.stream, c.dist, sig, wt, begin, end, src, dst, c.dist_ticket, done);
   FSB_CHECK_LAUNCH();
 }
 void launch_chan_wait(const Ctx& c, Chan ch, const int* done) {

@@ -12,11 +12,11 @@ void launch_spmv_sell(const Ctx& c, const Sell& A, const double* x, double* y, i
                       RowRange rr = RowRange(), Chan wch = Chan());
 void launch_spmv_dot_sell(const Ctx& c, const Sell& A, const double* x, double* y, double* partials, PcgScalars* sc, RowRange rr = RowRange(),
                           Chan wch = Chan());
-// multi-GPU exchanges over NVLink peer memory: the producer stores into the peers' copies and publishes the
-// channel epoch (never waits); the consumer kernel waits for the peers it receives from (wch), or a
-// stand-alone wait kernel does when the consumer has no hook
-void launch_halo_push(const Ctx& c, Chan ch, int total, const int* list, const int* list_ptr, const double* src, const PeerPtrs& dst, const int* done);
-void launch_push_all(const Ctx& c, Chan ch, int begin, int end, const double* src, const PeerPtrs& dst, const int* done);
+// multi-GPU exchanges over NVLink peer memory: the kernel stores into the peers' copies, its last CTA publishes
+// the channel epoch to the peers it wrote to (sig) and waits for the peers this GPU receives from (wt; id < 0:
+// no wait here — the consumer kernel waits itself through its `wch` hook, or launch_chan_wait does)
+void launch_halo_push(const Ctx& c, Chan sig, Chan wt, int total, const int* list, const int* list_ptr, const double* src, const PeerPtrs& dst, const int* done);
+void launch_push_all(const Ctx& c, Chan sig, Chan wt, int begin, int end, const double* src, const PeerPtrs& dst, const int* done);
 void launch_chan_wait(const Ctx& c, Chan ch, const int* done);
 // y = A x and the dot product x.y folded into the same pass; the last CTA finishes
 // py and alpha = rz_old / py in device memory.

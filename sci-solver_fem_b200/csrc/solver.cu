@@ -284,16 +284,20 @@ void Solver::setup() {
 // One V-cycle on level `lev`.  b_src is read through `gather` (external -> internal numbering,
 // null when b_src is already internal); the result goes to x_dst in internal numbering
 // (scatter == null) or is scattered to the external numbering through `scatter`.
+// one exchange of a sharded solve: my list entries of `v` into the peers' copies (arena offset `off`), signal, wait
+void Solver::exchange_chan(int chan, const PushList& pl, const double* v, size_t off, const int* done) {
+  Chan sig, wt;
+  sig.id = wt.id = chan; sig.mask = pl.dst_mask; wt.mask = pl.src_mask;
+  launch_halo_push(ctx, sig, wt, pl.total, pl.idx, pl.ptr, v, peers_at(off), done);
+}
+void Solver::exchange(int lev, int which, const PushList& pl, const double* v, size_t off, const int* done) {
+  exchange_chan(kChanLevel0 + kChanPerLevel * lev + which, pl, v, off, done);
+}
+
 void Solver::vcycle(int lev, const double* b_src, const int* gather, double* x_dst, const int* scatter, double* /*unused*/) {
   LevelData& L = levels[lev];
   const int* done = cg_active_ ? &scal.get()->done : nullptr;
   profiler.cur_level = lev;
-  // sharded solve: this level is computed redundantly on every GPU, but its right-hand side was restricted by the
-  // sharded level above and all-gathered -> wait for every peer's slice first
-  if (lev > 0 && sharded(lev - 1) && !sharded(lev)) {
-    Chan w; w.id = kChanLevel0 + kChanPerLevel * (lev - 1) + kDown; w.mask = (1u << dist.nranks) - 1u;
-    launch_chan_wait(ctx, w, done);
-  }
   if (lev == (int)levels.size() - 1) {  // coarsest: direct solve (amg_level.cu:25-31)
     launch_coarse_solve(ctx, L.n, Ainv, b_src, x_dst, done);
     return;
@@ -313,8 +317,6 @@ void Solver::vcycle(int lev, const double* b_src, const int* gather, double* x_d
     if (prm.postRelaxes != 1) throw std::invalid_argument("the sharded solve supports postRelaxes_ == 1");
     rr.begin = DL->rbeg[dist.rank]; rr.end = DL->rbeg[dist.rank + 1];
     rrc.begin = DL->abeg[dist.rank]; rrc.end = DL->abeg[dist.rank + 1];
-    // the right-hand side of a sharded level > 0 arrives through the parent's "down" channel
-    if (lev > 0) launch_chan_wait(ctx, chan_from(lev - 1, kDown, dist.lev[lev - 1].sendDown), done);
   }
   if (!D && L.RA.nrows > 0) {
     // pre: x = w b/d, nu1 sweeps; then bc = R (b - A x) = R b - (R A) x without forming the residual
@@ -323,48 +325,36 @@ void Solver::vcycle(int lev, const double* b_src, const int* gather, double* x_d
   } else {
     // pre: x = w b/d, nu1 sweeps, r = b - A_in x - d x  (one kernel, matrix slab read once)
     launch_smooth(ctx, L, b_src, gather, gather ? L.b.get() : nullptr, nullptr, w, prm.preInnerIters, L.x, nullptr, nullptr, L.r, done, D);
-    Chan wx, wr;
-    if (D) {  // x across the cut
-      launch_halo_push(ctx, chan_to(lev, kXPre, DL->sendA), DL->sendA.total, DL->sendA.idx, DL->sendA.ptr, L.x, peers_at(DL->off_x), done);
-      wx = chan_from(lev, kXPre, DL->sendA);
-    }
-    if (L.sAout.ready()) launch_spmv_sell(ctx, L.sAout, L.x, L.r, 3, nullptr, done, "residual_out", rr, wx);
-    else launch_spmv(ctx, L.Aout, L.x, L.r, 3, nullptr, done, "residual_out", rr, wx);   // r -= A_out x   (preAout_kernel)
-    if (D) {  // r rows the peers restrict
-      launch_halo_push(ctx, chan_to(lev, kRes, DL->sendR), DL->sendR.total, DL->sendR.idx, DL->sendR.ptr, L.r, peers_at(DL->off_r), done);
-      wr = chan_from(lev, kRes, DL->sendR);
-    }
-    launch_spmv(ctx, L.R, L.r, L.bc, 0, nullptr, done, "restrict", rrc, wr);            // bc = R r
+    // x across the cut (every exchange: push + signal to the peers written to + wait for the peers received from)
+    if (D) exchange(lev, kXPre, DL->sendA, L.x, DL->off_x, done);
+    if (L.sAout.ready()) launch_spmv_sell(ctx, L.sAout, L.x, L.r, 3, nullptr, done, "residual_out", rr);
+    else launch_spmv(ctx, L.Aout, L.x, L.r, 3, nullptr, done, "residual_out", rr);   // r -= A_out x   (preAout_kernel)
+    if (D) exchange(lev, kRes, DL->sendR, L.r, DL->off_r, done);                     // r rows the peers restrict
+    launch_spmv(ctx, L.R, L.r, L.bc, 0, nullptr, done, "restrict", rrc);            // bc = R r
   }
   if (D) {
-    if (Dn) launch_halo_push(ctx, chan_to(lev, kDown, DL->sendDown), DL->sendDown.total, DL->sendDown.idx, DL->sendDown.ptr, L.bc, peers_at(DL->off_bc), done);
-    else {  // the next level is replicated: all-gather of bc
+    // restricted residual: to the owners of the next level's rows, or — next level replicated — all-gathered
+    if (Dn) exchange(lev, kDown, DL->sendDown, L.bc, DL->off_bc, done);
+    else {
       Chan ch; ch.id = kChanLevel0 + kChanPerLevel * lev + kDown; ch.mask = (1u << dist.nranks) - 1u;
-      launch_push_all(ctx, ch, rrc.begin, rrc.end, L.bc, peers_at(DL->off_bc), done);
+      launch_push_all(ctx, ch, ch, rrc.begin, rrc.end, L.bc, peers_at(DL->off_bc), done);
     }
   }
   const bool next_is_coarsest = (lev + 1 == (int)levels.size() - 1);
   const int* ip = next_is_coarsest ? nullptr : levels[lev + 1].agg.ipermutation.get();
   vcycle(lev + 1, L.bc, ip, L.xc, ip, nullptr);
   profiler.cur_level = lev;
-  Chan wup;
-  if (Dn) {  // coarse corrections of the next level's rows I own that the peers' prolongator rows reference
-    launch_halo_push(ctx, chan_to(lev, kUp, DL->sendUp), DL->sendUp.total, DL->sendUp.idx, DL->sendUp.ptr, L.xc, peers_at(DL->off_xc), done);
-    wup = chan_from(lev, kUp, DL->sendUp);
-  }
-  if (L.sP.ready()) launch_spmv_sell(ctx, L.sP, L.xc, L.x, 2, nullptr, done, "prolong_add", rr, wup);
-  else launch_spmv(ctx, L.P, L.xc, L.x, 2, nullptr, done, "prolong_add", rr, wup);      // x += P xc
+  // coarse corrections of the next level's rows I own that the peers' prolongator rows reference
+  if (Dn) exchange(lev, kUp, DL->sendUp, L.xc, DL->off_xc, done);
+  if (L.sP.ready()) launch_spmv_sell(ctx, L.sP, L.xc, L.x, 2, nullptr, done, "prolong_add", rr);
+  else launch_spmv(ctx, L.P, L.xc, L.x, 2, nullptr, done, "prolong_add", rr);      // x += P xc
   double* xin = L.x;
   double* xtmp = L.x2;
   for (int rel = 0; rel < prm.postRelaxes; rel++) {
     bool lastpass = (rel == prm.postRelaxes - 1);
-    Chan wx;
-    if (D) {
-      launch_halo_push(ctx, chan_to(lev, kXPost, DL->sendA), DL->sendA.total, DL->sendA.idx, DL->sendA.ptr, xin, peers_at(DL->off_x), done);
-      wx = chan_from(lev, kXPost, DL->sendA);
-    }
-    if (L.sAout.ready()) launch_spmv_sell(ctx, L.sAout, xin, L.r, 1, b_eff, done, "bprime", rr, wx);
-    else launch_spmv(ctx, L.Aout, xin, L.r, 1, b_eff, done, "bprime", rr, wx);         // b' = b - A_out x (x frozen for this pass)
+    if (D) exchange(lev, kXPost, DL->sendA, xin, DL->off_x, done);
+    if (L.sAout.ready()) launch_spmv_sell(ctx, L.sAout, xin, L.r, 1, b_eff, done, "bprime", rr);
+    else launch_spmv(ctx, L.Aout, xin, L.r, 1, b_eff, done, "bprime", rr);         // b' = b - A_out x (x frozen for this pass)
     if (lastpass) launch_smooth(ctx, L, L.r, nullptr, nullptr, xin, w, prm.postInnerIters, scatter ? nullptr : x_dst, scatter, scatter ? x_dst : nullptr, nullptr, done, D);
     else { launch_smooth(ctx, L, L.r, nullptr, nullptr, xin, w, prm.postInnerIters, xtmp, nullptr, nullptr, nullptr, done, D); std::swap(xin, xtmp); }
   }
@@ -405,19 +395,14 @@ void Solver::enqueue_pcg_iteration() {
   const bool D = sharded(0);
   const int rb = D ? dist.lev[0].rbeg[dist.rank] : 0, re = D ? dist.lev[0].rbeg[dist.rank + 1] : n, nown = re - rb;
   RowRange rr;
-  Chan wp;
-  if (D) { rr.begin = rb; rr.end = re; wp.id = kChanP; wp.mask = dist.lev[0].sendA.src_mask; }
-  if (levels[0].sA.ready()) launch_spmv_dot_sell(ctx, levels[0].sA, cg_p, cg_y, partials, sc, rr, wp);
+  if (D) { rr.begin = rb; rr.end = re; }
+  if (levels[0].sA.ready()) launch_spmv_dot_sell(ctx, levels[0].sA, cg_p, cg_y, partials, sc, rr);
   else launch_spmv_dot(ctx, levels[0].A, cg_p, cg_y, partials, sc);          // y = A p, alpha = rz / (p.y)
   launch_cg_update(ctx, nown, cg_x.get() + rb, cg_r.get() + rb, cg_p.get() + rb, cg_y.get() + rb, partials, sc, hist);  // x += alpha p, r -= alpha y, ||r||, test
   vcycle(0, cg_r, nullptr, cg_z, nullptr, nullptr);                          // z = M^-1 r
   launch_dot(ctx, nown, cg_r.get() + rb, cg_z.get() + rb, partials, sc, 2);  // rz_new, beta
   launch_cg_pdir(ctx, nown, cg_p.get() + rb, cg_z.get() + rb, sc, 0);        // p = z + beta p
-  if (D) {  // p across the cut for the next SpMV
-    const PushList& pl = dist.lev[0].sendA;
-    Chan ch; ch.id = kChanP; ch.mask = pl.dst_mask;
-    launch_halo_push(ctx, ch, pl.total, pl.idx, pl.ptr, cg_p, peers_at(dist.off_p), &sc->done);
-  }
+  if (D) exchange_chan(kChanP, dist.lev[0].sendA, cg_p, dist.off_p, &sc->done);  // p across the cut for the next SpMV
 }
 
 void Solver::pcg(const double* b_user, double* x_user) {
@@ -460,23 +445,15 @@ void Solver::pcg(const double* b_user, double* x_user) {
   // peers' last reads of the previous solve (final scatter of the all-gathered solution)
   launch_dot(ctx, nown, cg_b.get() + rb, cg_b.get() + rb, partials, sc, 0);
   RowRange rr;
-  Chan wx0;
   if (D) {
     rr.begin = rb; rr.end = re;
-    const PushList& pl = dist.lev[0].sendA;
-    Chan ch; ch.id = kChanX0; ch.mask = pl.dst_mask;
-    launch_halo_push(ctx, ch, pl.total, pl.idx, pl.ptr, cg_x, peers_at(dist.off_cgx), nullptr);  // initial guess across the cut
-    wx0.id = kChanX0; wx0.mask = pl.src_mask;
+    exchange_chan(kChanX0, dist.lev[0].sendA, cg_x, dist.off_cgx, nullptr);  // initial guess across the cut
   }
-  if (L0.sA.ready()) launch_spmv_sell(ctx, L0.sA, cg_x, cg_r, 1, cg_b, nullptr, "residual", rr, wx0);
+  if (L0.sA.ready()) launch_spmv_sell(ctx, L0.sA, cg_x, cg_r, 1, cg_b, nullptr, "residual", rr);
   else launch_spmv(ctx, L0.A, cg_x, cg_r, 1, cg_b, nullptr, "residual"); // r = b - A x
   vcycle(0, cg_r, nullptr, cg_z, nullptr, nullptr);                // z = M^-1 r
   launch_cg_pdir(ctx, nown, cg_p.get() + rb, cg_z.get() + rb, sc, 1);  // p = z
-  if (D) {
-    const PushList& pl = dist.lev[0].sendA;
-    Chan ch; ch.id = kChanP; ch.mask = pl.dst_mask;
-    launch_halo_push(ctx, ch, pl.total, pl.idx, pl.ptr, cg_p, peers_at(dist.off_p), nullptr);
-  }
+  if (D) exchange_chan(kChanP, dist.lev[0].sendA, cg_p, dist.off_p, nullptr);
   launch_dot(ctx, nown, cg_r.get() + rb, cg_z.get() + rb, partials, sc, 1);  // rz_old
   FSB_CUDA(cudaStreamSynchronize(s));
 
@@ -529,8 +506,7 @@ void Solver::pcg(const double* b_user, double* x_user) {
     if (h.err || dist.error.read(0)) throw std::runtime_error("sharded solve: a peer did not arrive at an exchange (timeout)");
     // every GPU ends up with the full solution
     Chan ch; ch.id = kChanXAll; ch.mask = (1u << dist.nranks) - 1u;
-    launch_push_all(ctx, ch, rb, re, cg_x, peers_at(dist.off_cgx), nullptr);
-    launch_chan_wait(ctx, ch, nullptr);
+    launch_push_all(ctx, ch, ch, rb, re, cg_x, peers_at(dist.off_cgx), nullptr);
     if (dist.error.read(0)) throw std::runtime_error("sharded solve: a peer did not arrive at the final exchange (timeout)");
   }
   if (permute) launch_scatter(ctx, n, L0.agg.ipermutation, cg_x, x_user);

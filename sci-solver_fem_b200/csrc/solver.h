@@ -161,8 +161,8 @@ class Solver {
     DevBuf<unsigned int> ticket;
   } dist;
   bool sharded(int lev) const { return dist.connected && dist.nranks > 1 && cg_active_ && lev < dist.nshard; }
-  Chan chan_to(int lev, int which, const PushList& pl) const { Chan c; c.id = kChanLevel0 + kChanPerLevel * lev + which; c.mask = pl.dst_mask; return c; }
-  Chan chan_from(int lev, int which, const PushList& pl) const { Chan c; c.id = kChanLevel0 + kChanPerLevel * lev + which; c.mask = pl.src_mask; return c; }
+  void exchange_chan(int chan, const PushList& pl, const double* v, size_t off, const int* done);
+  void exchange(int lev, int which, const PushList& pl, const double* v, size_t off, const int* done);
   PeerPtrs peers_at(size_t off) const { PeerPtrs p = {}; for (int q = 0; q < dist.nranks; q++) p.p[q] = reinterpret_cast<double*>(dist.peer[q] + off); return p; }
   std::string profile_report();        // "name level launches total_ms" lines of the last profiled solve
   Profiler profiler;

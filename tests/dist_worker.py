@@ -93,7 +93,7 @@ def gpu_mode(N):
         errf = np.linalg.norm(xf - x1) / np.linalg.norm(x1)
         assert errf < 1e-8, errf
     # all ranks hold the same full solution, bit for bit
-    tt = torch.from_numpy(xf)
+    tt = torch.from_numpy(xf) if same_gpu else torch.from_numpy(xf).cuda()   # gloo moves host tensors, nccl device tensors
     ref = tt.clone()
     dist.broadcast(ref, 0)
     assert torch.equal(tt, ref), "ranks disagree on the solution"

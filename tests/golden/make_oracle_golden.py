@@ -1,11 +1,17 @@
-"""Regenerates tests/golden/oracle_cube118_pcg.json: the CPU oracle's PCG solve of BASELINE configs[2]
-(Kuhn cube N=118, b = A * egg-carton, defaults + solverType_=1, tolerance_=1e-8, seed_=0) — iteration count,
-residual history, solution norm and samples.  About 30 s on 8 cores; the `-m gpu` test
-tests/test_gpu_parity.py::test_config3_matches_the_oracle_golden compares the CUDA path against it without
-having to run the oracle at that size on the GPU box.
+"""Regenerates the oracle goldens of the BASELINE-size configurations: the CPU oracle's complete PCG solve
+(defaults + solverType_=1, seed_=0) of a Kuhn cube — iteration count, residual history, solution norm and
+samples, level sizes.  The `-m gpu` tests (tests/test_gpu_parity.py::test_baseline_size_matches_the_oracle_golden)
+and bench.py's `parity` block compare the CUDA path against them without running the oracle at that size on
+the GPU box.
 
-    python tests/golden/make_oracle_golden.py
+    python tests/golden/make_oracle_golden.py --cube 118                       # configs[2]  (~30 s on 8 cores)
+    python tests/golden/make_oracle_golden.py --cube 255                       # configs[3]  (~6 min, ~30 GB)
+    python tests/golden/make_oracle_golden.py --cube 149 --variant contrast    # configs[4](i)  label checkerboard c in 1..6
+    python tests/golden/make_oracle_golden.py --cube 149 --variant anisotropic # configs[4](ii) z squeezed by 1/64, 60 iterations
+
+Files: tests/golden/oracle_cube<N>[_<variant>]_pcg.json
 """
+import argparse
 import json
 import os
 import sys
@@ -14,20 +20,57 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-import bench  # noqa: E402
-from oracle import oracle as orc  # noqa: E402
 
-N = 118
-verts, tets, xstar = bench.build_problem(N)
-o = orc.Oracle(64, solverType=1, tolerance=1e-8, maxIters=200, seed=0)
-o.pattern(len(verts), tets); o.assemble(verts); o.setup()
-b = o.spmv(xstar)
-x, it = o.solve(b)
-h = np.array(o.resid_history())
-idx = [0, 1000, 123456, 842579, 1685158]
-g = {"cube": N, "iterations": int(it), "relres": float(h[-1]), "resid_history": [float(v) for v in h],
-     "x_norm2": float(np.linalg.norm(x)), "b_norm2": float(np.linalg.norm(b)), "sample_idx": idx,
-     "x_samples": [float(x[i]) for i in idx], "err_vs_exact": float(np.linalg.norm(x - xstar) / np.linalg.norm(xstar)),
-     "levels": [int(o.level_rows(l)) for l in range(4)]}
-json.dump(g, open(os.path.join(ROOT, "tests", "golden", "oracle_cube118_pcg.json"), "w"), indent=1)
-print(g["iterations"], g["relres"], g["x_norm2"], g["err_vs_exact"], g["levels"])
+
+def problem(N, variant):
+    """(verts, tets, labels, xstar, oracle/solver parameters) of a golden case — shared with the GPU tests."""
+    import sci_solver_fem_b200 as fsb
+    prm = dict(solverType=1, tolerance=1e-8, maxIters=200, seed=0)
+    labels = None
+    if variant == "anisotropic":
+        verts, tets = fsb.meshio.kuhn_cube(N, scale=(1.0, 1.0, 1.0 / 64.0))
+        # the 1/64 squeeze defeats the point smoother (that is what the configuration is for): compare at equal
+        # iteration index (SURVEY 8c parity policy 4) instead of waiting for 1e-8
+        prm.update(maxIters=60, tolerance=1e-30)
+        xs = verts * np.array([1.0, 1.0, 64.0])
+    else:
+        verts, tets = fsb.meshio.kuhn_cube(N)
+        xs = verts
+        if variant == "contrast":
+            labels = fsb.meshio.kuhn_cell_labels(N, block=8)
+            prm.update(maxIters=400)
+    xstar = np.sin(2 * np.pi * xs[:, 0]) * np.sin(2 * np.pi * xs[:, 1]) * np.sin(2 * np.pi * xs[:, 2])
+    return verts, tets, labels, xstar, prm
+
+
+def golden_path(N, variant):
+    tag = f"oracle_cube{N}" + (f"_{variant}" if variant else "") + "_pcg.json"
+    return os.path.join(ROOT, "tests", "golden", tag)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cube", type=int, default=118)
+    ap.add_argument("--variant", default="", choices=["", "contrast", "anisotropic"])
+    a = ap.parse_args()
+    from oracle import oracle as orc
+    N = a.cube
+    verts, tets, labels, xstar, prm = problem(N, a.variant)
+    n = len(verts)
+    o = orc.Oracle(64, **prm)
+    o.pattern(n, tets); o.assemble(verts, labels); o.setup()
+    b = o.spmv(xstar)
+    x, it = o.solve(b)
+    h = np.array(o.resid_history())
+    idx = sorted({0, 1000 % n, 123456 % n, n // 2, n - 1})
+    nl = o.num_levels()
+    g = {"cube": N, "variant": a.variant, "params": prm, "iterations": int(it), "relres": float(h[-1]), "resid_history": [float(v) for v in h],
+         "x_norm2": float(np.linalg.norm(x)), "b_norm2": float(np.linalg.norm(b)), "sample_idx": [int(i) for i in idx],
+         "x_samples": [float(x[i]) for i in idx], "err_vs_exact": float(np.linalg.norm(x - xstar) / np.linalg.norm(xstar)),
+         "levels": [int(o.level_rows(l)) for l in range(nl)]}
+    json.dump(g, open(golden_path(N, a.variant), "w"), indent=1)
+    print(g["iterations"], g["relres"], g["x_norm2"], g["err_vs_exact"], g["levels"])
+
+
+if __name__ == "__main__":
+    main()
