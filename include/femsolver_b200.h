@@ -91,6 +91,7 @@ int fsb_spmv_fine_device(fsb_solver* s, const double* x_dev, double* y_dev);
 /* y = A x with the assembled (user-ordered) matrix, device pointers: builds right-hand sides without
  * moving the matrix to the host */
 int fsb_apply_matrix_device(fsb_solver* s, const double* x_dev, double* y_dev);
+int fsb_apply_matrix(fsb_solver* s, const double* x_host, double* y_host);   /* the same with host vectors */
 int fsb_precondition_device(fsb_solver* s, const double* r_dev, double* z_dev);
 
 /* stage 4 — sharded solve over the GPUs of one box (absent upstream; one process per GPU).

@@ -226,6 +226,16 @@ int fsb_resid_history(const fsb_solver* s, double* buf, int cap) {
 int fsb_apply_matrix_device(fsb_solver* s, const double* x, double* y) {
   return guarded(s, [&](fsb::Solver& S) { S.apply_matrix(x, y); });
 }
+int fsb_apply_matrix(fsb_solver* s, const double* x, double* y) {
+  return guarded(s, [&](fsb::Solver& S) {
+    const int n = S.rows();
+    if (n == 0) throw std::invalid_argument("Error no matrix specified");
+    fsb::DBuf xd(n, S.ctx.stream), yd(n, S.ctx.stream);
+    xd.from_host(x, n);
+    S.apply_matrix(xd, yd);
+    yd.to_host(y, n);
+  });
+}
 int fsb_spmv_fine_device(fsb_solver* s, const double* x, double* y) {
   return guarded(s, [&](fsb::Solver& S) { if (!S.has_setup) throw std::runtime_error("setup first"); S.spmv_fine(x, y); });
 }

@@ -54,7 +54,7 @@ def load_library():
         "fsb_solve_device": (ci, [vp, vp, vp, C.POINTER(ci), C.POINTER(cd)]),
         "fsb_solve_fem": (ci, [vp, vp, vp, C.POINTER(ci), C.POINTER(cd)]),
         "fsb_resid_history": (ci, [vp, vp, ci]),
-        "fsb_spmv_fine_device": (ci, [vp, vp, vp]), "fsb_apply_matrix_device": (ci, [vp, vp, vp]), "fsb_precondition_device": (ci, [vp, vp, vp]),
+        "fsb_spmv_fine_device": (ci, [vp, vp, vp]), "fsb_apply_matrix_device": (ci, [vp, vp, vp]), "fsb_apply_matrix": (ci, [vp, vp, vp]), "fsb_precondition_device": (ci, [vp, vp, vp]),
         "fsb_time_ms": (cd, [vp, cs]), "fsb_last_launches": (cll, [vp]), "fsb_stream": (vp, [vp]),
         "fsb_profile_report": (ci, [vp, vp, ci]),
         "fsb_dist_prepare": (ci, [vp, ci, ci]), "fsb_dist_handle": (ci, [vp, vp, C.POINTER(cll)]),
@@ -78,7 +78,7 @@ EXPORTED_SYMBOLS = (
     "fsb_level_int fsb_level_val fsb_solve fsb_solve_device fsb_solve_fem fsb_resid_history fsb_spmv_fine_device "
     "fsb_precondition_device fsb_time_ms fsb_last_launches fsb_stream fsb_tet_mass_integrals fsb_tri_quadrature "
     "fsb_profile_report fsb_dist_prepare fsb_dist_handle fsb_dist_connect fsb_dist_disconnect fsb_dist_ranges fsb_dist_level_ranges fsb_dist_info "
-    "fsb_split_by_weight fsb_apply_matrix_device").split()
+    "fsb_split_by_weight fsb_apply_matrix_device fsb_apply_matrix").split()
 
 
 def _p(a):
@@ -355,6 +355,13 @@ class FEMSolver:
         self._L.fsb_dist_info(self._h, C.byref(ns), C.byref(lo), C.byref(hi), _p(hv))
         return {"sharded_levels": ns.value, "user_range": (lo.value, hi.value),
                 "halo_values": [dict(zip(("operator", "residual", "down", "up"), map(int, hv[4 * l: 4 * l + 4]))) for l in range(ns.value)]}
+
+    def apply_matrix(self, x):
+        """y = A x with the assembled (user-ordered) matrix; host vectors, the product runs on the GPU."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty_like(x)
+        self._check(self._L.fsb_apply_matrix(self._h, _p(x), _p(y)))
+        return y
 
     def apply_matrix_device(self, x_ptr: int, y_ptr: int):
         """y = A x on the device (user ordering)."""

@@ -307,29 +307,59 @@ def test_dense_tail_equals_the_kernel_cycle(monkeypatch):
     assert rel(xa2, xb2) <= 1e-12
 
 
-def test_config3_matches_the_oracle_golden():
-    """BASELINE configs[2] at full size (N=118, 1 685 159 DOF): the oracle's solve is stored as a golden fixture
-    (tests/golden/make_oracle_golden.py), so the comparison at this scale needs no CPU solve on the GPU box."""
-    import json, os
-    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "oracle_cube118_pcg.json")))
-    v, t = kuhn(g["cube"])
-    s = make_gpu(v, t, **PCG)
+def _golden_cases():
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("make_oracle_golden", os.path.join(os.path.dirname(__file__), "golden", "make_oracle_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+@pytest.mark.parametrize("N,variant", [(118, ""), (149, "contrast"), (149, "anisotropic"), (255, "")],
+                         ids=["configs2_N118", "configs4_N149_contrast", "configs4_N149_anisotropic", "configs3_N255"])
+def test_baseline_size_matches_the_oracle_golden(N, variant):
+    """BASELINE configs[2], [3] and [4] at FULL size (N=118: 1.7 M DOF; N=255: 16.8 M DOF / 99.5 M tets; N=149 with the
+    8^3-cell label checkerboard c in 1..6, and squeezed by 1/64 in z): the oracle's complete solve of each is stored as a
+    golden fixture (tests/golden/make_oracle_golden.py), so the comparison at this scale needs no CPU solve on the GPU box."""
+    import json
+    m = _golden_cases()
+    g = json.load(open(m.golden_path(N, variant)))
+    v, t, lab, xstar, prm = m.problem(N, variant)
+    s = make_gpu(v, t, lab, **prm)
     s.setup()
     assert [s.level_rows(l) for l in range(s.num_levels())] == g["levels"]   # same aggregates => same level sizes
-    xstar = egg_carton(v)
-    import scipy.sparse as sp
-    ptr, col, val = s.matrix_csr()
-    b = sp.csr_matrix((val, col, ptr)) @ xstar
+    b = s.apply_matrix(xstar)
     assert abs(np.linalg.norm(b) - g["b_norm2"]) <= 1e-12 * g["b_norm2"]
     x = s.solve(np.zeros_like(b), b)
     assert abs(s.iterations - g["iterations"]) <= 2, (s.iterations, g["iterations"])
     h = np.array(s.resid_history())
     ho = np.array(g["resid_history"])
-    m = min(len(h), len(ho))
-    assert np.allclose(h[:m], ho[:m], rtol=1e-6), "residual history differs from the oracle's"
+    k = min(len(h), len(ho))
+    # at equal iteration index (SURVEY 8c policy 4); the squeezed mesh stagnates, so its history is compared a little looser
+    assert np.allclose(h[:k], ho[:k], rtol=1e-6 if variant != "anisotropic" else 1e-5), np.abs(h[:k] / ho[:k] - 1).max()
     assert abs(np.linalg.norm(x) - g["x_norm2"]) <= 1e-8 * g["x_norm2"]
     assert np.allclose(x[g["sample_idx"]], g["x_samples"], rtol=1e-6, atol=1e-9)
     assert rel(x, xstar) <= 2 * g["err_vs_exact"] + 1e-12
+
+
+def test_cubemesh_size256step16_pcg_matches_the_oracle():
+    """BASELINE configs[1]: the repo's TetGen cube (.node/.ele, inverted tets and non-conforming faces), assembled K + M,
+    b = 1 (Example1's right-hand side), PCG to 1e-8: CUDA path against the oracle — pattern, values, aggregates of
+    level 0, iteration count, residual history, solution."""
+    g = golden("CubeMesh_size256step16")
+    prm = dict(PCG)
+    o, s, nl = _setup_pair(g["verts"], g["tets"], g["labels"], **prm)
+    for name in ("permutation", "aggregateIdx", "partitionIdx"):
+        assert np.array_equal(s.level_int(0, name), o.level_int(0, name)), name
+    b = np.ones(len(g["verts"]))
+    xo, ito = o.solve(b)
+    xg = s.solve(np.zeros_like(b), b)
+    assert o.final_relres() <= 1e-8 and s.relres <= 1e-8
+    assert abs(s.iterations - ito) <= 2, (s.iterations, ito)
+    ho, hg = np.array(o.resid_history()), np.array(s.resid_history())
+    k = min(len(ho), len(hg))
+    assert np.allclose(hg[:k], ho[:k], rtol=1e-6)
+    assert rel(xg, xo) <= 1e-6
 
 
 def test_pcg_parity_on_a_triangle_mesh():
