@@ -251,12 +251,13 @@ def parity_block(N, x, iters, hist, levels, x_single=None, iters_single=None):
         ho, h = np.array(g["resid_history"]), np.array(hist)
         m = min(len(h), len(ho))
         hist_rel = float(np.max(np.abs(h[:m] / ho[:m] - 1))) if m else None
-        samp = float(np.max(np.abs(x[g["sample_idx"]] - np.array(g["x_samples"])) / np.maximum(np.abs(np.array(g["x_samples"])), 1e-9)))
+        xs, gs = x[g["sample_idx"]], np.array(g["x_samples"])
+        samp = float(np.max(np.abs(xs - gs) / (1e-6 * np.abs(gs) + 1e-9)))   # <= 1 <=> |diff| <= 1e-6 |golden| + 1e-9 (np.allclose rule of the -m gpu test)
         nrm = float(abs(np.linalg.norm(x) - g["x_norm2"]) / g["x_norm2"])
-        ok = abs(iters - g["iterations"]) <= 2 and (hist_rel is None or hist_rel <= 1e-6) and samp <= 1e-6 and nrm <= 1e-6 \
+        ok = abs(iters - g["iterations"]) <= 2 and (hist_rel is None or hist_rel <= 1e-6) and samp <= 1.0 and nrm <= 1e-6 \
             and [int(r) for r, _ in levels] == g["levels"]
         out["oracle_golden"] = {"file": gpath, "iterations": iters, "golden_iterations": g["iterations"], "iters_equal": iters == g["iterations"],
-                                "hist_max_rel": hist_rel, "samples_max_rel": samp, "x_norm_rel": nrm, "levels_equal": [int(r) for r, _ in levels] == g["levels"], "ok": bool(ok)}
+                                "hist_max_rel": hist_rel, "samples_worst_vs_tol": samp, "x_norm_rel": nrm, "levels_equal": [int(r) for r, _ in levels] == g["levels"], "ok": bool(ok)}
         out["ok"] = out["ok"] and bool(ok)
         out["checks"].append("oracle_golden")
     else:

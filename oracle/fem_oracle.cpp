@@ -832,13 +832,15 @@ struct AggOut {
 
 // a13: CP::OldMIS, ComputePermutationMethods.cu:22-150 (agg_type 0) and a15: CP::MetisBottomUp
 // :151-266 (agg_type 1).  The two differ only in how the fine and the coarse labels are obtained.
+// agg_type 2, CP::MetisTopDown (:267-351), calls no METIS routine at all: statement for statement it is the
+// OldMIS pipeline without the timers and verbose prints (randMIS.cu:474-489 dispatches to it), so it shares the code.
 static void compute_permutation(const ivec& xadj, const ivec& adj, int agg_type, int parameters, int part_max_size, unsigned seed, AggOut& o) {
   int n = (int)xadj.size() - 1;
   int fineDepth = parameters % 100, coarseDepth = (parameters / 100) % 100, minAgg = (parameters / 10000) % 10;
   int coarseSize = part_max_size % 1000, fineSize = (part_max_size / 1000) % 1000;  // MetisBottomUp :180-182
   fineSize = fineSize <= 0 ? 1 : fineSize;
   ivec fineAggregate;
-  if (agg_type == 0) aggregate_graph(minAgg, fineDepth, xadj, adj, fineAggregate, seed);
+  if (agg_type == 0 || agg_type == 2) aggregate_graph(minAgg, fineDepth, xadj, adj, fineAggregate, seed);
   else metis_aggregation(xadj, adj, fineAggregate, fineSize);
   ivec perm(n);
   std::iota(perm.begin(), perm.end(), 0);
@@ -849,7 +851,7 @@ static void compute_permutation(const ivec& xadj, const ivec& adj, int agg_type,
   part_sizes(fineSort, weights, &aggIdx);
   induced_graph(xadj, adj, fineAggregate, o.xadjOut, o.adjOut);
   ivec coarse;
-  if (agg_type == 0) aggregate_weighted_graph(part_max_size, n, coarseDepth, o.xadjOut, o.adjOut, coarse, weights, seed);
+  if (agg_type == 0 || agg_type == 2) aggregate_weighted_graph(part_max_size, n, coarseDepth, o.xadjOut, o.adjOut, coarse, weights, seed);
   else metis_aggregation(o.xadjOut, o.adjOut, coarse, coarseSize);
   remap_induced_graph(o.xadjOut, o.adjOut, coarse);
   ivec plabel(n);
@@ -1056,7 +1058,7 @@ struct Hierarchy {
       Level<T>& L = levels.back();
       int N = L.A.nrows;
       if (N < prm.topSize || num_levels >= prm.maxLevels) { LU.factor(L.A); break; }
-      if (prm.aggregatorType != 0 && prm.aggregatorType != 1) throw std::runtime_error("oracle: only aggregatorType_ 0 (OldMIS) and 1 (METIS bottom-up) are restated");
+      if (prm.aggregatorType < 0 || prm.aggregatorType > 2) throw std::runtime_error("oracle: only aggregatorType_ 0 (OldMIS), 1 (METIS bottom-up) and 2 (\"METIS top-down\" = the MIS pipeline) are restated");
       compute_permutation(L.xadj, L.adj, prm.aggregatorType, prm.randMisParameters, prm.partitionMaxSize, prm.seed, L.agg);
       L.nnout = (int)L.agg.aggregateIdx.size() - 1;
       permute_and_split(L);

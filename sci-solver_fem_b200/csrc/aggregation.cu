@@ -13,11 +13,29 @@
 // a packed 64-bit atomicMax instead of a tuple sort for the per-partition best swap, packed
 // 64-bit radix sorts for the induced graph, device-side convergence counters.
 #include <cstdlib>
+#include <ctime>
 
 #include "fsb_internal.h"
 
 namespace fsb {
 namespace {
+
+// tools: FSB_SETUP_TRACE=1 prints wall-clock laps and loop counts of the aggregation pipeline on stderr
+struct AggTrace {
+  bool on = getenv("FSB_SETUP_TRACE") != nullptr;
+  double last = 0.0;
+  cudaStream_t s;
+  explicit AggTrace(cudaStream_t st) : s(st) { lap(nullptr, 0); }
+  void lap(const char* what, long long count) {
+    if (!on) return;
+    cudaStreamSynchronize(s);
+    timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+    const double now = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    if (what) fprintf(stderr, "[agg] %-22s %8.3f ms  (%lld)\n", what, now - last, count);
+    last = now;
+  }
+};
+long long g_trace_count[4] = {0, 0, 0, 0};  // MIS rounds, allocate sweeps, restrict iterations, runt removals
 
 // ---------------------------------------------------------------- randomized distance-k MIS
 __device__ __forceinline__ unsigned taus_step(unsigned z) {
@@ -103,6 +121,7 @@ void randomized_mis(const Ctx& c, int n, const int* xadj, const int* adj, int k,
       std::swap(bi, bo); std::swap(oi, oo);
     }
     FSB_CHECK_LAUNCH();
+    g_trace_count[0]++;
     if (incomplete.read(0) == 0) return;
   }
   throw std::runtime_error("randomizedMIS did not converge");
@@ -184,6 +203,7 @@ int allocate_sweep(const Ctx& c, int n, const int* xadj, const int* adj, IBuf& p
   allocate_nodes<<<cdiv(n, 256), 256, 0, s>>>(n, xadj, adj, partIn, partOut, aggregated, counter);
   FSB_CHECK_LAUNCH();
   partIn.from_device(partOut, n);  // "partIn = partOut"
+  g_trace_count[1]++;
   return counter.read(0);
 }
 
@@ -287,6 +307,7 @@ void restrict_partition_size(const Ctx& c, int n, const int* xadj, const int* ad
     find_desirability<<<cdiv(n, 256), 256, 0, s>>>(n, averageSize, xadj, adj, partition, partSizes, w, swap_to, bestOfPart);
     make_swaps<<<cdiv(nparts, 256), 256, 0, s>>>(nparts, partition, partSizes, w, swap_to, bestOfPart);
     FSB_CHECK_LAUNCH();
+    g_trace_count[2]++;
     largest = reduce_max_i32(partSizes, nparts, s);
   }
 }
@@ -421,6 +442,8 @@ int metis_aggregate_device_graph(const Ctx& c, int n, const int* xadj_d, const i
 
 // CP::OldMIS (ComputePermutationMethods.cu:22-150, agg_type 0) and CP::MetisBottomUp (:151-266, agg_type 1): the two
 // pipelines differ only in how the fine labels (aggregates) and the coarse labels (partitions) are obtained.
+// agg_type 2, CP::MetisTopDown (:267-351, dispatched at randMIS.cu:474-489), is — despite its name — the OldMIS
+// pipeline statement for statement (no METIS call; only the timers and verbose prints are missing): same code path.
 void compute_permutation(const Ctx& c, int n, const int* xadj, const int* adj, int agg_type, int parameters, int partMaxSize, unsigned seed,
                          Aggregation& out) {
   cudaStream_t s = c.stream;
@@ -429,13 +452,19 @@ void compute_permutation(const Ctx& c, int n, const int* xadj, const int* adj, i
   FSB_CUDA(cudaMemcpyAsync(&nedges, xadj + n, sizeof(int), cudaMemcpyDeviceToHost, s));
   FSB_CUDA(cudaStreamSynchronize(s));
 
+  AggTrace tr(s);
+  for (auto& v : g_trace_count) v = 0;
   const int coarseSize = partMaxSize % 1000;  // MetisBottomUp :180-182
   int fineSize = (partMaxSize / 1000) % 1000;
   fineSize = fineSize <= 0 ? 1 : fineSize;
   IBuf fineAggregate;
-  int nAgg = agg_type == 0 ? aggregate_graph(c, n, xadj, adj, minAgg, fineDepth, seed, fineAggregate)
+  const bool mis_pipeline = agg_type == 0 || agg_type == 2;
+  int nAgg = mis_pipeline ? aggregate_graph(c, n, xadj, adj, minAgg, fineDepth, seed, fineAggregate)
                            : metis_aggregate_device_graph(c, n, xadj, adj, fineSize, fineAggregate);
 
+  tr.lap("fine aggregates", n);
+  tr.lap("  MIS rounds", g_trace_count[0]); tr.lap("  allocate sweeps", g_trace_count[1]);
+  for (auto& v : g_trace_count) v = 0;
   // rows ordered by (aggregate, vertex): stable sort of the vertex ids by aggregate id (:72-75)
   IBuf perm(n, s), fineSort(n, s), iotaN(n, s);
   iota_i32(iotaN, n, s);
@@ -448,11 +477,14 @@ void compute_permutation(const Ctx& c, int n, const int* xadj, const int* adj, i
   induced_graph(c, n, xadj, adj, nedges, fineAggregate, nAgg, out.xadjOut, out.adjOut);
   if ((int)out.xadjOut.size() != nAgg + 1) throw std::runtime_error("induced graph: an aggregate has no external edge");
   int nInducedEdges = (int)out.adjOut.size();
+  tr.lap("sort + induced graph", nInducedEdges);
 
   IBuf coarse;
-  int nParts = agg_type == 0 ? aggregate_weighted_graph(c, nAgg, out.xadjOut, out.adjOut, weights, partMaxSize, n, coarseDepth, seed, coarse)
+  int nParts = mis_pipeline ? aggregate_weighted_graph(c, nAgg, out.xadjOut, out.adjOut, weights, partMaxSize, n, coarseDepth, seed, coarse)
                              : metis_aggregate_device_graph(c, nAgg, out.xadjOut, out.adjOut, std::max(coarseSize, 1), coarse);
 
+  tr.lap("coarse partitions", nAgg);
+  tr.lap("  MIS rounds", g_trace_count[0]); tr.lap("  allocate sweeps", g_trace_count[1]); tr.lap("  restrict iterations", g_trace_count[2]);
   // remapInducedGraph (misHelpers.cu:1258-1280): aggregates renumbered by (partition, old id)
   {
     IBuf iotaA(nAgg, s), cperm(nAgg, s), csorted(nAgg, s), ciperm(nAgg, s);
@@ -498,6 +530,7 @@ void compute_permutation(const Ctx& c, int n, const int* xadj, const int* adj, i
   inverse_perm<<<cdiv(n, 256), 256, 0, s>>>(n, out.ipermutation, out.permutation);
   out.partitionLabel.swap(plabelSorted);
   out.n = n; out.nAgg = nAgg; out.nParts = nParts;
+  tr.lap("remap + final orders", nParts);
   FSB_CHECK_LAUNCH();
   FSB_CUDA(cudaStreamSynchronize(s));
 }

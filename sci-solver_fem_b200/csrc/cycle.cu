@@ -189,11 +189,22 @@ __global__ void __launch_bounds__(256) halo_push_kernel(DistDev d, Chan sig, Cha
                                                         unsigned int* ticket, const int* __restrict__ done) {
   pdl_wait();
   if (done && *done) return;
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
-    int q = 0;
-    while (k >= list_ptr[q + 1]) q++;
-    const int j = list[k];
-    dst.p[q][j] = src[j];
+  // four independent entries per trip: all index loads, then all value loads, then the peer stores
+  const int S = gridDim.x * blockDim.x;
+  for (int k0 = blockIdx.x * blockDim.x + threadIdx.x; k0 < total; k0 += 4 * S) {
+    int j[4], q[4];
+    double v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int k = k0 + u * S;
+      j[u] = k < total ? __ldg(list + k) : -1;
+      q[u] = 0;
+      if (k < total) while (k >= __ldg(list_ptr + q[u] + 1)) q[u]++;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) v[u] = j[u] >= 0 ? src[j[u]] : 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; u++) if (j[u] >= 0) dst.p[q[u]][j[u]] = v[u];
   }
   push_epilogue(d, sig, wt, ticket);
 }
@@ -1176,7 +1187,7 @@ void launch_spmv_dot_sell(const Ctx& c, const Sell& A, const double* x, double* 
 void launch_halo_push(const Ctx& c, Chan sig, Chan wt, int total, const int* list, const int* list_ptr, const double* src, const PeerPtrs& dst, const int* done) {
   g_launch_counter++;
   ProfScope ps(c, "halo_push");
-  int blocks = std::max(1, std::min(cdiv(total, 512), c.num_sms));
+  int blocks = std::max(1, std::min(cdiv(total, 1024), c.num_sms));
   FSB_LAUNCH((halo_push_kernel), blocks, 256, 0, c.stream, c.dist, sig, wt, total, list, list_ptr, src, dst, c.dist_ticket, done);
   FSB_CHECK_LAUNCH();
 }

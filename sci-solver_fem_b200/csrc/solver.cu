@@ -177,10 +177,11 @@ __global__ static void part_rows_kernel(int nparts, const int* __restrict__ psta
 void Solver::setup() {
   if (A0.nrows == 0) throw std::invalid_argument("Error no matrix specified");  // FEMSolver::checkMatrixForValidContents
   if (pat.n == 0) throw std::runtime_error("setup needs the mesh graph: call assemble() first");
-  if (prm.aggregatorType != 0 && prm.aggregatorType != 1)
-    throw std::invalid_argument("aggregatorType_ 0 (OldMIS) and 1 (METIS bottom-up) are implemented; 2-5 are out of scope (SURVEY 8f-2)");
+  if (prm.aggregatorType < 0 || prm.aggregatorType > 2)
+    throw std::invalid_argument("aggregatorType_ 0 (OldMIS), 1 (METIS bottom-up) and 2 (METIS top-down = the MIS pipeline upstream) are implemented; "
+                                "3-5 (AggMIS) are out of scope (SURVEY 8f-2)");
   if (prm.dsType != 0) throw std::invalid_argument("only dsType_ 0 is implemented (dsType_ 1 cannot run upstream either)");
-  if (prm.aggregatorType == 0 && prm.partitionMaxSize > 1024) throw std::invalid_argument("partitionMaxSize_ must be <= 1024");
+  if (prm.aggregatorType != 1 && prm.partitionMaxSize > 1024) throw std::invalid_argument("partitionMaxSize_ must be <= 1024");
   FSB_CUDA(cudaSetDevice(ctx.device));
   cudaStream_t s = ctx.stream;
   dist_disconnect();

@@ -414,6 +414,24 @@ def test_metis_bottom_up_aggregator():
     assert abs(s.iterations - ito) <= 2 and rel(xg, xo) <= 1e-6
 
 
+def test_metis_top_down_aggregator_is_the_mis_pipeline():
+    """aggregatorType_ = 2 (CP::MetisTopDown, ComputePermutationMethods.cu:267-351): upstream's routine of that name calls
+    no METIS function — it is the OldMIS pipeline minus timers — so the hierarchy must equal type 0's bit for bit,
+    in the oracle and on the GPU."""
+    v, t = kuhn(20)
+    o0, s0, nl0 = _setup_pair(v, t, **dict(PCG, aggregatorType=0))
+    o2, s2, nl2 = _setup_pair(v, t, **dict(PCG, aggregatorType=2))
+    assert nl0 == nl2 == s2.num_levels() and nl2 >= 3
+    for lev in range(nl2 - 1):
+        for name in INT_ARRAYS:
+            assert np.array_equal(s2.level_int(lev, name), o2.level_int(lev, name)), (lev, name)
+            assert np.array_equal(s2.level_int(lev, name), s0.level_int(lev, name)), (lev, name)
+    b = o2.spmv(egg_carton(v))
+    xo, ito = o2.solve(b)
+    xg = s2.solve(np.zeros_like(b), b)
+    assert abs(s2.iterations - ito) <= 2 and rel(xg, xo) <= 1e-6
+
+
 @pytest.mark.parametrize("case", ["contrast", "anisotropic"])
 def test_config5_high_contrast_and_anisotropy(case):
     """BASELINE config 5 at oracle-checkable size: label checkerboard c in {1..6} (8^3-cell blocks -> 4^3 here)
