@@ -99,17 +99,20 @@ int fsb_precondition_device(fsb_solver* s, const double* r_dev, double* z_dev);
  *   fsb_dist_prepare(rank, nranks)  deals the partitions of the fine level — and of every coarser level that still
  *                                   gives each GPU enough rows — out in contiguous nnz-balanced ranges, builds
  *                                   the push lists of every exchange and allocates the exchange arena;
- *   fsb_dist_handle                 returns the 64-byte CUDA IPC handle of that arena (all-gather it, e.g.
- *                                   with torch.distributed / MPI);
- *   fsb_dist_connect(handles)       maps the peers' arenas (nranks x 64 bytes, rank order).
+ *   fsb_dist_blob                   returns this process's connection record (fsb_dist_blob_bytes() bytes: the CUDA
+ *                                   IPC handle of the arena and the layout of its receive buffers); all-gather the
+ *                                   records of all processes in rank order (e.g. with torch.distributed / MPI);
+ *   fsb_dist_connect(blobs)         maps the peers' arenas and checks that every pair of GPUs agrees on what it
+ *                                   exchanges (nranks x fsb_dist_blob_bytes() bytes, rank order).
  * After that fsb_solve / fsb_solve_device with solverType = 1 run sharded; all processes must call them
  * together.  fsb_solve_device reads b / x0 at this GPU's rows and leaves the FULL solution in x on every
  * GPU; fsb_solve (host buffers) moves only the slice [user_lo, user_hi) of b, x0 and x over PCIe (the
  * range of user-numbered rows that covers this GPU's rows, fsb_dist_info) — x outside it is untouched.
  * fsb_setup or fsb_dist_disconnect ends the sharded mode. */
 int fsb_dist_prepare(fsb_solver* s, int rank, int nranks);
-int fsb_dist_handle(fsb_solver* s, void* handle64, long long* arena_bytes);
-int fsb_dist_connect(fsb_solver* s, const void* handles);
+int fsb_dist_blob_bytes(void);
+int fsb_dist_blob(fsb_solver* s, void* blob, long long* arena_bytes);
+int fsb_dist_connect(fsb_solver* s, const void* blobs);
 int fsb_dist_disconnect(fsb_solver* s);
 /* first partition / first fine row / first coarse row of every rank (nranks+1 entries each); returns nranks */
 int fsb_dist_ranges(const fsb_solver* s, int* part_begin, int* row_begin, int* coarse_begin);

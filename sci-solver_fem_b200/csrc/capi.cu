@@ -259,10 +259,11 @@ int fsb_profile_report(fsb_solver* s, char* buf, int cap) {
   return (int)r.size() + 1;
 }
 int fsb_dist_prepare(fsb_solver* s, int rank, int nranks) { return guarded(s, [&](fsb::Solver& S) { S.dist_prepare(rank, nranks); }); }
-int fsb_dist_handle(fsb_solver* s, void* handle64, long long* arena_bytes) {
-  return guarded(s, [&](fsb::Solver& S) { S.dist_get_handle(handle64, arena_bytes); });
+int fsb_dist_blob_bytes(void) { return fsb::Solver::kDistBlobBytes; }
+int fsb_dist_blob(fsb_solver* s, void* blob, long long* arena_bytes) {
+  return guarded(s, [&](fsb::Solver& S) { S.dist_get_blob(blob, arena_bytes); });
 }
-int fsb_dist_connect(fsb_solver* s, const void* handles) { return guarded(s, [&](fsb::Solver& S) { S.dist_connect(handles); }); }
+int fsb_dist_connect(fsb_solver* s, const void* blobs) { return guarded(s, [&](fsb::Solver& S) { S.dist_connect(blobs); }); }
 int fsb_dist_disconnect(fsb_solver* s) { return guarded(s, [&](fsb::Solver& S) { S.dist_disconnect(); }); }
 int fsb_dist_ranges(const fsb_solver* s, int* part_begin, int* row_begin, int* coarse_begin) {
   return fsb_dist_level_ranges(s, 0, part_begin, row_begin, coarse_begin);

@@ -43,23 +43,33 @@ struct PerDeviceOnce {
 
 // Device-visible description of the GPU group of a sharded solve (one process per GPU; peers'
 // arenas are mapped through CUDA IPC and reached over NVLink).  nranks == 1: everything is local.
-// Exchanges are CHANNELS: a producer kernel stores its boundary values into the peers' copies of a
-// vector, fences, and publishes the channel's epoch into flag word [1 + chan][rank] of every destination
-// peer; it never waits.  A consumer waits (in its prologue) until the flag words of the peers it receives
-// from have reached its own epoch of that channel.  Row 0 of the flag table belongs to the all-reduce.
+//
+// Exchanges inside the iteration use a FLAG-IN-DATA protocol (the idea of NCCL's LL protocol): a value travels
+// as one 16-byte store {lo32, epoch, hi32, epoch} into the receiver's buffer; 8-byte stores are atomic, so a
+// receiver that polls its slot until both epoch words match has the value — no fence, no separate flag, no
+// barrier, one NVLink one-way latency.  The epoch is a device counter that every exchange kernel of the solve
+// bumps once (all GPUs run the same sequence of exchanges, skipped consistently once `done` is set).
+// The all-reduce of the dot products uses the same slots ([2][kMaxRanks], parity double-buffered).
+// Only the all-gather of the solution at the end of a solve still uses the fenced store + flag handshake.
 constexpr int kMaxRanks = 8;
-constexpr int kMaxChan = 47;   // flag table: (1 + kMaxChan) rows of kMaxRanks words
+constexpr int kMaxChan = 47;   // exchange channels: 3 of the PCG driver + 5 per sharded level
 struct DistDev {
   int rank = 0, nranks = 1;
-  unsigned long long* my_flags = nullptr;             // [(1 + kMaxChan) * kMaxRanks] written by the peers
-  unsigned long long* peer_flags[kMaxRanks] = {};     // the same table in every peer's arena
-  double* my_red = nullptr;                           // [2][kMaxRanks] all-reduce slots (parity double-buffered)
-  double* peer_red[kMaxRanks] = {};
-  unsigned long long* epoch = nullptr;                // [1 + kMaxChan] local counters: [0] all-reduce, [1 + c] channel c
+  unsigned long long* my_flags = nullptr;             // [kMaxRanks] epoch flags of the fenced handshake, written by the peers
+  unsigned long long* peer_flags[kMaxRanks] = {};     // the same array in every peer's arena
+  uint4* my_red = nullptr;                            // [2][kMaxRanks] all-reduce slots {lo, epoch, hi, epoch}
+  uint4* peer_red[kMaxRanks] = {};
+  unsigned long long* epoch = nullptr;                // [2] local counters: [0] all-reduce, [1] fenced handshake
+  unsigned* xchg = nullptr;                           // epoch of the flag-in-data exchanges (bumped by every exchange kernel)
   int* error = nullptr;                               // set when a peer wait times out; every later wait returns at once
 };
-// a channel as seen by one kernel launch: id, peers it signals (producer) / waits for (consumer)
-struct Chan { int id = -1; unsigned mask = 0; };
+// one flag-in-data exchange as seen by this GPU
+struct LLXchg {
+  const int* sidx = nullptr; const int* sptr = nullptr; int stotal = 0;  // what I send: indices into the source vector, segment per destination
+  const int* ridx = nullptr; int rtotal = 0;                              // where slot k of my receive buffer goes in the destination vector
+  uint4* mybuf = nullptr;                                                 // my receive buffer of the channel (rtotal slots)
+  uint4* peerbuf[kMaxRanks] = {};                                         // start of MY segment inside peer q's receive buffer
+};
 
 // Optional per-launch timing (CUDA events around every solve-phase kernel; used by bench.py's
 // roofline pass, never inside a timed region).

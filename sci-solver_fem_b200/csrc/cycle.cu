@@ -69,74 +69,51 @@ __device__ __forceinline__ double final_sum(const double* partials, int n, doubl
 }
 
 // ------------------------------------------------------------------ cross-GPU exchange (NVLink peer memory)
-// Flag words are epochs that only grow, and every GPU executes the same sequence of exchanges, so no
-// reset is ever needed.  A wait that exceeds ~10 s raises the error flag; once it is set every later
-// wait returns immediately (the PCG update kernel turns it into `done`, the host reports it).
-__device__ __forceinline__ void spin_until(const DistDev& d, volatile unsigned long long* f, unsigned long long ep) {
-  if (*(volatile int*)d.error) return;
+// Protocols: see DistDev / LLXchg (common.cuh).  A wait that exceeds ~10 s raises the error flag; once it is
+// set every later wait returns immediately (the PCG update kernel turns it into `done`, the host reports it).
+__device__ __forceinline__ bool wait_expired(const DistDev& d, long long t0, unsigned& spins) {
+  if ((++spins & 1023u) != 0) return false;
+  if (*(volatile int*)d.error) return true;
+  if (clock64() - t0 > 20000000000ll) { *(volatile int*)d.error = 1; __threadfence_system(); return true; }  // ~10 s: never hang the GPU
+  return false;
+}
+__device__ __forceinline__ void ll_store(uint4* p, double v, unsigned ep) {
+  const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(lo), "r"(ep), "r"(hi), "r"(ep) : "memory");
+}
+// polls a slot until both 8-byte halves carry the epoch; returns the value (0 when a wait timed out)
+__device__ __forceinline__ double ll_load(const DistDev& d, const uint4* p, unsigned ep) {
+  unsigned lo, f0, hi, f1, spins = 0;
+  if (*(volatile int*)d.error) return 0.0;
   const long long t0 = clock64();
-  unsigned spins = 0;
-  while (*f < ep) {
-    if ((++spins & 1023u) == 0) {
-      if (*(volatile int*)d.error) break;
-      if (clock64() - t0 > 20000000000ll) { *(volatile int*)d.error = 1; __threadfence_system(); break; }  // ~10 s: never hang the GPU
-    }
+  while (true) {
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1) : "l"(p) : "memory");
+    if (f0 == ep && f1 == ep) break;
+    if (wait_expired(d, t0, spins)) return 0.0;
   }
+  return __hiloint2double((int)hi, (int)lo);
 }
 
-// all-ranks barrier of the all-reduce: thread q publishes to peer q (value first, system fence, then the
-// epoch) and waits for peer q's word.
-__device__ __forceinline__ void cross_signal_wait(const DistDev& d, unsigned long long ep) {
-  const int t = threadIdx.x;
-  if (t < d.nranks) {
-    __threadfence_system();
-    *(reinterpret_cast<volatile unsigned long long*>(d.peer_flags[t]) + d.rank) = ep;
-    spin_until(d, reinterpret_cast<volatile unsigned long long*>(d.my_flags) + t, ep);
-    __threadfence_system();
-  }
-  __syncthreads();
-}
-
-// all-reduce(sum) of one double per GPU, executed by the last CTA of a reduction kernel: every GPU
-// adds the contributions in rank order, so the result is bit-identical everywhere.
+// all-reduce(sum) of one double per GPU, executed by the last CTA of a reduction kernel: thread q sends this
+// GPU's partial to GPU q and receives GPU q's; every GPU adds the contributions in rank order, so the result is
+// bit-identical everywhere.  Slots are double-buffered by the parity of the all-reduce count: a fast GPU's next
+// contribution cannot overwrite a slot a slow GPU has not read yet.
 __device__ __forceinline__ double cross_sum(const DistDev& d, double local) {
   if (d.nranks == 1) return local;  // uniform
-  __shared__ double s_val;
+  __shared__ double s_part[kMaxRanks];
   __shared__ unsigned long long s_ep;
-  if (threadIdx.x == 0) { s_val = local; s_ep = ++d.epoch[0]; }
+  if (threadIdx.x == 0) s_ep = ++d.epoch[0];
   __syncthreads();
-  const unsigned long long ep = s_ep;
-  const int par = (int)(ep & 1ull) * kMaxRanks;
-  if (threadIdx.x < d.nranks) *(reinterpret_cast<volatile double*>(d.peer_red[threadIdx.x]) + par + d.rank) = s_val;
-  cross_signal_wait(d, ep);
+  const unsigned ep = (unsigned)s_ep;
+  const int par = (int)(s_ep & 1ull) * kMaxRanks;
+  if (threadIdx.x < d.nranks) {
+    ll_store(d.peer_red[threadIdx.x] + par + d.rank, local, ep);
+    s_part[threadIdx.x] = ll_load(d, d.my_red + par + threadIdx.x, ep);
+  }
+  __syncthreads();
   double tot = 0.0;
-  if (threadIdx.x == 0) for (int q = 0; q < d.nranks; q++) tot += *(reinterpret_cast<volatile double*>(d.my_red) + par + q);
+  if (threadIdx.x == 0) for (int q = 0; q < d.nranks; q++) tot += s_part[q];
   return tot;
-}
-
-// producer side of a channel, called by the last CTA of a push kernel after all CTAs have fenced their
-// peer stores: bump the channel's epoch and publish it to the destination peers.  Never waits.
-__device__ __forceinline__ void chan_signal(const DistDev& d, Chan ch) {
-  __shared__ unsigned long long s_cep;
-  if (threadIdx.x == 0) s_cep = ++d.epoch[1 + ch.id];
-  __syncthreads();
-  if (threadIdx.x < d.nranks && threadIdx.x != d.rank && (ch.mask >> threadIdx.x & 1u)) {
-    __threadfence_system();
-    *(reinterpret_cast<volatile unsigned long long*>(d.peer_flags[threadIdx.x]) + (1 + ch.id) * kMaxRanks + d.rank) = s_cep;
-  }
-}
-
-// consumer side: every CTA that is about to read values pushed through channel `ch` calls this first.
-// The expected epoch is this GPU's own count of the channel (its own push precedes the consumer in stream
-// order and all GPUs run the same sequence).  Waits only for the peers in ch.mask (those that send to this GPU).
-__device__ __forceinline__ void chan_wait(const DistDev& d, Chan ch) {
-  if (ch.id < 0) return;  // uniform
-  if (threadIdx.x < d.nranks && threadIdx.x != d.rank && (ch.mask >> threadIdx.x & 1u)) {
-    const unsigned long long ep = *(reinterpret_cast<volatile unsigned long long*>(d.epoch) + 1 + ch.id);
-    spin_until(d, reinterpret_cast<volatile unsigned long long*>(d.my_flags) + (1 + ch.id) * kMaxRanks + threadIdx.x, ep);
-    __threadfence_system();
-  }
-  __syncthreads();
 }
 
 // Programmatic dependent launch: every kernel of the solve starts with griddepcontrol.wait
@@ -164,68 +141,93 @@ inline cudaLaunchConfig_t pdl_config(dim3 grid, dim3 block, size_t smem, cudaStr
   } while (0)
 
 
-// pushes owned boundary values into the peers' copies of a vector: entry k of `list` goes to the peer
-// whose segment of list_ptr contains k (same index in the peer's copy).  The last CTA publishes the
-// channel epoch to the destination peers (sig.mask) and then waits for the peers this GPU receives from
-// (wt.mask) — a neighbour-only handshake instead of an all-ranks barrier; when the kernel has finished, the
-// halo values of this exchange are in place for the consumer kernel that follows in the stream.
-// One system-scope fence per CTA (thread 0, after the CTA barrier: fences are cumulative) — a fence per
-// thread costs a round trip to the system coherence point each.
-__device__ __forceinline__ void push_epilogue(const DistDev& d, Chan sig, Chan wt, unsigned int* ticket) {
+// One exchange of the sharded solve (halo of a vector, restricted residual to the owners of the next level, coarse
+// corrections back, all-gather onto the replicated levels): every GPU sends its list entries of `src` into its
+// segment of each destination's receive buffer (coalesced 16-byte flag-in-data stores) and then drains its own
+// receive buffer into `dst`.  No fence, no flag word, no barrier: a thread that has seen the epoch in both halves
+// of a slot has the value.  The grid is small (<= one CTA per SM, all resident), every CTA sends before it polls.
+__global__ void __launch_bounds__(256) ll_exchange_kernel(DistDev d, LLXchg x, const double* __restrict__ src, double* __restrict__ dst,
+                                                          unsigned int* ticket, const int* __restrict__ done) {
+  pdl_wait();
   __shared__ int s_last;
+  if (done && *done) return;
+  // the last CTA of the previous exchange kernel bumped the epoch; it is bumped again only after every CTA of this
+  // grid has finished (ticket below), i.e. after every CTA has read it
+  const unsigned ep = *(volatile unsigned*)d.xchg + 1u;
+  const int S = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int k0 = t0; k0 < x.stotal; k0 += 4 * S) {  // four independent entries per trip
+    int j[4], q[4];
+    double v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int k = k0 + u * S;
+      j[u] = k < x.stotal ? __ldg(x.sidx + k) : -1;
+      q[u] = 0;
+      if (k < x.stotal) while (k >= __ldg(x.sptr + q[u] + 1)) q[u]++;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) v[u] = j[u] >= 0 ? src[j[u]] : 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (j[u] >= 0) ll_store(x.peerbuf[q[u]] + (k0 + u * S - __ldg(x.sptr + q[u])), v[u], ep);
+  }
+  for (int k0 = t0; k0 < x.rtotal; k0 += 8 * S) {  // eight slots polled together: one L2 round trip when the data is already there
+    unsigned lo[8], f0[8], hi[8], f1[8];
+    int r[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int k = k0 + u * S;
+      r[u] = -1;
+      if (k < x.rtotal) {
+        r[u] = __ldg(x.ridx + k);
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo[u]), "=r"(f0[u]), "=r"(hi[u]), "=r"(f1[u]) : "l"(x.mybuf + k) : "memory");
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      if (r[u] < 0) continue;
+      double v = __hiloint2double((int)hi[u], (int)lo[u]);
+      if (f0[u] != ep || f1[u] != ep) v = ll_load(d, x.mybuf + (k0 + u * S), ep);  // not there yet: poll this slot
+      dst[r[u]] = v;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) *d.xchg = ep;
+}
+
+// all-gather by peer stores with the fenced handshake (end of a solve: every GPU gets the full solution): the owned
+// slice [begin, end) of a vector goes into every peer's copy, one system fence per CTA (thread 0 after the CTA
+// barrier — fences are cumulative), the last CTA publishes an epoch flag to every peer and waits for theirs.
+__global__ void __launch_bounds__(256) push_all_kernel(DistDev d, int begin, int end, const double* __restrict__ src, PeerPtrs dst,
+                                                       unsigned int* ticket) {
+  pdl_wait();
+  __shared__ int s_last;
+  __shared__ unsigned long long s_ep;
+  for (int j = begin + blockIdx.x * blockDim.x + threadIdx.x; j < end; j += gridDim.x * blockDim.x) {
+    const double v = src[j];
+    for (int q = 0; q < d.nranks; q++) if (q != d.rank) dst.p[q][j] = v;
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence_system();
     s_last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1);
   }
   __syncthreads();
-  if (s_last) {
-    chan_signal(d, sig);
-    chan_wait(d, wt);
+  if (!s_last) return;
+  if (threadIdx.x == 0) s_ep = ++d.epoch[1];
+  __syncthreads();
+  if (threadIdx.x < d.nranks && threadIdx.x != d.rank) {
+    __threadfence_system();
+    *(reinterpret_cast<volatile unsigned long long*>(d.peer_flags[threadIdx.x]) + d.rank) = s_ep;
+    volatile unsigned long long* f = reinterpret_cast<volatile unsigned long long*>(d.my_flags) + threadIdx.x;
+    unsigned spins = 0;
+    const long long t0 = clock64();
+    if (!*(volatile int*)d.error)
+      while (*f < s_ep) if (wait_expired(d, t0, spins)) break;
+    __threadfence_system();
   }
-}
-__global__ void __launch_bounds__(256) halo_push_kernel(DistDev d, Chan sig, Chan wt, int total, const int* __restrict__ list,
-                                                        const int* __restrict__ list_ptr, const double* __restrict__ src, PeerPtrs dst,
-                                                        unsigned int* ticket, const int* __restrict__ done) {
-  pdl_wait();
-  if (done && *done) return;
-  // four independent entries per trip: all index loads, then all value loads, then the peer stores
-  const int S = gridDim.x * blockDim.x;
-  for (int k0 = blockIdx.x * blockDim.x + threadIdx.x; k0 < total; k0 += 4 * S) {
-    int j[4], q[4];
-    double v[4];
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const int k = k0 + u * S;
-      j[u] = k < total ? __ldg(list + k) : -1;
-      q[u] = 0;
-      if (k < total) while (k >= __ldg(list_ptr + q[u] + 1)) q[u]++;
-    }
-#pragma unroll
-    for (int u = 0; u < 4; u++) v[u] = j[u] >= 0 ? src[j[u]] : 0.0;
-#pragma unroll
-    for (int u = 0; u < 4; u++) if (j[u] >= 0) dst.p[q[u]][j[u]] = v[u];
-  }
-  push_epilogue(d, sig, wt, ticket);
-}
-
-// all-gather by peer stores: the owned slice [begin, end) of a vector is written into every peer's copy
-__global__ void __launch_bounds__(256) push_all_kernel(DistDev d, Chan sig, Chan wt, int begin, int end, const double* __restrict__ src, PeerPtrs dst,
-                                                       unsigned int* ticket, const int* __restrict__ done) {
-  pdl_wait();
-  if (done && *done) return;
-  for (int j = begin + blockIdx.x * blockDim.x + threadIdx.x; j < end; j += gridDim.x * blockDim.x) {
-    const double v = src[j];
-    for (int q = 0; q < d.nranks; q++) if (q != d.rank) dst.p[q][j] = v;
-  }
-  push_epilogue(d, sig, wt, ticket);
-}
-
-// stand-alone consumer wait for kernels that have no wait hook of their own (smoothers, dense GEMV, gathers)
-__global__ void __launch_bounds__(32) chan_wait_kernel(DistDev d, Chan ch, const int* __restrict__ done) {
-  pdl_wait();
-  if (done && *done) return;
-  chan_wait(d, ch);
 }
 
 // ------------------------------------------------------------------ SpMV family (CSR-stream)
@@ -307,25 +309,22 @@ __global__ void __launch_bounds__(SPMV_ROWS) csr_stream_kernel(int n, const int*
 }
 
 template <int MODE>
-__global__ void spmv_vector_kernel(DistDev dist, Chan wch, int row_begin, int n, const int* __restrict__ ptr, const int* __restrict__ col,
+__global__ void spmv_vector_kernel(int row_begin, int n, const int* __restrict__ ptr, const int* __restrict__ col,
                                    const double* __restrict__ val, const double* __restrict__ x, double* __restrict__ y,
                                    const double* __restrict__ b, const int* __restrict__ done);
 
 template <int MODE, bool DOT>
 void spmv_dispatch(const Ctx& c, const DCsr& A, const double* x, double* y, const double* b, double* partials, PcgScalars* sc,
-                   const int* done, const char* name, RowRange rr = RowRange(), Chan wch = Chan()) {
+                   const int* done, const char* name, RowRange rr = RowRange()) {
   int n = A.nrows;
   if (n == 0) return;
   g_launch_counter++;
   ProfScope ps(c, name);
   const bool ranged = rr.end >= 0;
   if (ranged && DOT) throw std::runtime_error("row-ranged CSR dot is not implemented (use the SELL copy)");
-  if (wch.id >= 0 && !ranged) throw std::runtime_error("a channel wait needs the row-ranged (sharded) SpMV");
   if (!DOT && (ranged || (double)A.nnz > 32.0 * n || n < 32768)) {  // long rows, a small operator or a row range: one warp per row
     const int r0 = ranged ? rr.begin : 0, r1 = ranged ? rr.end : n;
-    // an empty range still launches one CTA when it has to consume a channel (the epoch bookkeeping is per launch)
-    if (r1 > r0 || wch.id >= 0)
-      FSB_LAUNCH((spmv_vector_kernel<MODE>), std::max(1, cdiv((long long)(r1 - r0) * 32, 256)), 256, 0, c.stream, c.dist, wch, r0, r1, A.ptr, A.col, A.val, x, y, b, done);
+    if (r1 > r0) FSB_LAUNCH((spmv_vector_kernel<MODE>), cdiv((long long)(r1 - r0) * 32, 256), 256, 0, c.stream, r0, r1, A.ptr, A.col, A.val, x, y, b, done);
   } else
     FSB_LAUNCH((csr_stream_kernel<MODE, DOT>), cdiv(n, SPMV_ROWS), SPMV_ROWS, 0, c.stream, n, A.ptr, A.col, A.val, x, y, b, partials, sc, done);
   FSB_CHECK_LAUNCH();
@@ -335,7 +334,7 @@ void spmv_dispatch(const Ctx& c, const DCsr& A, const double* x, double* y, cons
 // request per warp for col and one for val; four steps are kept in flight together with their x
 // gathers.  The row sum runs in column order (same rounding sequence as a sequential CSR loop).
 template <int MODE, bool DOT>
-__global__ void __launch_bounds__(256) sell_spmv_kernel(DistDev dist, Chan wch, int row_begin, int row_end, int list_begin, int list_end,
+__global__ void __launch_bounds__(256) sell_spmv_kernel(DistDev dist, int row_begin, int row_end, int list_begin, int list_end,
                                                         const int* __restrict__ rowmap, int n, const long long* __restrict__ sptr,
                                                         const int* __restrict__ col, const double* __restrict__ val,
                                                         const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ b,
@@ -345,7 +344,6 @@ __global__ void __launch_bounds__(256) sell_spmv_kernel(DistDev dist, Chan wch, 
   __shared__ double s_warp[32];
   __shared__ int s_flag;
   if (done && *done) return;
-  chan_wait(dist, wch);  // sharded solve: the halo values of x have arrived (no-op otherwise)
   // list position i (rows may be length-sorted inside windows: rowmap); owned rows are [row_begin, row_end).
   // The grid may be smaller than the list (fused dot: fewer partial sums and tickets): grid-stride over 256-row chunks.
   const int lane = threadIdx.x & 31;
@@ -406,7 +404,7 @@ __global__ void __launch_bounds__(256) sell_spmv_kernel(DistDev dist, Chan wch, 
 
 template <int MODE, bool DOT>
 void sell_dispatch(const Ctx& c, const Sell& A, const double* x, double* y, const double* b, double* partials, PcgScalars* sc,
-                   const int* done, const char* name, RowRange rr = RowRange(), Chan wch = Chan()) {
+                   const int* done, const char* name, RowRange rr = RowRange()) {
   if (A.nrows == 0) return;
   const int r0 = rr.end >= 0 ? rr.begin : 0, r1 = rr.end >= 0 ? rr.end : A.nrows;
   g_launch_counter++;
@@ -414,11 +412,11 @@ void sell_dispatch(const Ctx& c, const Sell& A, const double* x, double* y, cons
   // list positions that can hold the owned rows: whole sort windows when the rows are length-sorted
   const int gran = A.window > 0 ? A.window : 32;
   const int l0 = r0 / gran * gran, l1 = std::min(A.nrows, (r1 + gran - 1) / gran * gran);
-  if (l1 <= l0 && !DOT && wch.id < 0) return;  // (an empty owned range still takes part in the all-reduce / consumes its channel)
+  if (l1 <= l0 && !DOT) return;  // (an empty owned range still takes part in the all-reduce)
   static const int dot_ctas_per_sm = getenv("FSB_DOT_CTAS") ? atoi(getenv("FSB_DOT_CTAS")) : 12;  // tuning knob
   int blocks = std::max(1, cdiv(std::max(0, l1 - l0), 256));
   if (DOT) blocks = std::min(blocks, c.num_sms * dot_ctas_per_sm);
-  FSB_LAUNCH((sell_spmv_kernel<MODE, DOT>), blocks, 256, 0, c.stream, c.dist, wch, r0, r1, l0, l1, A.rowmap.size() ? A.rowmap.get() : nullptr, A.nrows,
+  FSB_LAUNCH((sell_spmv_kernel<MODE, DOT>), blocks, 256, 0, c.stream, c.dist, r0, r1, l0, l1, A.rowmap.size() ? A.rowmap.get() : nullptr, A.nrows,
                                                                        A.sptr, A.col, A.val, x, y, b, partials, sc, done);
   FSB_CHECK_LAUNCH();
 }
@@ -923,13 +921,12 @@ __global__ void __launch_bounds__(BLOCK) smooth_cluster_kernel(int C, int G, int
 
 // warp-per-row SpMV for long rows (restriction operators, coarse operators)
 template <int MODE>
-__global__ void __launch_bounds__(256) spmv_vector_kernel(DistDev dist, Chan wch, int row_begin, int n, const int* __restrict__ ptr,
+__global__ void __launch_bounds__(256) spmv_vector_kernel(int row_begin, int n, const int* __restrict__ ptr,
                                                           const int* __restrict__ col, const double* __restrict__ val,
                                                           const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ b,
                                                           const int* __restrict__ done) {
   pdl_wait();
   if (done && *done) return;
-  chan_wait(dist, wch);  // sharded solve: the halo values this kernel gathers have arrived (no-op otherwise)
   const int row = row_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (row >= n) return;
   double s = 0.0;
@@ -1167,41 +1164,35 @@ inline int vec_blocks(const Ctx& c, int n, bool reduces = false) {
 
 }  // namespace
 
-void launch_spmv(const Ctx& c, const DCsr& A, const double* x, double* y, int mode, const double* b, const int* done, const char* name, RowRange rr, Chan wch) {
-  if (mode == 0) spmv_dispatch<0, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr, wch);
-  else if (mode == 1) spmv_dispatch<1, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr, wch);
-  else if (mode == 2) spmv_dispatch<2, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr, wch);
-  else spmv_dispatch<3, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr, wch);
+void launch_spmv(const Ctx& c, const DCsr& A, const double* x, double* y, int mode, const double* b, const int* done, const char* name, RowRange rr) {
+  if (mode == 0) spmv_dispatch<0, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr);
+  else if (mode == 1) spmv_dispatch<1, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr);
+  else if (mode == 2) spmv_dispatch<2, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr);
+  else spmv_dispatch<3, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr);
 }
 
-void launch_spmv_sell(const Ctx& c, const Sell& A, const double* x, double* y, int mode, const double* b, const int* done, const char* name, RowRange rr, Chan wch) {
-  if (mode == 0) sell_dispatch<0, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr, wch);
-  else if (mode == 1) sell_dispatch<1, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr, wch);
-  else if (mode == 2) sell_dispatch<2, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr, wch);
-  else sell_dispatch<3, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr, wch);
+void launch_spmv_sell(const Ctx& c, const Sell& A, const double* x, double* y, int mode, const double* b, const int* done, const char* name, RowRange rr) {
+  if (mode == 0) sell_dispatch<0, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr);
+  else if (mode == 1) sell_dispatch<1, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr);
+  else if (mode == 2) sell_dispatch<2, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr);
+  else sell_dispatch<3, false>(c, A, x, y, b, nullptr, nullptr, done, name, rr);
 }
-void launch_spmv_dot_sell(const Ctx& c, const Sell& A, const double* x, double* y, double* partials, PcgScalars* sc, RowRange rr, Chan wch) {
-  sell_dispatch<0, true>(c, A, x, y, nullptr, partials, sc, &sc->done, "spmv_dot", rr, wch);
+void launch_spmv_dot_sell(const Ctx& c, const Sell& A, const double* x, double* y, double* partials, PcgScalars* sc, RowRange rr) {
+  sell_dispatch<0, true>(c, A, x, y, nullptr, partials, sc, &sc->done, "spmv_dot", rr);
 }
 
-void launch_halo_push(const Ctx& c, Chan sig, Chan wt, int total, const int* list, const int* list_ptr, const double* src, const PeerPtrs& dst, const int* done) {
+void launch_ll_exchange(const Ctx& c, const LLXchg& x, const double* src, double* dst, const int* done) {
   g_launch_counter++;
-  ProfScope ps(c, "halo_push");
-  int blocks = std::max(1, std::min(cdiv(total, 1024), c.num_sms));
-  FSB_LAUNCH((halo_push_kernel), blocks, 256, 0, c.stream, c.dist, sig, wt, total, list, list_ptr, src, dst, c.dist_ticket, done);
+  ProfScope ps(c, "exchange");
+  int blocks = std::max(1, std::min(cdiv(std::max(x.stotal, x.rtotal), 1024), c.num_sms));
+  FSB_LAUNCH((ll_exchange_kernel), blocks, 256, 0, c.stream, c.dist, x, src, dst, c.dist_ticket, done);
   FSB_CHECK_LAUNCH();
 }
-void launch_push_all(const Ctx& c, Chan sig, Chan wt, int begin, int end, const double* src, const PeerPtrs& dst, const int* done) {
+void launch_push_all(const Ctx& c, int begin, int end, const double* src, const PeerPtrs& dst) {
   g_launch_counter++;
   ProfScope ps(c, "push_all");
   int blocks = std::max(1, std::min(cdiv(end - begin, 512), c.num_sms * 2));
-  FSB_LAUNCH((push_all_kernel), blocks, 256, 0, c.stream, c.dist, sig, wt, begin, end, src, dst, c.dist_ticket, done);
-  FSB_CHECK_LAUNCH();
-}
-void launch_chan_wait(const Ctx& c, Chan ch, const int* done) {
-  g_launch_counter++;
-  ProfScope ps(c, "chan_wait");
-  FSB_LAUNCH((chan_wait_kernel), 1, 32, 0, c.stream, c.dist, ch, done);
+  FSB_LAUNCH((push_all_kernel), blocks, 256, 0, c.stream, c.dist, begin, end, src, dst, c.dist_ticket);
   FSB_CHECK_LAUNCH();
 }
 

@@ -11,12 +11,12 @@
 //   * residual rows its restriction rows reference,
 //   * restricted-residual entries of rows it owns on the next level ("down"), coarse corrections its
 //     prolongator rows reference ("up"),
-// is PUSHED into the peer's copy by plain stores through NVLink peer mappings (CUDA IPC) by a small
-// producer kernel that then publishes a per-channel epoch flag to exactly the peers it wrote to and
-// never waits; the consumer kernel waits in its prologue for exactly the peers it receives from
-// (cycle.cu: chan_signal / chan_wait).  Dot products are all-reduced inside the reduction kernels
-// (cycle.cu: cross_sum).  The levels below the sharded ones are small and are computed redundantly on
-// every GPU after an all-gather of the restricted residual — the coarse grid is agglomerated onto
+// is sent by ONE small kernel per exchange with a flag-in-data protocol (cycle.cu: ll_exchange_kernel; the idea of
+// NCCL's LL protocol): every value travels as a 16-byte {lo, epoch, hi, epoch} store into the receiver's buffer over
+// the NVLink peer mapping (CUDA IPC), the receiver polls its slots — no fence, no flag word, no barrier, and only
+// the GPUs that actually share a cut talk to each other.  Dot products are all-reduced the same way inside the
+// reduction kernels (cycle.cu: cross_sum).  The levels below the sharded ones are small and are computed
+// redundantly on every GPU after an all-gather of the restricted residual — the coarse grid is agglomerated onto
 // every GPU instead of onto one, so the way back up needs no communication.
 #include <algorithm>
 #include <climits>
@@ -73,21 +73,6 @@ __global__ void mark_needed_kernel(int nrows, const int* __restrict__ ptr, const
     if (j >= myb && j < mye) flags[(size_t)q * nown + (j - myb)] = 1;
   }
 }
-// the other direction: which peers own values that MY rows [r0, r1) reference -> bit mask
-__global__ void mark_sources_kernel(int r0, int r1, const int* __restrict__ ptr, const int* __restrict__ col, const int* __restrict__ colmap,
-                                    Ranges colOwner, int me, unsigned* __restrict__ mask) {
-  int i = r0 + blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= r1) return;
-  unsigned m = 0;
-  const int e0 = ptr ? ptr[i] : i, e1 = ptr ? ptr[i + 1] : i + 1;
-  for (int e = e0; e < e1; e++) {
-    int j = col[e];
-    if (colmap) j = colmap[j];
-    int q = owner_of(colOwner, j);
-    if (q != me) m |= 1u << q;
-  }
-  if (m) atomicOr(mask, m);
-}
 __global__ void fill_list_kernel(long long total, int nown, int myb, const int* __restrict__ flags, const int* __restrict__ pos,
                                  const int* __restrict__ valmap, int* __restrict__ list) {
   long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -95,6 +80,24 @@ __global__ void fill_list_kernel(long long total, int nown, int myb, const int* 
     const int j = myb + (int)(k % nown);
     list[pos[k] - 1] = valmap ? valmap[j] : j;
   }
+}
+
+// what MY consumer rows [r0, r1) need from the others: flags over the (mapped) column space
+__global__ void mark_needs_kernel(int r0, int r1, const int* __restrict__ ptr, const int* __restrict__ col, const int* __restrict__ colmap,
+                                  int myb, int mye, int* __restrict__ flags) {
+  int i = r0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= r1) return;
+  const int e0 = ptr ? ptr[i] : i, e1 = ptr ? ptr[i + 1] : i + 1;
+  for (int e = e0; e < e1; e++) {
+    int j = col[e];
+    if (colmap) j = colmap[j];
+    if (j < myb || j >= mye) flags[j] = 1;
+  }
+}
+__global__ void fill_needs_kernel(int ncols, const int* __restrict__ flags, const int* __restrict__ pos, const int* __restrict__ valmap,
+                                  int* __restrict__ list) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < ncols && flags[j]) list[pos[j] - 1] = valmap ? valmap[j] : j;
 }
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -105,7 +108,7 @@ void build_push_list(const Ctx& c, int nranks, int me, int nrows, const int* ptr
                      const Ranges& colOwner, int myb, int mye, const int* valmap, Solver::PushList& out) {
   cudaStream_t s = c.stream;
   const int nown = std::max(mye - myb, 0);
-  out.total = 0; out.dst_mask = 0; out.src_mask = 0;
+  out.total = 0;
   std::vector<int> ptr_h(nranks + 1, 0);
   if (nown > 0 && nrows > 0) {
     const size_t m = (size_t)nranks * nown;
@@ -121,16 +124,50 @@ void build_push_list(const Ctx& c, int nranks, int me, int nrows, const int* ptr
   } else {
     out.idx.alloc(1, s);
   }
-  for (int q = 0; q < nranks; q++) if (ptr_h[q + 1] > ptr_h[q]) out.dst_mask |= 1u << q;
   out.ptr.alloc(nranks + 1, s);
   out.ptr.from_host(ptr_h.data(), nranks + 1);
-  // who sends to me: the owners of the values my own consumer rows reference
+  // what the peers send me: the values my own consumer rows reference, ascending in the owner's numbering (the
+  // order in which the owner's list sends them), grouped by owner
   const int r0 = rowOwner.b[me], r1 = rowOwner.b[me + 1];
-  DevBuf<unsigned> mask(1, s);
-  mask.zero();
-  if (r1 > r0) mark_sources_kernel<<<cdiv(r1 - r0, 256), 256, 0, s>>>(r0, r1, ptr, col, colmap, colOwner, me, mask);
-  FSB_CHECK_LAUNCH();
-  out.src_mask = mask.read(0);
+  const int ncols = colOwner.b[nranks];
+  out.rtotal = 0;
+  for (int q = 0; q <= nranks; q++) out.rptr[q] = 0;
+  if (r1 > r0 && ncols > 0) {
+    IBuf flags(ncols, s), pos(ncols, s);
+    flags.zero();
+    mark_needs_kernel<<<cdiv(r1 - r0, 256), 256, 0, s>>>(r0, r1, ptr, col, colmap, myb, mye, flags);
+    inclusive_scan_i32(flags, pos, ncols, s);
+    for (int q = 1; q <= nranks; q++) out.rptr[q] = colOwner.b[q] > 0 ? pos.read((size_t)colOwner.b[q] - 1) : 0;
+    out.rtotal = out.rptr[nranks];
+    out.ridx.alloc(std::max(1, out.rtotal), s);
+    fill_needs_kernel<<<cdiv(ncols, 256), 256, 0, s>>>(ncols, flags, pos, valmap, out.ridx);
+    FSB_CHECK_LAUNCH();
+    FSB_CUDA(cudaStreamSynchronize(s));
+  } else {
+    out.ridx.alloc(1, s);
+  }
+}
+
+// all-gather as an exchange: my slice [b[me], b[me+1]) of a vector goes to every peer, theirs come to me
+void build_allgather_list(const Ctx& c, int nranks, int me, const int* b, Solver::PushList& out) {
+  cudaStream_t s = c.stream;
+  const int mine = b[me + 1] - b[me];
+  std::vector<int> idx, ptr(nranks + 1, 0), ridx;
+  for (int q = 0; q < nranks; q++) {
+    if (q != me) for (int j = b[me]; j < b[me + 1]; j++) idx.push_back(j);
+    ptr[q + 1] = (int)idx.size();
+  }
+  out.rptr[0] = 0;
+  for (int q = 0; q < nranks; q++) {
+    if (q != me) for (int j = b[q]; j < b[q + 1]; j++) ridx.push_back(j);
+    out.rptr[q + 1] = (int)ridx.size();
+  }
+  (void)mine;
+  out.total = (int)idx.size(); out.rtotal = (int)ridx.size();
+  out.idx.alloc(std::max<size_t>(1, idx.size()), s); out.ridx.alloc(std::max<size_t>(1, ridx.size()), s); out.ptr.alloc(nranks + 1, s);
+  if (!idx.empty()) out.idx.from_host(idx.data(), idx.size());
+  if (!ridx.empty()) out.ridx.from_host(ridx.data(), ridx.size());
+  out.ptr.from_host(ptr.data(), nranks + 1);
   FSB_CUDA(cudaStreamSynchronize(s));
 }
 
@@ -239,7 +276,10 @@ void Solver::dist_prepare(int rank, int nranks) {
     build_push_list(ctx, nranks, rank, L.n, L.A.ptr, L.A.col, nullptr, rows, rows, myb, mye, nullptr, D.sendA);
     // my rows that a peer's restriction rows reference (rows of R = next level's external numbering)
     build_push_list(ctx, nranks, rank, L.nnout, L.R.ptr, L.R.col, nullptr, aggs, rows, myb, mye, nullptr, D.sendR);
-    if (l + 1 < nshard) {
+    if (l + 1 >= nshard) {
+      // the next level is replicated: its right-hand side is all-gathered
+      build_allgather_list(ctx, nranks, rank, D.abeg, D.sendDown);
+    } else {
       LevelData& Ln = levels[l + 1];
       DistLevel& Dn = dist.lev[l + 1];
       const Ranges rowsN = make_ranges(Dn.rbeg, nranks);
@@ -265,10 +305,27 @@ void Solver::dist_prepare(int rank, int nranks) {
       dist.user_lo = r[0]; dist.user_hi = r[1] + 1;
     } else { dist.user_lo = r0; dist.user_hi = r1; }
   }
-  // 4. arena (identical layout on every rank): flag table | reduction slots | p | cg_x | per sharded level x, r, bc, xc
+  // 4. channels: one receive buffer per exchange site
+  {
+    for (int c = 0; c < kMaxChan; c++) dist.chan[c] = Channel();
+    dist.chan[kChanP].list = &dist.lev[0].sendA;
+    dist.chan[kChanX0].list = &dist.lev[0].sendA;
+    for (int l = 0; l < nshard; l++) {
+      DistLevel& D = dist.lev[l];
+      const int c0 = kChanLevel0 + kChanPerLevel * l;
+      dist.chan[c0 + kXPre].list = &D.sendA;
+      dist.chan[c0 + kRes].list = &D.sendR;
+      dist.chan[c0 + kDown].list = &D.sendDown;
+      if (l + 1 < nshard) dist.chan[c0 + kUp].list = &D.sendUp;
+      dist.chan[c0 + kXPost].list = &D.sendA;
+    }
+    dist.nchan = kChanLevel0 + kChanPerLevel * nshard;
+  }
+  // 5. arena: flags | all-reduce slots | p | cg_x | per sharded level x, r, bc, xc | receive buffers.  The offsets of the
+  // receive buffers differ from rank to rank (they depend on what a rank receives) and travel in the blob.
   size_t off = 0;
-  dist.off_flags = off; off = align_up(off + (size_t)(1 + kMaxChan) * kMaxRanks * sizeof(unsigned long long), 256);
-  dist.off_red = off; off = align_up(off + 2 * kMaxRanks * sizeof(double), 256);
+  dist.off_flags = off; off = align_up(off + (size_t)kMaxRanks * sizeof(unsigned long long), 256);
+  dist.off_red = off; off = align_up(off + 2 * kMaxRanks * sizeof(uint4), 256);
   const int n = levels[0].n;
   dist.off_p = off; off = align_up(off + (size_t)n * 8, 256);
   dist.off_cgx = off; off = align_up(off + (size_t)n * 8, 256);
@@ -279,6 +336,11 @@ void Solver::dist_prepare(int rank, int nranks) {
     D.off_r = off; off = align_up(off + nl * 8, 256);
     D.off_bc = off; off = align_up(off + nc * 8, 256);
     D.off_xc = off; off = align_up(off + nc * 8, 256);
+  }
+  for (int c = 0; c < dist.nchan; c++) {
+    Channel& ch = dist.chan[c];
+    if (!ch.list) continue;
+    ch.buf_off = off; off = align_up(off + (size_t)std::max(ch.list->rtotal, 1) * sizeof(uint4), 256);
   }
   dist.arena_bytes = off;
   FSB_CUDA(cudaMalloc((void**)&dist.arena, dist.arena_bytes));
@@ -293,42 +355,77 @@ void Solver::dist_prepare(int rank, int nranks) {
     L.bc.view(reinterpret_cast<double*>(dist.arena + D.off_bc), L.nnout, s);
     L.xc.view(reinterpret_cast<double*>(dist.arena + D.off_xc), L.nnout, s);
   }
-  dist.epoch.alloc(1 + kMaxChan, s); dist.epoch.zero();
+  dist.epoch.alloc(2, s); dist.epoch.zero();
+  dist.xchg.alloc(1, s); dist.xchg.zero();
   dist.error.alloc(1, s); dist.error.zero();
   dist.ticket.alloc(1, s); dist.ticket.zero();
   FSB_CUDA(cudaStreamSynchronize(s));
 }
 
-void Solver::dist_get_handle(void* handle64, long long* bytes) {
-  if (!dist.arena) throw std::runtime_error("dist_get_handle before dist_prepare");
+void Solver::dist_get_blob(void* blob, long long* bytes) {
+  if (!dist.arena) throw std::runtime_error("dist_get_blob before dist_prepare");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  std::vector<unsigned char> raw(kDistBlobBytes, 0);
+  DistBlob* b = reinterpret_cast<DistBlob*>(raw.data());
   cudaIpcMemHandle_t h;
   FSB_CUDA(cudaIpcGetMemHandle(&h, dist.arena));
-  memcpy(handle64, &h, 64);
+  memcpy(b->handle, &h, 64);
+  b->nchan = dist.nchan; b->nranks = dist.nranks;
+  for (int c = 0; c < dist.nchan; c++) {
+    const Channel& ch = dist.chan[c];
+    b->buf_off[c] = ch.buf_off;
+    for (int q = 0; q <= kMaxRanks; q++) b->rptr[c][q] = ch.list ? ch.list->rptr[std::min(q, dist.nranks)] : 0;
+  }
+  memcpy(blob, raw.data(), kDistBlobBytes);
   if (bytes) *bytes = (long long)dist.arena_bytes;
 }
 
-void Solver::dist_connect(const void* handles) {
+void Solver::dist_connect(const void* blobs) {
   if (!dist.arena) throw std::runtime_error("dist_connect before dist_prepare");
   FSB_CUDA(cudaSetDevice(ctx.device));
-  const char* hb = static_cast<const char*>(handles);
+  const char* hb = static_cast<const char*>(blobs);
+  std::vector<DistBlob> B(dist.nranks);
+  for (int q = 0; q < dist.nranks; q++) memcpy(&B[q], hb + (size_t)kDistBlobBytes * q, sizeof(DistBlob));
+  for (int q = 0; q < dist.nranks; q++)
+    if (B[q].nchan != dist.nchan || B[q].nranks != dist.nranks) throw std::runtime_error("sharded solve: the ranks disagree on the exchange plan (setup must be replicated)");
   for (int q = 0; q < dist.nranks; q++) {
     if (q == dist.rank) { dist.peer[q] = dist.arena; continue; }
     cudaIpcMemHandle_t h;
-    memcpy(&h, hb + 64 * q, 64);
+    memcpy(&h, B[q].handle, 64);
     void* p = nullptr;
     FSB_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
     dist.peer[q] = static_cast<char*>(p);
   }
+  // exchange descriptors: my segment inside peer q's receive buffer of channel c starts at slot rptr_q[c][me]; what q
+  // expects from me must be exactly what my list sends (both sides derived it from the replicated hierarchy)
+  for (int c = 0; c < dist.nchan; c++) {
+    Channel& ch = dist.chan[c];
+    if (!ch.list) continue;
+    const PushList& pl = *ch.list;
+    std::vector<int> sptr = pl.ptr.to_vector();
+    LLXchg x;
+    x.sidx = pl.idx.get(); x.sptr = pl.ptr.get(); x.stotal = pl.total;
+    x.ridx = pl.ridx.get(); x.rtotal = pl.rtotal;
+    x.mybuf = reinterpret_cast<uint4*>(dist.arena + ch.buf_off);
+    for (int q = 0; q < dist.nranks; q++) {
+      const int expect = B[q].rptr[c][dist.rank + 1] - B[q].rptr[c][dist.rank], mine = sptr[q + 1] - sptr[q];
+      if (q != dist.rank && expect != mine)
+        throw std::runtime_error("sharded solve: channel " + std::to_string(c) + ": rank " + std::to_string(q) + " expects " + std::to_string(expect) +
+                                 " values from rank " + std::to_string(dist.rank) + ", which sends " + std::to_string(mine));
+      x.peerbuf[q] = reinterpret_cast<uint4*>(dist.peer[q] + B[q].buf_off[c]) + B[q].rptr[c][dist.rank];
+    }
+    ch.dev = x;
+  }
   DistDev d;
   d.rank = dist.rank; d.nranks = dist.nranks;
   d.my_flags = reinterpret_cast<unsigned long long*>(dist.arena + dist.off_flags);
-  d.my_red = reinterpret_cast<double*>(dist.arena + dist.off_red);
+  d.my_red = reinterpret_cast<uint4*>(dist.arena + dist.off_red);
   for (int q = 0; q < dist.nranks; q++) {
     d.peer_flags[q] = reinterpret_cast<unsigned long long*>(dist.peer[q] + dist.off_flags);
-    d.peer_red[q] = reinterpret_cast<double*>(dist.peer[q] + dist.off_red);
+    d.peer_red[q] = reinterpret_cast<uint4*>(dist.peer[q] + dist.off_red);
   }
   d.epoch = dist.epoch.get();
+  d.xchg = dist.xchg.get();
   d.error = dist.error.get();
   ctx.dist = d;
   ctx.dist_ticket = dist.ticket.get();

@@ -6,18 +6,15 @@ namespace fsb {
 
 // y = A x (mode 0), y = b - A x (1), y += A x (2), y -= A x (3); CSR-stream kernel. `name` tags the profile.
 void launch_spmv(const Ctx& c, const DCsr& A, const double* x, double* y, int mode, const double* b, const int* done, const char* name,
-                 RowRange rr = RowRange(), Chan wch = Chan());
+                 RowRange rr = RowRange());
 // same operation on the SELL-32 copy of an operator (thread per row, coalesced, no staging)
 void launch_spmv_sell(const Ctx& c, const Sell& A, const double* x, double* y, int mode, const double* b, const int* done, const char* name,
-                      RowRange rr = RowRange(), Chan wch = Chan());
-void launch_spmv_dot_sell(const Ctx& c, const Sell& A, const double* x, double* y, double* partials, PcgScalars* sc, RowRange rr = RowRange(),
-                          Chan wch = Chan());
-// multi-GPU exchanges over NVLink peer memory: the kernel stores into the peers' copies, its last CTA publishes
-// the channel epoch to the peers it wrote to (sig) and waits for the peers this GPU receives from (wt; id < 0:
-// no wait here — the consumer kernel waits itself through its `wch` hook, or launch_chan_wait does)
-void launch_halo_push(const Ctx& c, Chan sig, Chan wt, int total, const int* list, const int* list_ptr, const double* src, const PeerPtrs& dst, const int* done);
-void launch_push_all(const Ctx& c, Chan sig, Chan wt, int begin, int end, const double* src, const PeerPtrs& dst, const int* done);
-void launch_chan_wait(const Ctx& c, Chan ch, const int* done);
+                      RowRange rr = RowRange());
+void launch_spmv_dot_sell(const Ctx& c, const Sell& A, const double* x, double* y, double* partials, PcgScalars* sc, RowRange rr = RowRange());
+// multi-GPU exchanges over NVLink peer memory (cycle.cu): flag-in-data exchange of list entries of `src` (mine) into `dst`
+// (what the peers send me); fenced all-gather of a slice (end of a solve)
+void launch_ll_exchange(const Ctx& c, const LLXchg& x, const double* src, double* dst, const int* done);
+void launch_push_all(const Ctx& c, int begin, int end, const double* src, const PeerPtrs& dst);
 // y = A x and the dot product x.y folded into the same pass; the last CTA finishes
 // py and alpha = rz_old / py in device memory.
 void launch_spmv_dot(const Ctx& c, const DCsr& A, const double* x, double* y, double* partials, PcgScalars* sc);

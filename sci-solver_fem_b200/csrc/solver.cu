@@ -285,14 +285,9 @@ void Solver::setup() {
 // One V-cycle on level `lev`.  b_src is read through `gather` (external -> internal numbering,
 // null when b_src is already internal); the result goes to x_dst in internal numbering
 // (scatter == null) or is scattered to the external numbering through `scatter`.
-// one exchange of a sharded solve: my list entries of `v` into the peers' copies (arena offset `off`), signal, wait
-void Solver::exchange_chan(int chan, const PushList& pl, const double* v, size_t off, const int* done) {
-  Chan sig, wt;
-  sig.id = wt.id = chan; sig.mask = pl.dst_mask; wt.mask = pl.src_mask;
-  launch_halo_push(ctx, sig, wt, pl.total, pl.idx, pl.ptr, v, peers_at(off), done);
-}
-void Solver::exchange(int lev, int which, const PushList& pl, const double* v, size_t off, const int* done) {
-  exchange_chan(kChanLevel0 + kChanPerLevel * lev + which, pl, v, off, done);
+// one exchange of a sharded solve: my list entries of `src` to the peers, theirs into `dst` (cycle.cu: ll_exchange_kernel)
+void Solver::exchange_chan(int chan, const double* src, double* dst, const int* done) {
+  launch_ll_exchange(ctx, dist.chan[chan].dev, src, dst, done);
 }
 
 void Solver::vcycle(int lev, const double* b_src, const int* gather, double* x_dst, const int* scatter, double* /*unused*/) {
@@ -327,33 +322,29 @@ void Solver::vcycle(int lev, const double* b_src, const int* gather, double* x_d
     // pre: x = w b/d, nu1 sweeps, r = b - A_in x - d x  (one kernel, matrix slab read once)
     launch_smooth(ctx, L, b_src, gather, gather ? L.b.get() : nullptr, nullptr, w, prm.preInnerIters, L.x, nullptr, nullptr, L.r, done, D);
     // x across the cut (every exchange: push + signal to the peers written to + wait for the peers received from)
-    if (D) exchange(lev, kXPre, DL->sendA, L.x, DL->off_x, done);
+    if (D) exchange(lev, kXPre, L.x, L.x, done);
     if (L.sAout.ready()) launch_spmv_sell(ctx, L.sAout, L.x, L.r, 3, nullptr, done, "residual_out", rr);
     else launch_spmv(ctx, L.Aout, L.x, L.r, 3, nullptr, done, "residual_out", rr);   // r -= A_out x   (preAout_kernel)
-    if (D) exchange(lev, kRes, DL->sendR, L.r, DL->off_r, done);                     // r rows the peers restrict
+    if (D) exchange(lev, kRes, L.r, L.r, done);                                      // r rows the peers restrict
     launch_spmv(ctx, L.R, L.r, L.bc, 0, nullptr, done, "restrict", rrc);            // bc = R r
   }
   if (D) {
     // restricted residual: to the owners of the next level's rows, or — next level replicated — all-gathered
-    if (Dn) exchange(lev, kDown, DL->sendDown, L.bc, DL->off_bc, done);
-    else {
-      Chan ch; ch.id = kChanLevel0 + kChanPerLevel * lev + kDown; ch.mask = (1u << dist.nranks) - 1u;
-      launch_push_all(ctx, ch, ch, rrc.begin, rrc.end, L.bc, peers_at(DL->off_bc), done);
-    }
+    exchange(lev, kDown, L.bc, L.bc, done);
   }
   const bool next_is_coarsest = (lev + 1 == (int)levels.size() - 1);
   const int* ip = next_is_coarsest ? nullptr : levels[lev + 1].agg.ipermutation.get();
   vcycle(lev + 1, L.bc, ip, L.xc, ip, nullptr);
   profiler.cur_level = lev;
   // coarse corrections of the next level's rows I own that the peers' prolongator rows reference
-  if (Dn) exchange(lev, kUp, DL->sendUp, L.xc, DL->off_xc, done);
+  if (Dn) exchange(lev, kUp, L.xc, L.xc, done);
   if (L.sP.ready()) launch_spmv_sell(ctx, L.sP, L.xc, L.x, 2, nullptr, done, "prolong_add", rr);
   else launch_spmv(ctx, L.P, L.xc, L.x, 2, nullptr, done, "prolong_add", rr);      // x += P xc
   double* xin = L.x;
   double* xtmp = L.x2;
   for (int rel = 0; rel < prm.postRelaxes; rel++) {
     bool lastpass = (rel == prm.postRelaxes - 1);
-    if (D) exchange(lev, kXPost, DL->sendA, xin, DL->off_x, done);
+    if (D) exchange(lev, kXPost, xin, xin, done);
     if (L.sAout.ready()) launch_spmv_sell(ctx, L.sAout, xin, L.r, 1, b_eff, done, "bprime", rr);
     else launch_spmv(ctx, L.Aout, xin, L.r, 1, b_eff, done, "bprime", rr);         // b' = b - A_out x (x frozen for this pass)
     if (lastpass) launch_smooth(ctx, L, L.r, nullptr, nullptr, xin, w, prm.postInnerIters, scatter ? nullptr : x_dst, scatter, scatter ? x_dst : nullptr, nullptr, done, D);
@@ -403,7 +394,7 @@ void Solver::enqueue_pcg_iteration() {
   vcycle(0, cg_r, nullptr, cg_z, nullptr, nullptr);                          // z = M^-1 r
   launch_dot(ctx, nown, cg_r.get() + rb, cg_z.get() + rb, partials, sc, 2);  // rz_new, beta
   launch_cg_pdir(ctx, nown, cg_p.get() + rb, cg_z.get() + rb, sc, 0);        // p = z + beta p
-  if (D) exchange_chan(kChanP, dist.lev[0].sendA, cg_p, dist.off_p, &sc->done);  // p across the cut for the next SpMV
+  if (D) exchange_chan(kChanP, cg_p, cg_p, &sc->done);  // p across the cut for the next SpMV
 }
 
 void Solver::pcg(const double* b_user, double* x_user) {
@@ -448,13 +439,13 @@ void Solver::pcg(const double* b_user, double* x_user) {
   RowRange rr;
   if (D) {
     rr.begin = rb; rr.end = re;
-    exchange_chan(kChanX0, dist.lev[0].sendA, cg_x, dist.off_cgx, nullptr);  // initial guess across the cut
+    exchange_chan(kChanX0, cg_x, cg_x, nullptr);  // initial guess across the cut
   }
   if (L0.sA.ready()) launch_spmv_sell(ctx, L0.sA, cg_x, cg_r, 1, cg_b, nullptr, "residual", rr);
   else launch_spmv(ctx, L0.A, cg_x, cg_r, 1, cg_b, nullptr, "residual"); // r = b - A x
   vcycle(0, cg_r, nullptr, cg_z, nullptr, nullptr);                // z = M^-1 r
   launch_cg_pdir(ctx, nown, cg_p.get() + rb, cg_z.get() + rb, sc, 1);  // p = z
-  if (D) exchange_chan(kChanP, dist.lev[0].sendA, cg_p, dist.off_p, nullptr);
+  if (D) exchange_chan(kChanP, cg_p, cg_p, nullptr);
   launch_dot(ctx, nown, cg_r.get() + rb, cg_z.get() + rb, partials, sc, 1);  // rz_old
   FSB_CUDA(cudaStreamSynchronize(s));
 
@@ -506,8 +497,7 @@ void Solver::pcg(const double* b_user, double* x_user) {
   if (D) {
     if (h.err || dist.error.read(0)) throw std::runtime_error("sharded solve: a peer did not arrive at an exchange (timeout)");
     // every GPU ends up with the full solution
-    Chan ch; ch.id = kChanXAll; ch.mask = (1u << dist.nranks) - 1u;
-    launch_push_all(ctx, ch, ch, rb, re, cg_x, peers_at(dist.off_cgx), nullptr);
+    launch_push_all(ctx, rb, re, cg_x, peers_at(dist.off_cgx));
     if (dist.error.read(0)) throw std::runtime_error("sharded solve: a peer did not arrive at the final exchange (timeout)");
   }
   if (permute) launch_scatter(ctx, n, L0.agg.ipermutation, cg_x, x_user);

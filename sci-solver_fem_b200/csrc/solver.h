@@ -123,18 +123,20 @@ class Solver {
   // (contiguous, nnz-balanced ranges), builds the push lists of every exchange and allocates the IPC arena.
   // dist_connect(): maps the peers' arenas.  Then solve() (PCG) runs sharded.
   void dist_prepare(int rank, int nranks);
-  void dist_get_handle(void* handle64, long long* bytes);
-  void dist_connect(const void* handles /* nranks x 64 bytes */);
+  void dist_get_blob(void* blob /* kDistBlobBytes */, long long* arena_bytes);
+  void dist_connect(const void* blobs /* nranks x kDistBlobBytes, rank order */);
   void dist_disconnect();
-  // values of my rows that peers need, grouped by destination peer (same index in the peer's copy of the vector)
+  // one exchange pattern: the values of mine that peers need, grouped by destination peer, and the places where
+  // the values the peers send me go (same index in every GPU's copy of the exchanged vector)
   struct PushList {
-    IBuf idx, ptr;               // entries / nranks+1 segment offsets
+    IBuf idx, ptr;               // send entries / nranks+1 segment offsets
     int total = 0;
-    unsigned dst_mask = 0;       // peers with a non-empty segment
-    unsigned src_mask = 0;       // peers whose lists send to me
+    IBuf ridx;                   // receive entries, grouped by source peer (ascending index inside a segment — the order
+    int rptr[kMaxRanks + 1] = {};  //   in which that peer's list sends them)
+    int rtotal = 0;
   };
-  // channel ids: 0 p halo, 1 x0 halo (initial residual), 2 final all-gather of x, then 5 per sharded level
-  enum { kChanP = 0, kChanX0 = 1, kChanXAll = 2, kChanLevel0 = 3, kChanPerLevel = 5 };
+  // channel ids: 0 p halo, 1 x0 halo (initial residual), then 5 per sharded level
+  enum { kChanP = 0, kChanX0 = 1, kChanLevel0 = 2, kChanPerLevel = 5 };
   enum { kXPre = 0, kRes = 1, kDown = 2, kUp = 3, kXPost = 4 };
   struct DistLevel {
     int pbeg[kMaxRanks + 1] = {};  // partition ranges
@@ -142,27 +144,46 @@ class Solver {
     int abeg[kMaxRanks + 1] = {};  // row ranges of the next level in ITS external numbering = aggregates of the owned partitions
     PushList sendA;                // operator columns across the cut (x after pre-smoothing / after the coarse correction, p, x0)
     PushList sendR;                // residual rows the peers' restriction rows reference
-    PushList sendDown;             // restricted residual entries a peer owns on the next (sharded) level
+    PushList sendDown;             // restricted residual: entries a peer owns on the next (sharded) level, or — next level
+                                   //   replicated — my whole slice to everybody (all-gather)
     PushList sendUp;               // coarse corrections of my next-level rows that a peer's prolongator rows reference
     size_t off_x = 0, off_r = 0, off_bc = 0, off_xc = 0;
+  };
+  struct Channel {                 // receive buffer of one exchange site + where my segments start in the peers' buffers
+    const PushList* list = nullptr;
+    size_t buf_off = 0;            // my receive buffer (arena offset, rtotal slots of 16 B)
+    LLXchg dev;                    // filled by dist_connect
   };
   struct DistHost {
     int rank = 0, nranks = 1;
     bool connected = false;
     int nshard = 0;                // levels 0 .. nshard-1 are sharded, the rest is computed redundantly on every GPU
     std::vector<DistLevel> lev;
+    Channel chan[kMaxChan];
+    int nchan = 0;
     int user_lo = 0, user_hi = 0;  // user-numbering range that covers this GPU's fine rows (host-buffer solves copy only this slice)
     char* arena = nullptr;
     size_t arena_bytes = 0;
     size_t off_flags = 0, off_red = 0, off_p = 0, off_cgx = 0;
     char* peer[kMaxRanks] = {};
     DevBuf<unsigned long long> epoch;
+    DevBuf<unsigned> xchg;
     IBuf error;
     DevBuf<unsigned int> ticket;
   } dist;
+  // what every rank publishes before dist_connect (all-gathered by the caller): the IPC handle of its arena and, per
+  // channel, the offset of its receive buffer and the segment offsets of the source peers inside it
+  struct DistBlob {
+    unsigned char handle[64];
+    int nchan, nranks;
+    unsigned long long buf_off[kMaxChan];
+    int rptr[kMaxChan][kMaxRanks + 1];
+  };
+  static constexpr int kDistBlobBytes = 2560;
+  static_assert(sizeof(DistBlob) <= kDistBlobBytes, "blob size");
   bool sharded(int lev) const { return dist.connected && dist.nranks > 1 && cg_active_ && lev < dist.nshard; }
-  void exchange_chan(int chan, const PushList& pl, const double* v, size_t off, const int* done);
-  void exchange(int lev, int which, const PushList& pl, const double* v, size_t off, const int* done);
+  void exchange_chan(int chan, const double* src, double* dst, const int* done);
+  void exchange(int lev, int which, const double* src, double* dst, const int* done) { exchange_chan(kChanLevel0 + kChanPerLevel * lev + which, src, dst, done); }
   PeerPtrs peers_at(size_t off) const { PeerPtrs p = {}; for (int q = 0; q < dist.nranks; q++) p.p[q] = reinterpret_cast<double*>(dist.peer[q] + off); return p; }
   std::string profile_report();        // "name level launches total_ms" lines of the last profiled solve
   Profiler profiler;

@@ -57,7 +57,7 @@ def load_library():
         "fsb_spmv_fine_device": (ci, [vp, vp, vp]), "fsb_apply_matrix_device": (ci, [vp, vp, vp]), "fsb_apply_matrix": (ci, [vp, vp, vp]), "fsb_precondition_device": (ci, [vp, vp, vp]),
         "fsb_time_ms": (cd, [vp, cs]), "fsb_last_launches": (cll, [vp]), "fsb_stream": (vp, [vp]),
         "fsb_profile_report": (ci, [vp, vp, ci]),
-        "fsb_dist_prepare": (ci, [vp, ci, ci]), "fsb_dist_handle": (ci, [vp, vp, C.POINTER(cll)]),
+        "fsb_dist_prepare": (ci, [vp, ci, ci]), "fsb_dist_blob": (ci, [vp, vp, C.POINTER(cll)]), "fsb_dist_blob_bytes": (ci, []),
         "fsb_dist_connect": (ci, [vp, vp]), "fsb_dist_disconnect": (ci, [vp]), "fsb_dist_ranges": (ci, [vp, vp, vp, vp]),
         "fsb_dist_level_ranges": (ci, [vp, ci, vp, vp, vp]), "fsb_dist_info": (ci, [vp, vp, vp, vp, vp]),
         "fsb_split_by_weight": (None, [ci, vp, ci, vp]),
@@ -77,7 +77,7 @@ EXPORTED_SYMBOLS = (
     "fsb_get_matrix_csr fsb_set_matrix_values fsb_set_matrix_csr fsb_setup fsb_num_levels fsb_level_rows fsb_level_nnz "
     "fsb_level_int fsb_level_val fsb_solve fsb_solve_device fsb_solve_fem fsb_resid_history fsb_spmv_fine_device "
     "fsb_precondition_device fsb_time_ms fsb_last_launches fsb_stream fsb_tet_mass_integrals fsb_tri_quadrature "
-    "fsb_profile_report fsb_dist_prepare fsb_dist_handle fsb_dist_connect fsb_dist_disconnect fsb_dist_ranges fsb_dist_level_ranges fsb_dist_info "
+    "fsb_profile_report fsb_dist_prepare fsb_dist_blob fsb_dist_blob_bytes fsb_dist_connect fsb_dist_disconnect fsb_dist_ranges fsb_dist_level_ranges fsb_dist_info "
     "fsb_split_by_weight fsb_apply_matrix_device fsb_apply_matrix").split()
 
 
@@ -99,10 +99,10 @@ def exchange_handles_torch(payload: bytes, group=None):
     import torch.distributed as dist
     world = dist.get_world_size(group)
     dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
-    mine = torch.tensor(list(payload), dtype=torch.uint8, device=dev)
+    mine = torch.frombuffer(bytearray(payload), dtype=torch.uint8).to(dev)
     outs = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(outs, mine, group=group)
-    return [bytes(o.cpu().tolist()) for o in outs]
+    return [o.cpu().numpy().tobytes() for o in outs]
 
 
 _FIELDS = {  # reference field -> (C-ABI parameter, default)   FEMSolver.cu:11-34
@@ -325,18 +325,19 @@ class FEMSolver:
 
     # ------------------------------------------------------------------ stage 4: sharded solve
     def dist_connect(self, rank: int, world: int, allgather):
-        """Switches the PCG solve to the sharded mode.  `allgather(bytes) -> list[bytes]` exchanges the
-        64-byte IPC handles in rank order (see exchange_handles_torch)."""
+        """Switches the PCG solve to the sharded mode.  `allgather(bytes) -> list[bytes]` exchanges the ranks'
+        connection records (IPC handle + receive-buffer layout) in rank order (see exchange_handles_torch)."""
         self._check(self._L.fsb_dist_prepare(self._h, int(rank), int(world)))
         if world == 1:
             return
-        buf = C.create_string_buffer(64)
+        nb = self._L.fsb_dist_blob_bytes()
+        buf = C.create_string_buffer(nb)
         nbytes = C.c_longlong(0)
-        self._check(self._L.fsb_dist_handle(self._h, buf, C.byref(nbytes)))
-        handles = allgather(buf.raw)
-        assert len(handles) == world and all(len(h) == 64 for h in handles)
-        assert handles[rank] == buf.raw, "all-gather returned the handles in the wrong order"
-        self._check(self._L.fsb_dist_connect(self._h, C.create_string_buffer(b"".join(handles), 64 * world)))
+        self._check(self._L.fsb_dist_blob(self._h, buf, C.byref(nbytes)))
+        blobs = allgather(buf.raw)
+        assert len(blobs) == world and all(len(h) == nb for h in blobs)
+        assert blobs[rank] == buf.raw, "all-gather returned the records in the wrong order"
+        self._check(self._L.fsb_dist_connect(self._h, C.create_string_buffer(b"".join(blobs), nb * world)))
 
     def dist_disconnect(self):
         self._check(self._L.fsb_dist_disconnect(self._h))

@@ -22,7 +22,12 @@ def launch(nproc, args, timeout, env=None):
            "--master-port", str(free_port()), WORKER] + args
     e = dict(os.environ)
     e.update(env or {})
-    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT, env=e)
+    for attempt in range(3):  # the probed port can be taken again before torchrun binds it: retry with a new one
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT, env=e)
+        if r.returncode == 0 or "EADDRINUSE" not in r.stderr:
+            return r
+        cmd[cmd.index("--master-port") + 1] = str(free_port())
+    return r
 
 
 def test_host_plumbing_gloo_world2():
