@@ -100,14 +100,14 @@ __device__ __forceinline__ double ll_load(const DistDev& d, const uint4* p, unsi
 // contribution cannot overwrite a slot a slow GPU has not read yet.
 __device__ __forceinline__ double cross_sum(const DistDev& d, double local) {
   if (d.nranks == 1) return local;  // uniform
-  __shared__ double s_part[kMaxRanks];
+  __shared__ double s_part[kMaxRanks], s_val;
   __shared__ unsigned long long s_ep;
-  if (threadIdx.x == 0) s_ep = ++d.epoch[0];
+  if (threadIdx.x == 0) { s_val = local; s_ep = ++d.epoch[0]; }  // the partial is valid in thread 0 only
   __syncthreads();
   const unsigned ep = (unsigned)s_ep;
   const int par = (int)(s_ep & 1ull) * kMaxRanks;
   if (threadIdx.x < d.nranks) {
-    ll_store(d.peer_red[threadIdx.x] + par + d.rank, local, ep);
+    ll_store(d.peer_red[threadIdx.x] + par + d.rank, s_val, ep);
     s_part[threadIdx.x] = ll_load(d, d.my_red + par + threadIdx.x, ep);
   }
   __syncthreads();
