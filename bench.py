@@ -388,6 +388,12 @@ def run_case(N, args, primary, world, rank, local, torch, dist, fsb):
     prof = s.profile_report()
     s.profile_ = 0
     tot = sum(ms for (_, ms) in prof.values())
+    spread = None
+    if world > 1:  # the same kernel on every GPU: shortest / longest mean launch (load balance of each phase)
+        allp = [None] * world
+        dist.all_gather_object(allp, {f"{k}@L{l}": ms / c * 1e3 for (k, l), (c, ms) in prof.items()})
+        spread = {name: [round(min(p.get(name, 0.0) for p in allp), 1), round(max(p.get(name, 0.0) for p in allp), 1)]
+                  for name in sorted(allp[0], key=lambda nm: -allp[0][nm])[:16]}
     nlev = len(levels)
     nnzP = [int(s._L.fsb_level_int(s.handle, l, b"P_col", None, 0)) for l in range(nlev - 1)]
     nnz_out = [int(s.level_int(l, "Aout_ptr")[-1]) for l in range(nlev - 1)]
@@ -450,7 +456,8 @@ def run_case(N, args, primary, world, rank, local, torch, dist, fsb):
                ms_single=ms_single, dinfo=dinfo, lo=lo, hi=hi, clocks=clocks, parity=parity,
                roofline={"bound": "hbm", "kernel": f"{kname}@level{klev}", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src, "bytes_per_launch": bytes_per_launch,
-                         "us_per_launch": kms / kcnt * 1e3, "share_of_step": kms / tot, "fine_level_kernels": fine, "top_kernels": kernels},
+                         "us_per_launch": kms / kcnt * 1e3, "share_of_step": kms / tot, "fine_level_kernels": fine, "top_kernels": kernels,
+                         "us_per_launch_min_max_over_ranks": spread},
                stages=stages)
     if rank == 0 and world == 1 and args.scipy_check and N <= 160:
         out["scipy"] = scipy_sanity(s, b_host.numpy(), xg)

@@ -294,6 +294,13 @@ int fsb_dist_info(const fsb_solver* s, int* sharded_levels, int* user_lo, int* u
   }
   return d.nranks;
 }
+// tools only (not part of the public header): `reps` back-to-back exchanges of channel `chan` (no compute in between, all
+// ranks must call it together) timed with CUDA events -> microseconds per exchange; chan < 0: all-reduces instead
+double fsb_dist_bench_exchange(fsb_solver* s, int chan, int reps) {
+  double us = -1.0;
+  guarded(s, [&](fsb::Solver& S) { us = S.dist_bench_exchange(chan, reps); });
+  return us;
+}
 void fsb_split_by_weight(int nparts, const long long* weights, int nranks, int* out_begin) { fsb::split_by_weight(nparts, weights, nranks, out_begin); }
 // tools only (not part of the public header): phase timestamps of one CTA of the cluster smoother
 void fsb_debug_stamps(int cta_plus1, long long* out64) { fsb::debug_stamps(cta_plus1, out64); }

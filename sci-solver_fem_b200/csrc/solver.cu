@@ -290,6 +290,36 @@ void Solver::exchange_chan(int chan, const double* src, double* dst, const int* 
   launch_ll_exchange(ctx, dist.chan[chan].dev, src, dst, done);
 }
 
+double Solver::dist_bench_exchange(int chan, int reps) {
+  if (!dist.connected || dist.nranks < 2) throw std::runtime_error("not connected");
+  cudaStream_t s = ctx.stream;
+  LevelData& L0 = levels[0];
+  if (scal.size() != 1) scal.alloc(1, s);
+  if (partials.size() < 4096) partials.alloc(4096, s);
+  launch_cg_init(ctx, scal.get(), 0.0, 1 << 30, 2);
+  auto one = [&]() {
+    if (chan >= 0) {
+      if (chan >= dist.nchan || !dist.chan[chan].list) throw std::invalid_argument("no such channel");
+      const int lev = chan < kChanLevel0 ? 0 : (chan - kChanLevel0) / kChanPerLevel;
+      const int which = chan < kChanLevel0 ? kXPre : (chan - kChanLevel0) % kChanPerLevel;
+      LevelData& L = levels[lev];
+      double* v = (which == kDown) ? L.bc.get() : (which == kUp) ? L.xc.get() : (which == kRes) ? L.r.get() : L.x.get();
+      exchange_chan(chan, v, v, nullptr);
+    } else {
+      launch_dot(ctx, 1024, L0.x, L0.x, partials, scal.get(), 1);
+    }
+  };
+  for (int i = 0; i < 5; i++) one();
+  FSB_CUDA(cudaStreamSynchronize(s));
+  FSB_CUDA(cudaEventRecord(ev0_, s));
+  for (int i = 0; i < reps; i++) one();
+  FSB_CUDA(cudaEventRecord(ev1_, s));
+  FSB_CUDA(cudaEventSynchronize(ev1_));
+  float ms = 0;
+  FSB_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
+  return ms * 1e3 / reps;
+}
+
 void Solver::vcycle(int lev, const double* b_src, const int* gather, double* x_dst, const int* scatter, double* /*unused*/) {
   LevelData& L = levels[lev];
   const int* done = cg_active_ ? &scal.get()->done : nullptr;

@@ -126,6 +126,7 @@ class Solver {
   void dist_get_blob(void* blob /* kDistBlobBytes */, long long* arena_bytes);
   void dist_connect(const void* blobs /* nranks x kDistBlobBytes, rank order */);
   void dist_disconnect();
+  double dist_bench_exchange(int chan, int reps);  // tools: microseconds per back-to-back exchange (chan < 0: all-reduce)
   // one exchange pattern: the values of mine that peers need, grouped by destination peer, and the places where
   // the values the peers send me go (same index in every GPU's copy of the exchanged vector)
   struct PushList {

@@ -14,6 +14,8 @@ for f in sys.argv[1:]:
     print("   roofline", r["kernel"], round(r["frac"], 3), "us", round(r["us_per_launch"], 1))
     for k, v in r["top_kernels"].items():
         print("     ", k, v)
+    if r.get("us_per_launch_min_max_over_ranks"):
+        print("   min/max over ranks (us):", r["us_per_launch_min_max_over_ranks"])
     if p.get("secondary"):
         s = p["secondary"]
         print("   secondary", s["ms_per_step"], s["roofline"]["kernel"], round(s["roofline"]["frac"], 3), "setup", s["setup_ms"], "scipy", s.get("scipy_cg_jacobi"))
