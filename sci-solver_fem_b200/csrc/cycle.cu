@@ -239,7 +239,7 @@ constexpr int SPMV_ROWS = 256;
 constexpr int SPMV_CAP = 4096;  // products per tile (32 KB)
 
 template <int MODE, bool DOT>  // MODE 0: y = A x   1: y = b - A x   2: y += A x   3: y -= A x
-__global__ void __launch_bounds__(SPMV_ROWS) csr_stream_kernel(int n, const int* __restrict__ ptr, const int* __restrict__ col,
+__global__ void __launch_bounds__(SPMV_ROWS) csr_stream_kernel(int row_begin, int n, const int* __restrict__ ptr, const int* __restrict__ col,
                                                                const double* __restrict__ val, const double* __restrict__ x,
                                                                double* __restrict__ y, const double* __restrict__ b,
                                                                double* __restrict__ partials, PcgScalars* __restrict__ sc,
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(SPMV_ROWS) csr_stream_kernel(int n, const int*
   __shared__ int s_flag;
   if (done && *done) return;
   const int t = threadIdx.x;
-  const int r0 = blockIdx.x * SPMV_ROWS;
+  const int r0 = row_begin + blockIdx.x * SPMV_ROWS;  // rows [row_begin, n): all rows, or this GPU's range of a sharded level
   const int nr = min(SPMV_ROWS, n - r0);
   // every thread learns the CTA's entry range directly (two broadcast loads): the streaming loads
   // below do not wait for a barrier
@@ -322,11 +322,14 @@ void spmv_dispatch(const Ctx& c, const DCsr& A, const double* x, double* y, cons
   ProfScope ps(c, name);
   const bool ranged = rr.end >= 0;
   if (ranged && DOT) throw std::runtime_error("row-ranged CSR dot is not implemented (use the SELL copy)");
-  if (!DOT && (ranged || (double)A.nnz > 32.0 * n || n < 32768)) {  // long rows, a small operator or a row range: one warp per row
-    const int r0 = ranged ? rr.begin : 0, r1 = ranged ? rr.end : n;
-    if (r1 > r0) FSB_LAUNCH((spmv_vector_kernel<MODE>), cdiv((long long)(r1 - r0) * 32, 256), 256, 0, c.stream, r0, r1, A.ptr, A.col, A.val, x, y, b, done);
-  } else
-    FSB_LAUNCH((csr_stream_kernel<MODE, DOT>), cdiv(n, SPMV_ROWS), SPMV_ROWS, 0, c.stream, n, A.ptr, A.col, A.val, x, y, b, partials, sc, done);
+  const int r0 = ranged ? rr.begin : 0, r1 = ranged ? rr.end : n;
+  if (r1 <= r0 && !DOT) return;
+  // long rows or a small operator: one warp per row; otherwise (also a row range of short rows — A_out, P of a sharded
+  // level) the coalesced stream kernel
+  if (!DOT && ((double)A.nnz > 32.0 * n || (!ranged && n < 32768)))
+    FSB_LAUNCH((spmv_vector_kernel<MODE>), cdiv((long long)(r1 - r0) * 32, 256), 256, 0, c.stream, r0, r1, A.ptr, A.col, A.val, x, y, b, done);
+  else
+    FSB_LAUNCH((csr_stream_kernel<MODE, DOT>), cdiv(r1 - r0, SPMV_ROWS), SPMV_ROWS, 0, c.stream, r0, r1, A.ptr, A.col, A.val, x, y, b, partials, sc, done);
   FSB_CHECK_LAUNCH();
 }
 

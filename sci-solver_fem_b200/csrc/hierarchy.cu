@@ -130,15 +130,20 @@ __global__ void spgemm_rows(int n, const int* __restrict__ ptrA, const int* __re
 
 // Warp-per-row Gustavson for rows with many products (R * (A P): ~850 products, ~40 distinct columns
 // per coarse row).  Pass 1 collects the distinct columns in a shared-memory hash set and sorts them;
-// pass 2 streams the products again in sequence order, and lane l adds up the products of the output
-// slots it owns (slot mod 32 == l) — every slot is therefore summed by one lane in product order, the
-// same order as a sequential accumulation, so the result stays bit-identical to the host-order sum.
-constexpr int WG_CHUNK = 1024;    // products staged per step
+// pass 2 streams the products again in sequence order, groups them by output slot with a STABLE counting
+// sort inside the warp (rank of a product among the earlier products of its slot: __match_any_sync over
+// batches of 32 consecutive products + a running count per slot), and lane l then adds up the products of
+// the slots it owns (slot mod 32 == l) as one contiguous run each — every slot is summed by one lane in
+// product order, the same order as a sequential accumulation, so the result stays bit-identical to the
+// host-order sum.  (The first version let every lane walk over ALL products of the row and pick its own:
+// 91 % of the kernel's instructions, 10 of the 46 ms of the setup at N=118; profiles/r2_spgemm_before.txt.)
+constexpr int WG_CHUNK = 512;     // products staged per step
 constexpr int WG_MAXROW = 512;    // entries of the A-row (prefix table + staged A-row)
 constexpr int WG_HASH = 256;      // hash-set size; rows with more than WG_MAXD distinct columns fall back
 constexpr int WG_MAXD = 192;
 constexpr int WG_WARPS = 4;
-constexpr int WG_SMEM_PER_WARP = WG_CHUNK * 8 + WG_CHUNK * 4 + WG_CHUNK + WG_HASH * 4 + WG_HASH * 4 + (WG_MAXROW + 1) * 4 + WG_MAXROW * 12 + 12;
+constexpr int WG_SMEM_PER_WARP = WG_CHUNK * 8 + WG_CHUNK * 4 + WG_CHUNK + WG_HASH * 4 + WG_HASH * 4 + (WG_MAXROW + 1) * 4 + WG_MAXROW * 12 + 12 +
+                                 WG_CHUNK * 8 + WG_CHUNK * 2 + 16;  // + products grouped by slot, rank of a product inside its slot
 
 // products q0 .. q0+WG_CHUNK of the row: the A-row (B-row starts pb, values va) is staged in shared
 // memory, so a product costs one global hop (colB / valB); four products per lane are in flight.
@@ -178,6 +183,9 @@ __global__ void __launch_bounds__(32 * WG_WARPS) spgemm_warp_kernel(int n, const
   int* pref = dist + WG_HASH;
   int* pb = pref + (WG_MAXROW + 1);
   double* va = reinterpret_cast<double*>(base + ((WG_CHUNK * 13 + WG_HASH * 8 + (WG_MAXROW + 1) * 4 + WG_MAXROW * 4 + 7) & ~7));
+  double* sorted = va + WG_MAXROW;                                        // products of the chunk grouped by slot
+  unsigned short* prank = reinterpret_cast<unsigned short*>(sorted + WG_CHUNK);
+  int* scnt = hash;                                                       // the hash set is free after pass 1: per-slot counts / offsets
   const int i = blockIdx.x * WG_WARPS + w;
   if (i >= n) return;
   const int a0 = ptrA[i], na = ptrA[i + 1] - a0;
@@ -246,20 +254,52 @@ __global__ void __launch_bounds__(32 * WG_WARPS) spgemm_warp_kernel(int n, const
     const int mc = min(m, q0 + WG_CHUNK) - q0;
     wg_expand(q0, m, na, lane, pref, pb, va, colB, valB, pcol, pval);
     __syncwarp();
-    for (int q = lane; q < mc; q += 32) {  // slot of every product (binary search in the sorted distinct list)
-      const int c = pcol[q];
-      int lo = 0, hi = nd - 1;
-      while (lo < hi) { const int mid = (lo + hi) >> 1; if (dist[mid] < c) lo = mid + 1; else hi = mid; }
-      pslot[q] = (unsigned char)lo;
+    for (int h = lane; h < WG_HASH; h += 32) scnt[h] = 0;
+    __syncwarp();
+    // slot of every product (binary search in the sorted distinct list) and its rank among the earlier products of
+    // that slot: batches of 32 consecutive products, lanes with equal slots found by __match_any_sync
+    for (int q0b = 0; q0b < mc; q0b += 32) {
+      const int q = q0b + lane;
+      int sl = -1;
+      if (q < mc) {
+        const int c = pcol[q];
+        int lo = 0, hi = nd - 1;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (dist[mid] < c) lo = mid + 1; else hi = mid; }
+        sl = lo;
+        pslot[q] = (unsigned char)lo;
+      }
+      const unsigned peers = __match_any_sync(0xffffffffu, sl);
+      if (q < mc) prank[q] = (unsigned short)(scnt[sl] + __popc(peers & ((1u << lane) - 1u)));
+      __syncwarp();
+      if (q < mc && (peers & ((1u << lane) - 1u)) == 0) scnt[sl] += __popc(peers);  // one lane per distinct slot
+      __syncwarp();
+    }
+    // counts -> offsets (exclusive scan over the nd <= 192 slots; slot = j * 32 + lane)
+    {
+      int run = 0;
+      for (int j0 = 0; j0 < nd; j0 += 32) {
+        const int sl = j0 + lane;
+        const int cnt = sl < nd ? scnt[sl] : 0;
+        int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        __syncwarp();
+        if (sl < nd) scnt[sl] = run + inc - cnt;
+        run += __shfl_sync(0xffffffffu, inc, 31);
+      }
+      if (lane == 0) scnt[nd] = run;  // nd <= WG_MAXD < WG_HASH
     }
     __syncwarp();
-    for (int q = 0; q < mc; q++) {
-      const int sl = pslot[q];
-      if ((sl & 31) == lane) {
-        const double v = pval[q];
-        const int j = sl >> 5;
+    for (int q = lane; q < mc; q += 32) sorted[scnt[pslot[q]] + prank[q]] = pval[q];  // stable: sequence order inside a slot
+    __syncwarp();
 #pragma unroll
-        for (int jj = 0; jj < WG_MAXD / 32; jj++) if (jj == j) acc[jj] += v;
+    for (int jj = 0; jj < WG_MAXD / 32; jj++) {
+      const int sl = jj * 32 + lane;
+      if (sl < nd) {
+        const int e1 = scnt[sl + 1];
+        double a = acc[jj];
+        for (int k = scnt[sl]; k < e1; k++) a += sorted[k];
+        acc[jj] = a;
       }
     }
     __syncwarp();

@@ -1,0 +1,11 @@
+"""One cold pass of pattern + assembly + AMG setup (for an ncu launch list of the setup-phase kernels):
+   ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file out.csv python tools/setup_only.py [--cube 118]"""
+import argparse, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import sci_solver_fem_b200 as fsb
+ap = argparse.ArgumentParser(); ap.add_argument("--cube", type=int, default=118); a = ap.parse_args()
+v, t = fsb.meshio.kuhn_cube(a.cube)
+s = fsb.FEMSolver.from_arrays(v, t)
+s.solverType_, s.seed_ = 1, 0
+s.setup()
+print({k: round(s.time_ms(k), 2) for k in ("pattern", "assemble", "setup")})
