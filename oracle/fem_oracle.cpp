@@ -1027,7 +1027,13 @@ struct DenseLU {
   }
   void solve(const std::vector<T>& b, std::vector<T>& x) const {
     x = b;
-    for (int k = 0; k < n; k++) { if (piv[k] != k) std::swap(x[k], x[piv[k]]); for (int i = k + 1; i < n; i++) x[i] -= lu[(size_t)i * n + k] * x[k]; }
+    // factor() swaps whole rows (LAPACK style: the multipliers already stored travel with their row), so ALL row
+    // interchanges are applied to the right-hand side first, then the unit-lower solve.  (Interleaving the swap of step k
+    // with the elimination of step k is only equivalent when no pivoting happens — true for the structured cubes, not
+    // for the repo's TetGen cube, where the mistake cost the oracle 7 PCG iterations; found by an independent NumPy
+    // V-cycle, tests/test_oracle_golden.py::test_coarse_lu_with_row_interchanges.)
+    for (int k = 0; k < n; k++) if (piv[k] != k) std::swap(x[k], x[piv[k]]);
+    for (int k = 0; k < n; k++) for (int i = k + 1; i < n; i++) x[i] -= lu[(size_t)i * n + k] * x[k];
     for (int i = n - 1; i >= 0; i--) { T s = x[i]; for (int j = i + 1; j < n; j++) s -= lu[(size_t)i * n + j] * x[j]; x[i] = s / lu[(size_t)i * n + i]; }
   }
 };

@@ -239,7 +239,9 @@ void Solver::setup() {
     if (N >= sell_min_rows && (double)L.A.nnz <= 24.0 * N) {
       if (L.level_id == 0) build_sell(ctx, L.A, L.sA);
       build_sell(ctx, L.Aout, L.sAout, 1024);  // rows have 0..8 inter-partition entries: sort by length inside 1024-row windows
-      build_sell(ctx, L.P, L.sP);
+      // prolongator rows have 1..8 entries (one per adjacent aggregate): length-sorted windows keep the slices tight
+      static const int sp_window = getenv("FSB_SP_WINDOW") ? atoi(getenv("FSB_SP_WINDOW")) : 1024;  // tuning knob, 0: unsorted
+      build_sell(ctx, L.P, L.sP, sp_window);
     }
     times_ms["setup_prolongator"] += now_ms() - t0; t0 = now_ms();
     DCsr AP, Ac;

@@ -239,3 +239,48 @@ def test_topsize_single_level():
     b = A @ (egg_carton(v) + 1)
     x, it = o.solve(b)
     assert it == 0 and rel(x, egg_carton(v) + 1) < 1e-10
+
+
+def test_coarse_lu_with_row_interchanges():
+    """The oracle's V-cycle against an independent NumPy/SciPy restatement of Appendix B on the repo's TetGen cube
+    (BASELINE configs[1]): its coarse matrix is the one case in the fixtures where the dense LU actually pivots.
+    (A first version of the oracle's LU solve interleaved the row interchanges with the forward substitution, which is
+    only right when no pivoting happens: the preconditioner was off by 2e-3 and PCG needed 31 instead of 24 iterations.)"""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from tests.util import make_oracle
+    g = golden("CubeMesh_size256step16")
+    o, ptr, col, val = make_oracle(g["verts"], g["tets"], g["labels"], solverType=1, tolerance=1e-8, maxIters=200, seed=0)
+    assert o.setup() == 2
+    n = len(g["verts"])
+    agg_idx, part_idx = o.level_int(0, "aggregateIdx"), o.level_int(0, "partitionIdx")
+    nc = len(agg_idx) - 1
+    A = sp.csr_matrix((o.level_val(0, "A_val"), o.level_int(0, "A_col"), o.level_int(0, "A_ptr")), shape=(n, n))
+    P = sp.csr_matrix((o.level_val(0, "P_val"), o.level_int(0, "P_col"), o.level_int(0, "P_ptr")), shape=(n, nc))
+    R = P.T.tocsr()
+    lu = spla.splu((R @ A @ P).tocsc())
+    pstart = agg_idx[part_idx]
+    part = np.zeros(n, dtype=int)
+    for p in range(len(pstart) - 1):
+        part[pstart[p]:pstart[p + 1]] = p
+    C = A.tocoo()
+    inside = part[C.row] == part[C.col]
+    Ain = sp.csr_matrix((C.data[inside], (C.row[inside], C.col[inside])), shape=(n, n))
+    Aout = sp.csr_matrix((C.data[~inside], (C.row[~inside], C.col[~inside])), shape=(n, n))
+    d = A.diagonal()
+
+    def vcycle(b):
+        x = b / d
+        for _ in range(5):
+            x = x + (b - Ain @ x) / d
+        x = x + P @ lu.solve(R @ (b - Ain @ x - Aout @ x))
+        bp = b - Aout @ x
+        for _ in range(5):
+            x = x + (bp - Ain @ x) / d
+        return x
+
+    r = np.random.default_rng(0).uniform(-1, 1, n)
+    z = vcycle(r)
+    assert np.linalg.norm(o.precond_permuted(r) - z) <= 1e-10 * np.linalg.norm(z)
+    x, it = o.solve(np.ones(n))
+    assert it == 24 and o.final_relres() <= 1e-8
