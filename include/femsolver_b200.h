@@ -73,6 +73,9 @@ int fsb_level_rows(const fsb_solver* s, int level);
 long long fsb_level_nnz(const fsb_solver* s, int level);
 /* integer arrays of a level: permutation, ipermutation, aggregateIdx, partitionIdx, partitionLabel,
  * xadjOut, adjOut, A_ptr, A_col, P_ptr, P_col, R_ptr, R_col, pstart.  buf == NULL: returns the length. */
+/* scalar facts about a level: "nparts", "max_part_rows", "smoother" (0 register-resident ELL, 1 shared-memory ELL,
+ * 2 cluster, 3 cooperative, 4 dense partition blocks), "dense_tail" (1: this level starts the dense tail), "sell" */
+long long fsb_level_stat(const fsb_solver* s, int level, const char* name);
 long long fsb_level_int(fsb_solver* s, int level, const char* name, int* buf, long long cap);
 /* value arrays: A_val, P_val, R_val, diag; level == num_levels-1 also: Ainv */
 long long fsb_level_val(fsb_solver* s, int level, const char* name, double* buf, long long cap);

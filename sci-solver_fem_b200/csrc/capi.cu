@@ -166,6 +166,17 @@ long long fsb_level_nnz(const fsb_solver* s, int level) {
   return s->impl->level(level).A.nnz;
 }
 
+long long fsb_level_stat(const fsb_solver* s, int level, const char* name) {
+  if (!s || !s->impl || !name || level < 0 || level >= s->impl->num_levels()) return -1;
+  const fsb::LevelData& L = s->impl->level(level);
+  const std::string n(name);
+  if (n == "nparts") return L.nparts;
+  if (n == "max_part_rows") return L.maxPartRows;
+  if (n == "smoother") return L.use_blockdense ? 4 : L.use_ell ? 0 : L.use_sellg ? 1 : L.smemBytes > 0 ? 2 : 3;  // 0 register ELL, 1 shared-memory ELL, 2 cluster, 3 cooperative, 4 dense blocks
+  if (n == "dense_tail") return level == s->impl->tail_level_ ? 1 : 0;
+  if (n == "sell") return L.sA.ready() || L.sAout.ready() ? 1 : 0;
+  return -1;
+}
 long long fsb_level_int(fsb_solver* s, int level, const char* name, int* buf, long long cap) {
   if (!s || !s->impl || level < 0 || level >= s->impl->num_levels()) return -1;
   long long rc = -1;

@@ -922,6 +922,52 @@ __global__ void __launch_bounds__(BLOCK) smooth_cluster_kernel(int C, int G, int
   FSB_STAMP(41);
 }
 
+// (d) dense partition blocks (dense_tail.cu: build_block_smoothers): a whole smoothing stage of a partition as small
+// dense GEMVs.  One CTA per 32 rows of a partition: the partition's vector(s) in shared memory, a warp per row, lanes
+// stride over the columns (coalesced), four independent accumulators per lane (fixed order).
+//   pre  (x_in == null): x = S1 b            post: x = Gp x_in + S2 b
+template <int ROWS>
+__global__ void __launch_bounds__(256) smooth_blockdense_kernel(const int* __restrict__ work, const int* __restrict__ pstart,
+                                                                const long long* __restrict__ off, const double* __restrict__ S1,
+                                                                const double* __restrict__ Gp, const double* __restrict__ S2,
+                                                                const double* __restrict__ b_src, const int* __restrict__ gather,
+                                                                double* __restrict__ b_int, const double* __restrict__ x_in,
+                                                                double* __restrict__ x_out, const int* __restrict__ scatter,
+                                                                double* __restrict__ x_ext, const int* __restrict__ done) {
+  pdl_wait();
+  __shared__ double sb[1024], sx[1024];
+  if (done && *done) return;
+  const int p = work[2 * blockIdx.x], lr0 = work[2 * blockIdx.x + 1];
+  const int r0 = pstart[p], m = pstart[p + 1] - r0;
+  const long long base = off[p];
+  for (int c = threadIdx.x; c < m; c += blockDim.x) {
+    const double bv = b_src[gather ? gather[r0 + c] : r0 + c];
+    sb[c] = bv;
+    if (x_in) sx[c] = x_in[r0 + c];
+    if (b_int && c >= lr0 && c < lr0 + ROWS) b_int[r0 + c] = bv;  // every row of the partition is saved by exactly one CTA
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int lr = lr0 + warp; lr < min(lr0 + ROWS, m); lr += 8) {
+    const double* A = (x_in ? S2 : S1) + base + (size_t)lr * m;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int c = lane;
+    for (; c + 96 < m; c += 128) { s0 += A[c] * sb[c]; s1 += A[c + 32] * sb[c + 32]; s2 += A[c + 64] * sb[c + 64]; s3 += A[c + 96] * sb[c + 96]; }
+    for (; c < m; c += 32) s0 += A[c] * sb[c];
+    if (x_in) {
+      const double* G = Gp + base + (size_t)lr * m;
+      c = lane;
+      for (; c + 96 < m; c += 128) { s0 += G[c] * sx[c]; s1 += G[c + 32] * sx[c + 32]; s2 += G[c + 64] * sx[c + 64]; s3 += G[c + 96] * sx[c + 96]; }
+      for (; c < m; c += 32) s0 += G[c] * sx[c];
+    }
+    const double s = warp_sum((s0 + s1) + (s2 + s3));
+    if (lane == 0) {
+      if (x_out) x_out[r0 + lr] = s;
+      if (scatter) x_ext[scatter[r0 + lr]] = s;
+    }
+  }
+}
+
 // warp-per-row SpMV for long rows (restriction operators, coarse operators)
 template <int MODE>
 __global__ void __launch_bounds__(256) spmv_vector_kernel(int row_begin, int n, const int* __restrict__ ptr,
@@ -955,6 +1001,21 @@ __global__ void __launch_bounds__(256) spmv_vector_kernel(int row_begin, int n, 
     else if (MODE == 2) y[row] = y[row] + s;
     else y[row] = y[row] - s;
   }
+}
+
+// y[r] += (A x)[r] for the rows r of a list (ghost copies of a sharded level apply the coarse correction themselves:
+// x_ghost += P_ghost xc); rows are short (a prolongator row has <= 8 entries): one thread per listed row
+__global__ void __launch_bounds__(256) spmv_list_add_kernel(int count, const int* __restrict__ rows, const int* __restrict__ ptr,
+                                                            const int* __restrict__ col, const double* __restrict__ val,
+                                                            const double* __restrict__ x, double* __restrict__ y, const int* __restrict__ done) {
+  pdl_wait();
+  if (done && *done) return;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  const int r = rows[k];
+  double s = 0.0;
+  for (int e = ptr[r]; e < ptr[r + 1]; e++) s += val[e] * __ldg(x + col[e]);  // same order as the owner's row sum
+  y[r] = y[r] + s;
 }
 
 // bc = R b - T x, T = R A: warp per coarse row, first the row of R against b, then the row of T against x;
@@ -1184,6 +1245,13 @@ void launch_spmv_dot_sell(const Ctx& c, const Sell& A, const double* x, double* 
   sell_dispatch<0, true>(c, A, x, y, nullptr, partials, sc, &sc->done, "spmv_dot", rr);
 }
 
+void launch_spmv_list_add(const Ctx& c, const DCsr& A, const int* rows, int count, const double* x, double* y, const int* done) {
+  if (count <= 0) return;
+  g_launch_counter++;
+  ProfScope ps(c, "prolong_ghost");
+  FSB_LAUNCH((spmv_list_add_kernel), cdiv(count, 256), 256, 0, c.stream, count, rows, A.ptr, A.col, A.val, x, y, done);
+  FSB_CHECK_LAUNCH();
+}
 void launch_ll_exchange(const Ctx& c, const LLXchg& x, const double* src, double* dst, const int* done) {
   g_launch_counter++;
   ProfScope ps(c, "exchange");
@@ -1211,6 +1279,12 @@ void launch_smooth(const Ctx& c, const LevelData& L, const double* b_src, const 
   // sharded level: this GPU smooths its own contiguous range of partitions only
   const int p0 = owned_only ? L.ownP0 : 0, pn = owned_only ? L.ownPn : L.nparts;
   if (pn <= 0) return;
+  if (L.use_blockdense && !r_out && !owned_only) {  // few small partitions: the whole stage as dense GEMVs on precomputed blocks
+    FSB_LAUNCH((smooth_blockdense_kernel<32>), L.bdCtas, 256, 0, s, L.bdWork, L.pstart, L.bdOff, L.bdS1, L.bdGp, L.bdS2, b_src, gather, b_int, x_in,
+                                                x_out, scatter, x_ext, done);
+    FSB_CHECK_LAUNCH();
+    return;
+  }
   const int* nl = owned_only ? L.nlistOwn : L.nlist;
   const DevBuf<EllDesc>* pl = owned_only ? L.plistOwn : L.plist;
   static const bool serial = getenv("FSB_ELL_SERIAL") && atoi(getenv("FSB_ELL_SERIAL")) != 0;  // tuning knob: size classes one after the other

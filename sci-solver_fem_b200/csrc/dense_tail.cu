@@ -188,6 +188,7 @@ static void level_operator(const Ctx& ctx, cublasHandle_t h, const LevelData& L,
 void Solver::build_dense_tail() {
   tail_level_ = -1;
   Mtail.release();
+  tail_key_[0] = prm.preInnerIters; tail_key_[1] = prm.postInnerIters; tail_key_[2] = prm.postRelaxes; tail_key_[3] = prm.smootherWeight;
   const char* env = getenv("FSB_DENSE_TAIL");  // tuning / test knob, read at every setup: 0 disables, n > 1 sets the row limit
   const int limit = env ? atoi(env) : kDenseTailMaxRows;
   const int last = (int)levels.size() - 1;
@@ -222,6 +223,136 @@ void Solver::build_dense_tail() {
     Mtail.release();
   }
   tail_key_[0] = prm.preInnerIters; tail_key_[1] = prm.postInnerIters; tail_key_[2] = prm.postRelaxes; tail_key_[3] = prm.smootherWeight;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Dense partition blocks: the same idea one step up.  A level with a few dozen partitions of a few hundred rows (the
+// 21 202-row level 2 of the ~100 M-tet cube: 53 partitions) is too large for the dense tail (n^2) but its smoothing
+// stages are pure latency — six barrier-separated passes over ~40 k entries per partition take 48 us, the bytes would
+// take 4.  Per partition the stage is a fixed linear map of (b) resp. (x_in, b'), so S(nu1), G^nu2 and S(nu2-1) are
+// formed once (Horner on the m x m diagonal block, the same recurrences as in level_operator above) and a stage becomes
+// one pass of small dense GEMVs (cycle.cu: smooth_blockdense_kernel).  Used where the restricted residual comes from
+// R b - (R A) x (no in-partition residual needed) and the three block sets stay below kBlockDenseMaxBytes.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+constexpr size_t kBlockDenseMaxBytes = 96u << 20;  // per block set: a stage then streams <= 96 / 192 MB (pre / post)
+constexpr int kBlockDenseRows = 32;                 // rows of a block per CTA of the apply kernel
+
+// in-partition entries (incl. the diagonal) of partition rows -> G = I - W B and S0 = W, both as packed m x m blocks
+__global__ void bd_make_blocks(int n, const int* __restrict__ ptr, const int* __restrict__ col, const double* __restrict__ val,
+                               const double* __restrict__ diag, const int* __restrict__ rowPart, const int* __restrict__ pstart,
+                               const long long* __restrict__ off, double w, double* __restrict__ G, double* __restrict__ S0) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int p = rowPart[r], r0 = pstart[p], m = pstart[p + 1] - r0, lr = r - r0;
+  const double wr = w / diag[r];
+  double* g = G + off[p] + (size_t)lr * m;
+  for (int e = ptr[r]; e < ptr[r + 1]; e++) {
+    const int c = col[e] - r0;
+    if ((unsigned)c < (unsigned)m) g[c] -= wr * val[e];
+  }
+  g[lr] += 1.0;
+  S0[off[p] + (size_t)lr * m + lr] = wr;
+}
+__global__ void bd_add_w(int n, const double* __restrict__ diag, const int* __restrict__ rowPart, const int* __restrict__ pstart,
+                         const long long* __restrict__ off, double w, double* __restrict__ M) {  // M_p += W_p
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int p = rowPart[r], r0 = pstart[p], m = pstart[p + 1] - r0, lr = r - r0;
+  M[off[p] + (size_t)lr * m + lr] += w / diag[r];
+}
+__global__ void bd_identity(int n, const int* __restrict__ rowPart, const int* __restrict__ pstart, const long long* __restrict__ off,
+                            double* __restrict__ M) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int p = rowPart[r], r0 = pstart[p], m = pstart[p + 1] - r0, lr = r - r0;
+  M[off[p] + (size_t)lr * m + lr] = 1.0;
+}
+}  // namespace
+
+void Solver::build_block_smoothers() {
+  for (auto& L : levels) { L.use_blockdense = false; L.bdS1.release(); L.bdGp.release(); L.bdS2.release(); L.bdOff.release(); L.bdWork.release(); L.bdCtas = 0; }
+  const char* env = getenv("FSB_BLOCK_DENSE");  // tuning / test knob, read at every setup: 0 disables
+  if (env && atoi(env) == 0) return;
+  const int last = (int)levels.size() - 1;
+  const int end = tail_level_ >= 0 ? tail_level_ : last;
+  cudaStream_t s = ctx.stream;
+  const double w = prm.smootherWeight;
+  const int nu1 = std::max(0, prm.preInnerIters), nu2 = std::max(0, prm.postInnerIters);
+  if (prm.postRelaxes != 1) return;  // the blocks encode one post-relaxation pass
+  for (int l = 1; l < end; l++) {
+    LevelData& L = levels[l];
+    if (L.RA.nrows == 0 || L.use_ell || L.nparts <= 0) continue;  // (the register-resident kernel is the better fit where it applies)
+    std::vector<int> ps = L.pstart.to_vector();
+    std::vector<long long> off(L.nparts + 1, 0);
+    for (int p = 0; p < L.nparts; p++) { const long long m = ps[p + 1] - ps[p]; off[p + 1] = off[p] + m * m; }
+    const size_t total = (size_t)off[L.nparts];
+    if (total * sizeof(double) > kBlockDenseMaxBytes || L.nparts > 2 * ctx.num_sms) continue;
+    try {
+      if (!cublas_) {
+        cublasHandle_t h;
+        FSB_CUBLAS(cublasCreate(&h));
+        cublas_ = h;
+      }
+      cublasHandle_t h = static_cast<cublasHandle_t>(cublas_);
+      FSB_CUBLAS(cublasSetStream(h, s));
+      FSB_CUBLAS(cublasSetPointerMode(h, CUBLAS_POINTER_MODE_HOST));
+      const int n = L.n;
+      IBuf rowPart(n, s);
+      dt_row_partition<<<cdiv(L.nparts, 128), 128, 0, s>>>(L.nparts, L.pstart, rowPart);
+      L.bdOff.alloc(L.nparts + 1, s);
+      L.bdOff.from_host(off.data(), L.nparts + 1);
+      DBuf G(total, s), Sa(total, s), Sb(total, s);
+      G.zero(); Sa.zero();
+      L.bdS1.alloc(total, s); L.bdGp.alloc(total, s); L.bdS2.alloc(total, s);
+      L.bdS2.zero();
+      bd_make_blocks<<<cdiv(n, 128), 128, 0, s>>>(n, L.A.ptr, L.A.col, L.A.val, L.diag, rowPart, L.pstart, L.bdOff, w, G, Sa);
+      auto block_mul = [&](const double* A, const double* B, double* C) {  // C_p = A_p B_p for every partition
+        for (int p = 0; p < L.nparts; p++) {
+          const int m = ps[p + 1] - ps[p];
+          gemm_rm(h, m, m, m, 1.0, A + off[p], m, B + off[p], m, 0.0, C + off[p], m);
+        }
+      };
+      // Horner: S(k+1) = W + G S(k), S(0) = W;  S1 = S(nu1), S2 = S(nu2 - 1) (zero for nu2 == 0)
+      double* cur = Sa;
+      double* nxt = Sb;
+      const int steps = std::max(nu1, nu2 - 1);
+      for (int k = 0; k <= steps; k++) {
+        if (k == nu1) L.bdS1.from_device(cur, total);
+        if (k == nu2 - 1) L.bdS2.from_device(cur, total);
+        if (k == steps) break;
+        block_mul(G, cur, nxt);
+        bd_add_w<<<cdiv(n, 128), 128, 0, s>>>(n, L.diag, rowPart, L.pstart, L.bdOff, w, nxt);
+        std::swap(cur, nxt);
+      }
+      // Gp = G^nu2
+      {
+        DBuf& A = Sa;
+        DBuf& B = Sb;
+        A.zero();
+        bd_identity<<<cdiv(n, 128), 128, 0, s>>>(n, rowPart, L.pstart, L.bdOff, A);
+        double* a = A;
+        double* b = B;
+        for (int k = 0; k < nu2; k++) { block_mul(G, a, b); std::swap(a, b); }
+        L.bdGp.from_device(a, total);
+      }
+      // CTA work list of the apply kernel: kBlockDenseRows rows of one partition per CTA
+      std::vector<int> work;
+      for (int p = 0; p < L.nparts; p++)
+        for (int r = 0; r < ps[p + 1] - ps[p]; r += kBlockDenseRows) { work.push_back(p); work.push_back(r); }
+      L.bdCtas = (int)work.size() / 2;
+      L.bdWork.alloc(work.size(), s);
+      L.bdWork.from_host(work.data(), work.size());
+      FSB_CHECK_LAUNCH();
+      FSB_CUDA(cudaStreamSynchronize(s));
+      L.use_blockdense = true;
+    } catch (const std::exception& e) {
+      cudaGetLastError();
+      if (prm.verbose) fprintf(stderr, "dense partition blocks not built on level %d (%s): the sweep kernels stay\n", l, e.what());
+      L.use_blockdense = false;
+      L.bdS1.release(); L.bdGp.release(); L.bdS2.release();
+    }
+  }
 }
 
 void Solver::destroy_cublas() {

@@ -59,18 +59,35 @@ __device__ __forceinline__ int owner_of(const Ranges& rg, int i) {
 // col[ptr[i] .. ptr[i+1]) (ptr == null: the single entry col[i]); an entry j is first mapped through
 // colmap when given (e.g. external -> internal numbering); it is MINE when it falls into [myb, mye).
 // flags[q * nown + (j - myb)] = 1 when a row owned by q != me references my value j.
+// rowmask (optional): bit q set <=> rank q consumes row i (its owner AND the ranks that hold it as a ghost row); without
+// it the only consumer of a row is its owner.
 __global__ void mark_needed_kernel(int nrows, const int* __restrict__ ptr, const int* __restrict__ col, const int* __restrict__ colmap,
-                                   Ranges rowOwner, int me, int myb, int mye, int* __restrict__ flags) {
+                                   Ranges rowOwner, const unsigned* __restrict__ rowmask, int me, int myb, int mye,
+                                   int* __restrict__ flags) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nrows) return;
-  int q = owner_of(rowOwner, i);
-  if (q == me) return;
+  unsigned consumers = rowmask ? rowmask[i] : (1u << owner_of(rowOwner, i));
+  consumers &= ~(1u << me);
+  if (!consumers) return;
   int nown = mye - myb;
   const int e0 = ptr ? ptr[i] : i, e1 = ptr ? ptr[i + 1] : i + 1;
   for (int e = e0; e < e1; e++) {
     int j = col[e];
     if (colmap) j = colmap[j];
-    if (j >= myb && j < mye) flags[(size_t)q * nown + (j - myb)] = 1;
+    if (j >= myb && j < mye)
+      for (unsigned m = consumers; m; m &= m - 1) flags[(size_t)(__ffs(m) - 1) * nown + (j - myb)] = 1;
+  }
+}
+// which ranks consume a row of a sharded level: its owner and the owners of the operator rows that reference it (exactly
+// the relation the operator-halo lists are built from; no symmetry assumption).  mask must be zeroed.
+__global__ void consumer_mask_kernel(int n, const int* __restrict__ ptr, const int* __restrict__ col, Ranges rows, unsigned* __restrict__ mask) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned me = 1u << owner_of(rows, i);
+  atomicOr(&mask[i], me);
+  for (int e = ptr[i]; e < ptr[i + 1]; e++) {
+    const int j = col[e];
+    if (!(mask[j] & me)) atomicOr(&mask[j], me);
   }
 }
 __global__ void fill_list_kernel(long long total, int nown, int myb, const int* __restrict__ flags, const int* __restrict__ pos,
@@ -84,9 +101,10 @@ __global__ void fill_list_kernel(long long total, int nown, int myb, const int* 
 
 // what MY consumer rows [r0, r1) need from the others: flags over the (mapped) column space
 __global__ void mark_needs_kernel(int r0, int r1, const int* __restrict__ ptr, const int* __restrict__ col, const int* __restrict__ colmap,
-                                  int myb, int mye, int* __restrict__ flags) {
+                                  const unsigned* __restrict__ rowmask, int me, int myb, int mye, int* __restrict__ flags) {
   int i = r0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= r1) return;
+  if (rowmask && !(rowmask[i] >> me & 1u)) return;  // consumer rows = all rows whose mask names me (own + ghost rows)
   const int e0 = ptr ? ptr[i] : i, e1 = ptr ? ptr[i + 1] : i + 1;
   for (int e = e0; e < e1; e++) {
     int j = col[e];
@@ -105,7 +123,8 @@ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // One exchange: `nrows` consumer rows (owner by rowOwner) reference values (col / colmap) of which
 // [myb, mye) are mine; the list stores valmap[j] (or j) = index into the exchanged vector.
 void build_push_list(const Ctx& c, int nranks, int me, int nrows, const int* ptr, const int* col, const int* colmap, const Ranges& rowOwner,
-                     const Ranges& colOwner, int myb, int mye, const int* valmap, Solver::PushList& out) {
+                     const Ranges& colOwner, int myb, int mye, const int* valmap, Solver::PushList& out,
+                     const unsigned* rowmask = nullptr) {
   cudaStream_t s = c.stream;
   const int nown = std::max(mye - myb, 0);
   out.total = 0;
@@ -114,7 +133,7 @@ void build_push_list(const Ctx& c, int nranks, int me, int nrows, const int* ptr
     const size_t m = (size_t)nranks * nown;
     IBuf flags(m, s), pos(m, s);
     flags.zero();
-    mark_needed_kernel<<<cdiv(nrows, 256), 256, 0, s>>>(nrows, ptr, col, colmap, rowOwner, me, myb, mye, flags);
+    mark_needed_kernel<<<cdiv(nrows, 256), 256, 0, s>>>(nrows, ptr, col, colmap, rowOwner, rowmask, me, myb, mye, flags);
     inclusive_scan_i32(flags, pos, m, s);
     for (int q = 0; q < nranks; q++) ptr_h[q + 1] = pos.read((size_t)(q + 1) * nown - 1);
     out.total = ptr_h[nranks];
@@ -128,14 +147,14 @@ void build_push_list(const Ctx& c, int nranks, int me, int nrows, const int* ptr
   out.ptr.from_host(ptr_h.data(), nranks + 1);
   // what the peers send me: the values my own consumer rows reference, ascending in the owner's numbering (the
   // order in which the owner's list sends them), grouped by owner
-  const int r0 = rowOwner.b[me], r1 = rowOwner.b[me + 1];
+  const int r0 = rowmask ? 0 : rowOwner.b[me], r1 = rowmask ? nrows : rowOwner.b[me + 1];
   const int ncols = colOwner.b[nranks];
   out.rtotal = 0;
   for (int q = 0; q <= nranks; q++) out.rptr[q] = 0;
   if (r1 > r0 && ncols > 0) {
     IBuf flags(ncols, s), pos(ncols, s);
     flags.zero();
-    mark_needs_kernel<<<cdiv(r1 - r0, 256), 256, 0, s>>>(r0, r1, ptr, col, colmap, myb, mye, flags);
+    mark_needs_kernel<<<cdiv(r1 - r0, 256), 256, 0, s>>>(r0, r1, ptr, col, colmap, rowmask, me, myb, mye, flags);
     inclusive_scan_i32(flags, pos, ncols, s);
     for (int q = 1; q <= nranks; q++) out.rptr[q] = colOwner.b[q] > 0 ? pos.read((size_t)colOwner.b[q] - 1) : 0;
     out.rtotal = out.rptr[nranks];
@@ -285,10 +304,15 @@ void Solver::dist_prepare(int rank, int nranks) {
       const Ranges rowsN = make_ranges(Dn.rbeg, nranks);
       // down: internal row i of the next level reads bc[ipermutation[i]]; I computed the entries of my aggregates
       build_push_list(ctx, nranks, rank, Ln.n, nullptr, Ln.agg.ipermutation, nullptr, rowsN, aggs, D.abeg[rank], D.abeg[rank + 1], nullptr, D.sendDown);
-      // up: a prolongator row (owner by this level's rows) references xc[e], e external on the next level; mine when
-      // permutation[e] is one of my next-level rows; the pushed index is e = ipermutation[internal]
+      // up: a prolongator row references xc[e], e external on the next level; mine when permutation[e] is one of my
+      // next-level rows; the pushed index is e = ipermutation[internal].  The consumers of a row are its owner AND the
+      // ranks that hold it as a ghost row: those apply the coarse correction to their ghost copy themselves
+      // (x_ghost += P_ghost xc, bit-identical to the owner's update), which saves the halo exchange after the prolongation.
+      DevBuf<unsigned> cmask(L.n, s);
+      cmask.zero();
+      consumer_mask_kernel<<<cdiv(L.n, 256), 256, 0, s>>>(L.n, L.A.ptr, L.A.col, rows, cmask);
       build_push_list(ctx, nranks, rank, L.n, L.P.ptr, L.P.col, Ln.agg.permutation, rows, rowsN, Dn.rbeg[rank], Dn.rbeg[rank + 1], Ln.agg.ipermutation,
-                      D.sendUp);
+                      D.sendUp, cmask);
     }
   }
   // 3. user-numbering range that covers my fine rows (host-buffer solves move only this slice over PCIe)

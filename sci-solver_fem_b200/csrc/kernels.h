@@ -13,6 +13,8 @@ void launch_spmv_sell(const Ctx& c, const Sell& A, const double* x, double* y, i
 void launch_spmv_dot_sell(const Ctx& c, const Sell& A, const double* x, double* y, double* partials, PcgScalars* sc, RowRange rr = RowRange());
 // multi-GPU exchanges over NVLink peer memory (cycle.cu): flag-in-data exchange of list entries of `src` (mine) into `dst`
 // (what the peers send me); fenced all-gather of a slice (end of a solve)
+// y[r] += (A x)[r] for the listed rows (thread per row; ghost rows of a sharded level)
+void launch_spmv_list_add(const Ctx& c, const DCsr& A, const int* rows, int count, const double* x, double* y, const int* done);
 void launch_ll_exchange(const Ctx& c, const LLXchg& x, const double* src, double* dst, const int* done);
 void launch_push_all(const Ctx& c, int begin, int end, const double* src, const PeerPtrs& dst);
 // y = A x and the dot product x.y folded into the same pass; the last CTA finishes

@@ -278,6 +278,9 @@ void Solver::setup() {
     double t0 = now_ms();
     build_dense_tail();
     times_ms["setup_dense_tail"] = now_ms() - t0;
+    t0 = now_ms();
+    build_block_smoothers();
+    times_ms["setup_block_smoothers"] = now_ms() - t0;
   }
   toc("setup");
   has_setup = true;
@@ -372,11 +375,15 @@ void Solver::vcycle(int lev, const double* b_src, const int* gather, double* x_d
   if (Dn) exchange(lev, kUp, L.xc, L.xc, done);
   if (L.sP.ready()) launch_spmv_sell(ctx, L.sP, L.xc, L.x, 2, nullptr, done, "prolong_add", rr);
   else launch_spmv(ctx, L.P, L.xc, L.x, 2, nullptr, done, "prolong_add", rr);      // x += P xc
+  // sharded level: the ghost copies of x (they hold the neighbours' x after pre-smoothing) get the same correction here,
+  // bit-identical to what their owners compute — no halo exchange after the prolongation
+  static const bool ghost_prolong = !(getenv("FSB_GHOST_PROLONG") && atoi(getenv("FSB_GHOST_PROLONG")) == 0);  // tuning knob
+  if (D && ghost_prolong) launch_spmv_list_add(ctx, L.P, DL->sendA.ridx, DL->sendA.rtotal, L.xc, L.x, done);
   double* xin = L.x;
   double* xtmp = L.x2;
   for (int rel = 0; rel < prm.postRelaxes; rel++) {
     bool lastpass = (rel == prm.postRelaxes - 1);
-    if (D) exchange(lev, kXPost, xin, xin, done);
+    if (D && !ghost_prolong) exchange(lev, kXPost, xin, xin, done);
     if (L.sAout.ready()) launch_spmv_sell(ctx, L.sAout, xin, L.r, 1, b_eff, done, "bprime", rr);
     else launch_spmv(ctx, L.Aout, xin, L.r, 1, b_eff, done, "bprime", rr);         // b' = b - A_out x (x frozen for this pass)
     if (lastpass) launch_smooth(ctx, L, L.r, nullptr, nullptr, xin, w, prm.postInnerIters, scatter ? nullptr : x_dst, scatter, scatter ? x_dst : nullptr, nullptr, done, D);
@@ -396,11 +403,15 @@ void Solver::apply_matrix(const double* x, double* y) {
 
 void Solver::spmv_fine(const double* x, double* y) { launch_spmv(ctx, levels.at(0).A, x, y, 0, nullptr, nullptr, "spmv"); FSB_CUDA(cudaStreamSynchronize(ctx.stream)); }
 
-// the dense tail encodes the smoother parameters: rebuild it when they changed since setup()
+// the dense tail and the dense partition blocks encode the smoother parameters: rebuild them when they changed since setup()
 void Solver::ensure_dense_tail() {
-  if (tail_level_ >= 0 && (tail_key_[0] != prm.preInnerIters || tail_key_[1] != prm.postInnerIters || tail_key_[2] != prm.postRelaxes ||
+  bool dense = tail_level_ >= 0;
+  for (const auto& L : levels) dense = dense || L.use_blockdense;
+  // (also when the blocks were skipped because of postRelaxes_ != 1 and it is 1 now)
+  if ((dense || tail_key_[2] != prm.postRelaxes) && (tail_key_[0] != prm.preInnerIters || tail_key_[1] != prm.postInnerIters || tail_key_[2] != prm.postRelaxes ||
                            tail_key_[3] != prm.smootherWeight)) {
     build_dense_tail();
+    build_block_smoothers();
     destroy_graph();
   }
 }

@@ -83,6 +83,15 @@ struct LevelData {
   long long ellSlots = 0;         // stored entries (incl. padding)
   DBuf ellval;
   DevBuf<unsigned short> ellcol;  // position of the column in the partition's sorted order; bit 15: copy B of the x tile
+  // dense partition blocks (dense_tail.cu: build_block_smoother): on a level with few, small partitions the nu sweeps of a
+  // smoothing stage are latency (one barrier-separated pass per sweep), but the stage is a fixed linear map per partition:
+  //   pre  x = S(nu1) b          post  x = G^nu2 x_in + S(nu2-1) b'
+  // so the three m x m blocks per partition are formed once at setup and a stage is ONE pass of small dense GEMVs
+  bool use_blockdense = false;
+  DBuf bdS1, bdGp, bdS2;          // packed row-major blocks, partition p at bdOff[p]
+  DevBuf<long long> bdOff;        // nparts + 1
+  IBuf bdWork;                    // per CTA: partition, first local row (2 ints)
+  int bdCtas = 0;
   IBuf xadj, adj;     // graph handed to the aggregator (external numbering)
   DBuf b, x, x2, r;   // work vectors, internal numbering
   DBuf bc, xc;        // restricted residual / coarse correction, external numbering of level l+1
@@ -203,6 +212,7 @@ class Solver {
   double tail_key_[4] = {0, 0, 0, 0};    // smoother parameters Mtail was built for
   void* cublas_ = nullptr;
   void build_dense_tail();
+  void build_block_smoothers();          // dense partition blocks of the small levels above the tail
   void ensure_dense_tail();
   void destroy_cublas();
   bool has_setup = false;

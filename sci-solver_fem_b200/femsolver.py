@@ -49,7 +49,7 @@ def load_library():
         "fsb_get_matrix_csr": (ci, [vp, vp, vp, vp]), "fsb_set_matrix_values": (ci, [vp, vp]),
         "fsb_set_matrix_csr": (ci, [vp, ci, cll, vp, vp, vp]),
         "fsb_setup": (ci, [vp]), "fsb_num_levels": (ci, [vp]), "fsb_level_rows": (ci, [vp, ci]), "fsb_level_nnz": (cll, [vp, ci]),
-        "fsb_level_int": (cll, [vp, ci, cs, vp, cll]), "fsb_level_val": (cll, [vp, ci, cs, vp, cll]),
+        "fsb_level_stat": (cll, [vp, ci, cs]), "fsb_level_int": (cll, [vp, ci, cs, vp, cll]), "fsb_level_val": (cll, [vp, ci, cs, vp, cll]),
         "fsb_solve": (ci, [vp, vp, vp, C.POINTER(ci), C.POINTER(cd)]),
         "fsb_solve_device": (ci, [vp, vp, vp, C.POINTER(ci), C.POINTER(cd)]),
         "fsb_solve_fem": (ci, [vp, vp, vp, C.POINTER(ci), C.POINTER(cd)]),
@@ -75,7 +75,7 @@ EXPORTED_SYMBOLS = (
     "fsb_version fsb_device_count fsb_create fsb_destroy fsb_last_error fsb_set_param fsb_get_param fsb_set_tet_mesh "
     "fsb_set_tri_mesh fsb_set_tet_mesh_device fsb_set_tri_mesh_device fsb_assemble fsb_matrix_rows fsb_matrix_nnz "
     "fsb_get_matrix_csr fsb_set_matrix_values fsb_set_matrix_csr fsb_setup fsb_num_levels fsb_level_rows fsb_level_nnz "
-    "fsb_level_int fsb_level_val fsb_solve fsb_solve_device fsb_solve_fem fsb_resid_history fsb_spmv_fine_device "
+    "fsb_level_stat fsb_level_int fsb_level_val fsb_solve fsb_solve_device fsb_solve_fem fsb_resid_history fsb_spmv_fine_device "
     "fsb_precondition_device fsb_time_ms fsb_last_launches fsb_stream fsb_tet_mass_integrals fsb_tri_quadrature "
     "fsb_profile_report fsb_dist_prepare fsb_dist_blob fsb_dist_blob_bytes fsb_dist_connect fsb_dist_disconnect fsb_dist_ranges fsb_dist_level_ranges fsb_dist_info "
     "fsb_split_by_weight fsb_apply_matrix_device fsb_apply_matrix").split()
@@ -324,6 +324,9 @@ class FEMSolver:
         return out
 
     # ------------------------------------------------------------------ stage 4: sharded solve
+    def level_stat(self, level: int, name: str) -> int:
+        return int(self._L.fsb_level_stat(self._h, int(level), name.encode()))
+
     def dist_connect(self, rank: int, world: int, allgather):
         """Switches the PCG solve to the sharded mode.  `allgather(bytes) -> list[bytes]` exchanges the ranks'
         connection records (IPC handle + receive-buffer layout) in rank order (see exchange_handles_torch)."""

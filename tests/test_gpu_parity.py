@@ -307,6 +307,32 @@ def test_dense_tail_equals_the_kernel_cycle(monkeypatch):
     assert rel(xa2, xb2) <= 1e-12
 
 
+def test_dense_partition_blocks_equal_the_sweep_kernels(monkeypatch):
+    """A level with few, small partitions above the dense tail applies its smoothing stages as precomputed dense blocks
+    per partition (S(nu1); G^nu2 and S(nu2-1): csrc/dense_tail.cu build_block_smoothers).  Those blocks are the sweeps' own
+    linear maps, so switching them off (FSB_BLOCK_DENSE=0) must give the same iterates up to rounding — also after the
+    smoother parameters changed (blocks rebuilt lazily)."""
+    v, t = kuhn(60)
+    b = egg_carton(v) + 0.25
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("FSB_BLOCK_DENSE", mode)
+        s = make_gpu(v, t, **PCG)
+        s.setup()
+        kinds = [s.level_stat(l, "smoother") for l in range(s.num_levels())]
+        assert (4 in kinds) == (mode == "1"), kinds
+        x = s.solve(np.zeros_like(b), b)
+        h = np.array(s.resid_history())
+        s.preInnerIters_, s.postInnerIters_, s.smootherWeight_ = 3, 2, 0.9   # rebuilt lazily at the next solve
+        x2 = s.solve(np.zeros_like(b), b)
+        out[mode] = (x, s.iterations, h, x2, np.array(s.resid_history()))
+    (xa, ita, ha, xa2, ha2), (xb, itb, hb, xb2, hb2) = out["0"], out["1"]
+    assert len(ha) == len(hb) and np.allclose(ha, hb, rtol=1e-8)
+    assert rel(xa, xb) <= 1e-12
+    assert len(ha2) == len(hb2) and np.allclose(ha2, hb2, rtol=1e-8)
+    assert rel(xa2, xb2) <= 1e-12
+
+
 def _golden_cases():
     import importlib.util, os
     spec = importlib.util.spec_from_file_location("make_oracle_golden", os.path.join(os.path.dirname(__file__), "golden", "make_oracle_golden.py"))
