@@ -948,22 +948,50 @@ __global__ void __launch_bounds__(256) smooth_blockdense_kernel(const int* __res
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int lr = lr0 + warp; lr < min(lr0 + ROWS, m); lr += 8) {
-    const double* A = (x_in ? S2 : S1) + base + (size_t)lr * m;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  // a warp owns ROWS / 8 = 4 consecutive rows and streams them together: 4 (8 in the post stage) independent row
+  // streams per lane, two columns each in flight; every row sum is reduced in a fixed order
+  constexpr int RW = ROWS / 8;
+  const int lrw = lr0 + warp * RW;
+  double acc[RW][2];
+#pragma unroll
+  for (int j = 0; j < RW; j++) { acc[j][0] = 0.0; acc[j][1] = 0.0; }
+  const int nrow = max(0, min(RW, m - lrw));  // rows of this warp that exist
+  {
+    const double* A = (x_in ? S2 : S1) + base + (size_t)lrw * m;
     int c = lane;
-    for (; c + 96 < m; c += 128) { s0 += A[c] * sb[c]; s1 += A[c + 32] * sb[c + 32]; s2 += A[c + 64] * sb[c + 64]; s3 += A[c + 96] * sb[c + 96]; }
-    for (; c < m; c += 32) s0 += A[c] * sb[c];
-    if (x_in) {
-      const double* G = Gp + base + (size_t)lr * m;
-      c = lane;
-      for (; c + 96 < m; c += 128) { s0 += G[c] * sx[c]; s1 += G[c + 32] * sx[c + 32]; s2 += G[c + 64] * sx[c + 64]; s3 += G[c + 96] * sx[c + 96]; }
-      for (; c < m; c += 32) s0 += G[c] * sx[c];
+    for (; c + 32 < m; c += 64) {
+      const double v0 = sb[c], v1 = sb[c + 32];
+#pragma unroll
+      for (int j = 0; j < RW; j++)
+        if (j < nrow) { acc[j][0] += A[(size_t)j * m + c] * v0; acc[j][1] += A[(size_t)j * m + c + 32] * v1; }
     }
-    const double s = warp_sum((s0 + s1) + (s2 + s3));
-    if (lane == 0) {
-      if (x_out) x_out[r0 + lr] = s;
-      if (scatter) x_ext[scatter[r0 + lr]] = s;
+    if (c < m) {
+      const double v0 = sb[c];
+#pragma unroll
+      for (int j = 0; j < RW; j++) if (j < nrow) acc[j][0] += A[(size_t)j * m + c] * v0;
+    }
+  }
+  if (x_in) {
+    const double* G = Gp + base + (size_t)lrw * m;
+    int c = lane;
+    for (; c + 32 < m; c += 64) {
+      const double v0 = sx[c], v1 = sx[c + 32];
+#pragma unroll
+      for (int j = 0; j < RW; j++)
+        if (j < nrow) { acc[j][0] += G[(size_t)j * m + c] * v0; acc[j][1] += G[(size_t)j * m + c + 32] * v1; }
+    }
+    if (c < m) {
+      const double v0 = sx[c];
+#pragma unroll
+      for (int j = 0; j < RW; j++) if (j < nrow) acc[j][0] += G[(size_t)j * m + c] * v0;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < RW; j++) {
+    const double s = warp_sum(acc[j][0] + acc[j][1]);
+    if (lane == 0 && j < nrow) {
+      if (x_out) x_out[r0 + lrw + j] = s;
+      if (scatter) x_ext[scatter[r0 + lrw + j]] = s;
     }
   }
 }
