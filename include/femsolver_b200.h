@@ -124,6 +124,10 @@ int fsb_dist_level_ranges(const fsb_solver* s, int level, int* part_begin, int* 
 /* number of sharded levels, the host-copy slice, and per sharded level the number of values this GPU pushes per
  * exchange (4 entries per level: operator halo, residual halo, down, up; halo_values may be NULL); returns nranks */
 int fsb_dist_info(const fsb_solver* s, int* sharded_levels, int* user_lo, int* user_hi, long long* halo_values);
+/* interior ranges of sharded level `level` on this GPU (begin, end pairs; begin >= end: none): rows whose operator rows,
+ * coarse rows whose restriction rows, rows whose prolongator rows reference nothing that arrives through an exchange —
+ * their share of the consumer kernel runs while the exchange is in flight */
+int fsb_dist_interior(const fsb_solver* s, int level, int* out6);
 /* host-only helper: contiguous split of weighted partitions over nranks (out_begin has nranks+1 entries) */
 void fsb_split_by_weight(int nparts, const long long* weights, int nranks, int* out_begin);
 

@@ -305,6 +305,14 @@ int fsb_dist_info(const fsb_solver* s, int* sharded_levels, int* user_lo, int* u
   }
   return d.nranks;
 }
+int fsb_dist_interior(const fsb_solver* s, int level, int* out6) {
+  if (!s || !s->impl || !out6) return FSB_ERR_INVALID;
+  const auto& d = s->impl->dist;
+  if (level < 0 || level >= (int)d.lev.size()) return FSB_ERR_INVALID;
+  const auto& L = d.lev[level];
+  out6[0] = L.intA.begin; out6[1] = L.intA.end; out6[2] = L.intR.begin; out6[3] = L.intR.end; out6[4] = L.intP.begin; out6[5] = L.intP.end;
+  return FSB_OK;
+}
 // tools only (not part of the public header): `reps` back-to-back exchanges of channel `chan` (no compute in between, all
 // ranks must call it together) timed with CUDA events -> microseconds per exchange; chan < 0: all-reduces instead
 double fsb_dist_bench_exchange(fsb_solver* s, int chan, int reps) {

@@ -97,6 +97,8 @@ struct Ctx {
   unsigned int* dist_ticket = nullptr; // last-CTA ticket of the push kernels
   cudaStream_t side[2] = {nullptr, nullptr};  // helper streams: kernels that may run next to each other (fork/join by events)
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+  cudaStream_t xstream = nullptr;      // sharded solve: a halo exchange runs here while the interior rows of its consumer run on `stream`
+  cudaEvent_t ev_xfork = nullptr, ev_xjoin = nullptr;
 };
 
 struct RowRange { int begin = 0, end = -1; };  // end < 0: all rows

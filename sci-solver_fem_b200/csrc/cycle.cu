@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(256) sell_spmv_kernel(DistDev dist, int row_be
                                                         const int* __restrict__ col, const double* __restrict__ val,
                                                         const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ b,
                                                         double* __restrict__ partials, PcgScalars* __restrict__ sc,
-                                                        const int* __restrict__ done) {
+                                                        const int* __restrict__ done, int pprev, int finalize) {
   pdl_wait();
   __shared__ double s_warp[32];
   __shared__ int s_flag;
@@ -396,9 +396,14 @@ __global__ void __launch_bounds__(256) sell_spmv_kernel(DistDev dist, int row_be
     }
   }
   if (DOT) {
+    // The product may be split over several launches (interior rows while the halo of x is in flight, boundary rows
+    // after it): all but the last one only park their CTA sums; the last one finds `pprev` parked sums right in front
+    // of its own and finishes the fixed-order sum over all of them.
     double bs = block_sum(contrib, s_warp);
-    if (publish_partial(bs, partials, &sc->ticket[0], &s_flag)) {
-      double tot = final_sum(partials, gridDim.x, s_warp);
+    if (!finalize) {
+      if (threadIdx.x == 0) partials[blockIdx.x] = bs;
+    } else if (publish_partial(bs, partials, &sc->ticket[0], &s_flag)) {
+      double tot = final_sum(partials - pprev, gridDim.x + pprev, s_warp);
       tot = cross_sum(dist, tot);  // all-reduce over the GPUs of a sharded solve (no-op on one GPU)
       if (threadIdx.x == 0) { sc->py = tot; sc->alpha = sc->rz_old / tot; }
     }
@@ -406,22 +411,23 @@ __global__ void __launch_bounds__(256) sell_spmv_kernel(DistDev dist, int row_be
 }
 
 template <int MODE, bool DOT>
-void sell_dispatch(const Ctx& c, const Sell& A, const double* x, double* y, const double* b, double* partials, PcgScalars* sc,
-                   const int* done, const char* name, RowRange rr = RowRange()) {
-  if (A.nrows == 0) return;
+int sell_dispatch(const Ctx& c, const Sell& A, const double* x, double* y, const double* b, double* partials, PcgScalars* sc,
+                  const int* done, const char* name, RowRange rr = RowRange(), int pprev = 0, int finalize = 1) {
+  if (A.nrows == 0) return 0;
   const int r0 = rr.end >= 0 ? rr.begin : 0, r1 = rr.end >= 0 ? rr.end : A.nrows;
   g_launch_counter++;
   ProfScope ps(c, name);
   // list positions that can hold the owned rows: whole sort windows when the rows are length-sorted
   const int gran = A.window > 0 ? A.window : 32;
   const int l0 = r0 / gran * gran, l1 = std::min(A.nrows, (r1 + gran - 1) / gran * gran);
-  if (l1 <= l0 && !DOT) return;  // (an empty owned range still takes part in the all-reduce)
+  if (l1 <= l0 && !DOT) return 0;  // (an empty owned range still takes part in the all-reduce)
   static const int dot_ctas_per_sm = getenv("FSB_DOT_CTAS") ? atoi(getenv("FSB_DOT_CTAS")) : 12;  // tuning knob
   int blocks = std::max(1, cdiv(std::max(0, l1 - l0), 256));
   if (DOT) blocks = std::min(blocks, c.num_sms * dot_ctas_per_sm);
   FSB_LAUNCH((sell_spmv_kernel<MODE, DOT>), blocks, 256, 0, c.stream, c.dist, r0, r1, l0, l1, A.rowmap.size() ? A.rowmap.get() : nullptr, A.nrows,
-                                                                       A.sptr, A.col, A.val, x, y, b, partials, sc, done);
+                                                                       A.sptr, A.col, A.val, x, y, b, partials, sc, done, pprev, finalize);
   FSB_CHECK_LAUNCH();
+  return blocks;
 }
 
 // debug timestamps (tools only): one CTA stamps clock64 at phase boundaries when g_dbg_on != 0
@@ -1271,6 +1277,9 @@ void launch_spmv_sell(const Ctx& c, const Sell& A, const double* x, double* y, i
 }
 void launch_spmv_dot_sell(const Ctx& c, const Sell& A, const double* x, double* y, double* partials, PcgScalars* sc, RowRange rr) {
   sell_dispatch<0, true>(c, A, x, y, nullptr, partials, sc, &sc->done, "spmv_dot", rr);
+}
+int launch_spmv_dot_sell_part(const Ctx& c, const Sell& A, const double* x, double* y, double* partials, PcgScalars* sc, RowRange rr, int pprev, bool finalize) {
+  return sell_dispatch<0, true>(c, A, x, y, nullptr, partials + pprev, sc, &sc->done, "spmv_dot", rr, pprev, finalize ? 1 : 0);
 }
 
 void launch_spmv_list_add(const Ctx& c, const DCsr& A, const int* rows, int count, const double* x, double* y, const int* done) {

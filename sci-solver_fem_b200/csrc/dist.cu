@@ -118,7 +118,45 @@ __global__ void fill_needs_kernel(int ncols, const int* __restrict__ flags, cons
   if (j < ncols && flags[j]) list[pos[j] - 1] = valmap ? valmap[j] : j;
 }
 
+// flag[i - r0] = 1 when consumer row i of [r0, r1) references a value that is not mine (it arrives through an exchange)
+__global__ void ghost_ref_rows_kernel(int r0, int r1, const int* __restrict__ ptr, const int* __restrict__ col, const int* __restrict__ colmap,
+                                      int myb, int mye, unsigned char* __restrict__ flag) {
+  int i = r0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= r1) return;
+  unsigned char f = 0;
+  for (int e = ptr[i]; e < ptr[i + 1]; e++) {
+    int j = col[e];
+    if (colmap) j = colmap[j];
+    if (j < myb || j >= mye) { f = 1; break; }
+  }
+  flag[i - r0] = f;
+}
+
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// longest run of 1024-row blocks (globally aligned, fully inside [r0, r1)) without a ghost reference
+RowRange interior_range(const Ctx& c, int r0, int r1, const int* ptr, const int* col, const int* colmap, int myb, int mye) {
+  RowRange out;
+  out.begin = out.end = 0;
+  if (r1 - r0 < 4096) return out;
+  cudaStream_t s = c.stream;
+  DevBuf<unsigned char> flag(r1 - r0, s);
+  ghost_ref_rows_kernel<<<cdiv(r1 - r0, 256), 256, 0, s>>>(r0, r1, ptr, col, colmap, myb, mye, flag);
+  FSB_CHECK_LAUNCH();
+  std::vector<unsigned char> f = flag.to_vector();
+  const int B = 1024;
+  int best0 = 0, best1 = 0, run0 = -1;
+  for (int k = (r0 + B - 1) / B; (k + 1) * B <= r1; k++) {
+    bool clean = true;
+    for (int i = k * B; i < (k + 1) * B; i++) if (f[i - r0]) { clean = false; break; }
+    if (clean) {
+      if (run0 < 0) run0 = k * B;
+      if ((k + 1) * B - run0 > best1 - best0) { best0 = run0; best1 = (k + 1) * B; }
+    } else run0 = -1;
+  }
+  if (best1 - best0 >= (r1 - r0) / 4) { out.begin = best0; out.end = best1; }
+  return out;
+}
 
 // One exchange: `nrows` consumer rows (owner by rowOwner) reference values (col / colmap) of which
 // [myb, mye) are mine; the list stores valmap[j] (or j) = index into the exchanged vector.
@@ -313,6 +351,22 @@ void Solver::dist_prepare(int rank, int nranks) {
       consumer_mask_kernel<<<cdiv(L.n, 256), 256, 0, s>>>(L.n, L.A.ptr, L.A.col, rows, cmask);
       build_push_list(ctx, nranks, rank, L.n, L.P.ptr, L.P.col, Ln.agg.permutation, rows, rowsN, Dn.rbeg[rank], Dn.rbeg[rank + 1], Ln.agg.ipermutation,
                       D.sendUp, cmask);
+    }
+  }
+  // 2b. interior ranges of the big sharded levels: where the consumer of an exchange can start before the halo is in
+  static const int overlap_min_rows = getenv("FSB_OVERLAP_MINROWS") ? atoi(getenv("FSB_OVERLAP_MINROWS")) : 262144;  // tuning knob, 0: no overlap
+  for (int l = 0; l < nshard; l++) {
+    LevelData& L = levels[l];
+    DistLevel& D = dist.lev[l];
+    D.intA = D.intR = D.intP = RowRange();
+    D.intA.end = D.intR.end = D.intP.end = 0;
+    const int myb = D.rbeg[rank], mye = D.rbeg[rank + 1];
+    if (overlap_min_rows <= 0 || mye - myb < overlap_min_rows) continue;
+    D.intA = interior_range(ctx, myb, mye, L.Aout.ptr, L.Aout.col, nullptr, myb, mye);
+    D.intR = interior_range(ctx, D.abeg[rank], D.abeg[rank + 1], L.R.ptr, L.R.col, nullptr, myb, mye);
+    if (l + 1 < nshard) {
+      DistLevel& Dn = dist.lev[l + 1];
+      D.intP = interior_range(ctx, myb, mye, L.P.ptr, L.P.col, levels[l + 1].agg.permutation, Dn.rbeg[rank], Dn.rbeg[rank + 1]);
     }
   }
   // 3. user-numbering range that covers my fine rows (host-buffer solves move only this slice over PCIe)

@@ -11,6 +11,9 @@ void launch_spmv(const Ctx& c, const DCsr& A, const double* x, double* y, int mo
 void launch_spmv_sell(const Ctx& c, const Sell& A, const double* x, double* y, int mode, const double* b, const int* done, const char* name,
                       RowRange rr = RowRange());
 void launch_spmv_dot_sell(const Ctx& c, const Sell& A, const double* x, double* y, double* partials, PcgScalars* sc, RowRange rr = RowRange());
+// one part of a split y = A x, p.y: CTA sums parked behind the `pprev` sums of the earlier parts; the last part (finalize)
+// finishes the dot product.  Returns the number of CTA sums this part parked.
+int launch_spmv_dot_sell_part(const Ctx& c, const Sell& A, const double* x, double* y, double* partials, PcgScalars* sc, RowRange rr, int pprev, bool finalize);
 // multi-GPU exchanges over NVLink peer memory (cycle.cu): flag-in-data exchange of list entries of `src` (mine) into `dst`
 // (what the peers send me); fenced all-gather of a slice (end of a solve)
 // y[r] += (A x)[r] for the listed rows (thread per row; ghost rows of a sharded level)

@@ -28,6 +28,9 @@ Solver::Solver(int device) {
     FSB_CUDA(cudaStreamCreateWithFlags(&ctx.side[q], cudaStreamNonBlocking));
     FSB_CUDA(cudaEventCreateWithFlags(&ctx.ev_join[q], cudaEventDisableTiming));
   }
+  FSB_CUDA(cudaStreamCreateWithFlags(&ctx.xstream, cudaStreamNonBlocking));
+  FSB_CUDA(cudaEventCreateWithFlags(&ctx.ev_xfork, cudaEventDisableTiming));
+  FSB_CUDA(cudaEventCreateWithFlags(&ctx.ev_xjoin, cudaEventDisableTiming));
   // keep freed setup temporaries in the pool: setup allocates hundreds of short-lived buffers
   cudaMemPool_t pool;
   FSB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -57,6 +60,9 @@ Solver::~Solver() {
     if (ctx.ev_join[q]) cudaEventDestroy(ctx.ev_join[q]);
   }
   if (ctx.ev_fork) cudaEventDestroy(ctx.ev_fork);
+  if (ctx.xstream) { cudaStreamSynchronize(ctx.xstream); cudaStreamDestroy(ctx.xstream); }
+  if (ctx.ev_xfork) cudaEventDestroy(ctx.ev_xfork);
+  if (ctx.ev_xjoin) cudaEventDestroy(ctx.ev_xjoin);
 }
 
 void Solver::destroy_graph() {
@@ -291,8 +297,15 @@ void Solver::setup() {
 // null when b_src is already internal); the result goes to x_dst in internal numbering
 // (scatter == null) or is scattered to the external numbering through `scatter`.
 // one exchange of a sharded solve: my list entries of `src` to the peers, theirs into `dst` (cycle.cu: ll_exchange_kernel)
-void Solver::exchange_chan(int chan, const double* src, double* dst, const int* done) {
-  launch_ll_exchange(ctx, dist.chan[chan].dev, src, dst, done);
+void Solver::exchange_chan(int chan, const double* src, double* dst, const int* done, bool side_stream) {
+  if (!side_stream) { launch_ll_exchange(ctx, dist.chan[chan].dev, src, dst, done); return; }
+  // fork: the exchange runs on its own stream behind everything enqueued so far; the caller joins with ev_xjoin
+  FSB_CUDA(cudaEventRecord(ctx.ev_xfork, ctx.stream));
+  FSB_CUDA(cudaStreamWaitEvent(ctx.xstream, ctx.ev_xfork, 0));
+  Ctx cx = ctx;
+  cx.stream = ctx.xstream;
+  launch_ll_exchange(cx, dist.chan[chan].dev, src, dst, done);
+  FSB_CUDA(cudaEventRecord(ctx.ev_xjoin, ctx.xstream));
 }
 
 double Solver::dist_bench_exchange(int chan, int reps) {
@@ -323,6 +336,20 @@ double Solver::dist_bench_exchange(int chan, int reps) {
   float ms = 0;
   FSB_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
   return ms * 1e3 / reps;
+}
+
+// An exchange of vector v followed by its consumer kernel over `full` rows.  With an interior range (rows that reference
+// nothing the exchange delivers) the exchange runs on its own stream while the consumer works on the interior rows; the
+// boundary rows follow after the join.  Without one (or when `on` is false: no exchange at all) the consumer runs once.
+template <typename F>
+void Solver::with_exchange(bool on, int lev, int which, double* v, RowRange full, RowRange interior, const int* done, F&& consumer) {
+  if (!on) { consumer(full); return; }
+  if (interior.end <= interior.begin) { exchange(lev, which, v, v, done); consumer(full); return; }
+  exchange_chan(kChanLevel0 + kChanPerLevel * lev + which, v, v, done, /*side_stream=*/true);
+  consumer(interior);
+  FSB_CUDA(cudaStreamWaitEvent(ctx.stream, ctx.ev_xjoin, 0));
+  if (full.begin < interior.begin) { RowRange q; q.begin = full.begin; q.end = interior.begin; consumer(q); }
+  if (interior.end < full.end) { RowRange q; q.begin = interior.end; q.end = full.end; consumer(q); }
 }
 
 void Solver::vcycle(int lev, const double* b_src, const int* gather, double* x_dst, const int* scatter, double* /*unused*/) {
@@ -356,12 +383,15 @@ void Solver::vcycle(int lev, const double* b_src, const int* gather, double* x_d
   } else {
     // pre: x = w b/d, nu1 sweeps, r = b - A_in x - d x  (one kernel, matrix slab read once)
     launch_smooth(ctx, L, b_src, gather, gather ? L.b.get() : nullptr, nullptr, w, prm.preInnerIters, L.x, nullptr, nullptr, L.r, done, D);
-    // x across the cut (every exchange: push + signal to the peers written to + wait for the peers received from)
-    if (D) exchange(lev, kXPre, L.x, L.x, done);
-    if (L.sAout.ready()) launch_spmv_sell(ctx, L.sAout, L.x, L.r, 3, nullptr, done, "residual_out", rr);
-    else launch_spmv(ctx, L.Aout, L.x, L.r, 3, nullptr, done, "residual_out", rr);   // r -= A_out x   (preAout_kernel)
-    if (D) exchange(lev, kRes, L.r, L.r, done);                                      // r rows the peers restrict
-    launch_spmv(ctx, L.R, L.r, L.bc, 0, nullptr, done, "restrict", rrc);            // bc = R r
+    // x across the cut, overlapped with the interior rows of its consumer: r -= A_out x   (preAout_kernel)
+    with_exchange(D, lev, kXPre, L.x, rr, D ? DL->intA : RowRange(), done, [&](RowRange q) {
+      if (L.sAout.ready()) launch_spmv_sell(ctx, L.sAout, L.x, L.r, 3, nullptr, done, "residual_out", q);
+      else launch_spmv(ctx, L.Aout, L.x, L.r, 3, nullptr, done, "residual_out", q);
+    });
+    // r rows the peers restrict, overlapped with the interior coarse rows: bc = R r
+    with_exchange(D, lev, kRes, L.r, rrc, D ? DL->intR : RowRange(), done, [&](RowRange q) {
+      launch_spmv(ctx, L.R, L.r, L.bc, 0, nullptr, done, "restrict", q);
+    });
   }
   if (D) {
     // restricted residual: to the owners of the next level's rows, or — next level replicated — all-gathered
@@ -371,10 +401,12 @@ void Solver::vcycle(int lev, const double* b_src, const int* gather, double* x_d
   const int* ip = next_is_coarsest ? nullptr : levels[lev + 1].agg.ipermutation.get();
   vcycle(lev + 1, L.bc, ip, L.xc, ip, nullptr);
   profiler.cur_level = lev;
-  // coarse corrections of the next level's rows I own that the peers' prolongator rows reference
-  if (Dn) exchange(lev, kUp, L.xc, L.xc, done);
-  if (L.sP.ready()) launch_spmv_sell(ctx, L.sP, L.xc, L.x, 2, nullptr, done, "prolong_add", rr);
-  else launch_spmv(ctx, L.P, L.xc, L.x, 2, nullptr, done, "prolong_add", rr);      // x += P xc
+  // coarse corrections of the next level's rows I own that the peers' prolongator rows (and ghost rows) reference,
+  // overlapped with the rows whose prolongator entries are all mine: x += P xc
+  with_exchange(Dn, lev, kUp, L.xc, rr, Dn ? DL->intP : RowRange(), done, [&](RowRange q) {
+    if (L.sP.ready()) launch_spmv_sell(ctx, L.sP, L.xc, L.x, 2, nullptr, done, "prolong_add", q);
+    else launch_spmv(ctx, L.P, L.xc, L.x, 2, nullptr, done, "prolong_add", q);
+  });
   // sharded level: the ghost copies of x (they hold the neighbours' x after pre-smoothing) get the same correction here,
   // bit-identical to what their owners compute — no halo exchange after the prolongation
   static const bool ghost_prolong = !(getenv("FSB_GHOST_PROLONG") && atoi(getenv("FSB_GHOST_PROLONG")) == 0);  // tuning knob
@@ -431,13 +463,24 @@ void Solver::enqueue_pcg_iteration() {
   const int rb = D ? dist.lev[0].rbeg[dist.rank] : 0, re = D ? dist.lev[0].rbeg[dist.rank + 1] : n, nown = re - rb;
   RowRange rr;
   if (D) { rr.begin = rb; rr.end = re; }
-  if (levels[0].sA.ready()) launch_spmv_dot_sell(ctx, levels[0].sA, cg_p, cg_y, partials, sc, rr);
-  else launch_spmv_dot(ctx, levels[0].A, cg_p, cg_y, partials, sc);          // y = A p, alpha = rz / (p.y)
+  // y = A p, alpha = rz / (p.y).  Sharded with an interior range: p crosses the cut WHILE the interior rows are multiplied
+  const bool overlap_p = D && dist.lev[0].intA.end > dist.lev[0].intA.begin;
+  if (overlap_p) {
+    const RowRange in = dist.lev[0].intA;
+    exchange_chan(kChanP, cg_p, cg_p, &sc->done, /*side_stream=*/true);
+    int parked = launch_spmv_dot_sell_part(ctx, levels[0].sA, cg_p, cg_y, partials, sc, in, 0, false);
+    FSB_CUDA(cudaStreamWaitEvent(ctx.stream, ctx.ev_xjoin, 0));
+    RowRange lo, hi;
+    lo.begin = rb; lo.end = in.begin; hi.begin = in.end; hi.end = re;
+    parked += launch_spmv_dot_sell_part(ctx, levels[0].sA, cg_p, cg_y, partials, sc, lo, parked, false);
+    launch_spmv_dot_sell_part(ctx, levels[0].sA, cg_p, cg_y, partials, sc, hi, parked, true);
+  } else if (levels[0].sA.ready()) launch_spmv_dot_sell(ctx, levels[0].sA, cg_p, cg_y, partials, sc, rr);
+  else launch_spmv_dot(ctx, levels[0].A, cg_p, cg_y, partials, sc);
   launch_cg_update(ctx, nown, cg_x.get() + rb, cg_r.get() + rb, cg_p.get() + rb, cg_y.get() + rb, partials, sc, hist);  // x += alpha p, r -= alpha y, ||r||, test
   vcycle(0, cg_r, nullptr, cg_z, nullptr, nullptr);                          // z = M^-1 r
   launch_dot(ctx, nown, cg_r.get() + rb, cg_z.get() + rb, partials, sc, 2);  // rz_new, beta
   launch_cg_pdir(ctx, nown, cg_p.get() + rb, cg_z.get() + rb, sc, 0);        // p = z + beta p
-  if (D) exchange_chan(kChanP, cg_p, cg_p, &sc->done);  // p across the cut for the next SpMV
+  if (D && !overlap_p) exchange_chan(kChanP, cg_p, cg_p, &sc->done);  // p across the cut for the next SpMV
 }
 
 void Solver::pcg(const double* b_user, double* x_user) {
@@ -488,7 +531,7 @@ void Solver::pcg(const double* b_user, double* x_user) {
   else launch_spmv(ctx, L0.A, cg_x, cg_r, 1, cg_b, nullptr, "residual"); // r = b - A x
   vcycle(0, cg_r, nullptr, cg_z, nullptr, nullptr);                // z = M^-1 r
   launch_cg_pdir(ctx, nown, cg_p.get() + rb, cg_z.get() + rb, sc, 1);  // p = z
-  if (D) exchange_chan(kChanP, cg_p, cg_p, nullptr);
+  if (D && !(dist.lev[0].intA.end > dist.lev[0].intA.begin)) exchange_chan(kChanP, cg_p, cg_p, nullptr);  // (else: first thing of the iteration)
   launch_dot(ctx, nown, cg_r.get() + rb, cg_z.get() + rb, partials, sc, 1);  // rz_old
   FSB_CUDA(cudaStreamSynchronize(s));
 

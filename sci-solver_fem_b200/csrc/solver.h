@@ -158,6 +158,10 @@ class Solver {
                                    //   replicated — my whole slice to everybody (all-gather)
     PushList sendUp;               // coarse corrections of my next-level rows that a peer's prolongator rows reference
     size_t off_x = 0, off_r = 0, off_bc = 0, off_xc = 0;
+    // interior ranges (1024-aligned, inside this GPU's ranges): rows whose operator / prolongator rows and coarse rows whose
+    // restriction rows reference nothing that arrives through an exchange — the consumer kernel runs on them WHILE the
+    // exchange is in flight (begin >= end: no overlap on this level)
+    RowRange intA, intR, intP;
   };
   struct Channel {                 // receive buffer of one exchange site + where my segments start in the peers' buffers
     const PushList* list = nullptr;
@@ -192,7 +196,9 @@ class Solver {
   static constexpr int kDistBlobBytes = 2560;
   static_assert(sizeof(DistBlob) <= kDistBlobBytes, "blob size");
   bool sharded(int lev) const { return dist.connected && dist.nranks > 1 && cg_active_ && lev < dist.nshard; }
-  void exchange_chan(int chan, const double* src, double* dst, const int* done);
+  void exchange_chan(int chan, const double* src, double* dst, const int* done, bool side_stream = false);
+  template <typename F>
+  void with_exchange(bool on, int lev, int which, double* v, RowRange full, RowRange interior, const int* done, F&& consumer);
   void exchange(int lev, int which, const double* src, double* dst, const int* done) { exchange_chan(kChanLevel0 + kChanPerLevel * lev + which, src, dst, done); }
   PeerPtrs peers_at(size_t off) const { PeerPtrs p = {}; for (int q = 0; q < dist.nranks; q++) p.p[q] = reinterpret_cast<double*>(dist.peer[q] + off); return p; }
   std::string profile_report();        // "name level launches total_ms" lines of the last profiled solve

@@ -59,7 +59,7 @@ def load_library():
         "fsb_profile_report": (ci, [vp, vp, ci]),
         "fsb_dist_prepare": (ci, [vp, ci, ci]), "fsb_dist_blob": (ci, [vp, vp, C.POINTER(cll)]), "fsb_dist_blob_bytes": (ci, []),
         "fsb_dist_connect": (ci, [vp, vp]), "fsb_dist_disconnect": (ci, [vp]), "fsb_dist_ranges": (ci, [vp, vp, vp, vp]),
-        "fsb_dist_level_ranges": (ci, [vp, ci, vp, vp, vp]), "fsb_dist_info": (ci, [vp, vp, vp, vp, vp]),
+        "fsb_dist_level_ranges": (ci, [vp, ci, vp, vp, vp]), "fsb_dist_info": (ci, [vp, vp, vp, vp, vp]), "fsb_dist_interior": (ci, [vp, ci, vp]),
         "fsb_split_by_weight": (None, [ci, vp, ci, vp]),
         "fsb_tet_mass_integrals": (None, [vp]), "fsb_tri_quadrature": (None, [vp, vp, vp, vp]),
     }
@@ -77,7 +77,7 @@ EXPORTED_SYMBOLS = (
     "fsb_get_matrix_csr fsb_set_matrix_values fsb_set_matrix_csr fsb_setup fsb_num_levels fsb_level_rows fsb_level_nnz "
     "fsb_level_stat fsb_level_int fsb_level_val fsb_solve fsb_solve_device fsb_solve_fem fsb_resid_history fsb_spmv_fine_device "
     "fsb_precondition_device fsb_time_ms fsb_last_launches fsb_stream fsb_tet_mass_integrals fsb_tri_quadrature "
-    "fsb_profile_report fsb_dist_prepare fsb_dist_blob fsb_dist_blob_bytes fsb_dist_connect fsb_dist_disconnect fsb_dist_ranges fsb_dist_level_ranges fsb_dist_info "
+    "fsb_profile_report fsb_dist_prepare fsb_dist_blob fsb_dist_blob_bytes fsb_dist_connect fsb_dist_disconnect fsb_dist_ranges fsb_dist_level_ranges fsb_dist_info fsb_dist_interior "
     "fsb_split_by_weight fsb_apply_matrix_device fsb_apply_matrix").split()
 
 
@@ -357,8 +357,14 @@ class FEMSolver:
         ns, lo, hi = C.c_int(0), C.c_int(0), C.c_int(0)
         hv = np.zeros(4 * 16, dtype=np.int64)
         self._L.fsb_dist_info(self._h, C.byref(ns), C.byref(lo), C.byref(hi), _p(hv))
+        interior = []
+        for l in range(ns.value):
+            o = np.zeros(6, dtype=np.int32)
+            self._L.fsb_dist_interior(self._h, l, _p(o))
+            interior.append({"operator_rows": [int(o[0]), int(o[1])], "restriction_rows": [int(o[2]), int(o[3])], "prolongator_rows": [int(o[4]), int(o[5])]})
         return {"sharded_levels": ns.value, "user_range": (lo.value, hi.value),
-                "halo_values": [dict(zip(("operator", "residual", "down", "up"), map(int, hv[4 * l: 4 * l + 4]))) for l in range(ns.value)]}
+                "halo_values": [dict(zip(("operator", "residual", "down", "up"), map(int, hv[4 * l: 4 * l + 4]))) for l in range(ns.value)],
+                "interior_ranges": interior}
 
     def apply_matrix(self, x):
         """y = A x with the assembled (user-ordered) matrix; host vectors, the product runs on the GPU."""
