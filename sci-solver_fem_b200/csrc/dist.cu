@@ -362,6 +362,9 @@ void Solver::dist_prepare(int rank, int nranks) {
     D.intA.end = D.intR.end = D.intP.end = 0;
     const int myb = D.rbeg[rank], mye = D.rbeg[rank + 1];
     if (overlap_min_rows <= 0 || mye - myb < overlap_min_rows) continue;
+    // test knob: only the odd ranks split their consumers (GPUs decide on their interior ranges independently — mixed
+    // decisions must work: every exchange sits at the same point of the sequence on every rank, whatever stream it runs on)
+    if (getenv("FSB_OVERLAP_ODD_RANKS") && atoi(getenv("FSB_OVERLAP_ODD_RANKS")) != 0 && (rank & 1) == 0) continue;
     D.intA = interior_range(ctx, myb, mye, L.Aout.ptr, L.Aout.col, nullptr, myb, mye);
     D.intR = interior_range(ctx, D.abeg[rank], D.abeg[rank + 1], L.R.ptr, L.R.col, nullptr, myb, mye);
     if (l + 1 < nshard) {

@@ -463,7 +463,9 @@ void Solver::enqueue_pcg_iteration() {
   const int rb = D ? dist.lev[0].rbeg[dist.rank] : 0, re = D ? dist.lev[0].rbeg[dist.rank + 1] : n, nown = re - rb;
   RowRange rr;
   if (D) { rr.begin = rb; rr.end = re; }
-  // y = A p, alpha = rz / (p.y).  Sharded with an interior range: p crosses the cut WHILE the interior rows are multiplied
+  // y = A p, alpha = rz / (p.y).  Sharded: p crosses the cut first — on EVERY rank at this point of the sequence (an
+  // exchange that one rank issues before and another after an all-reduce would be a circular wait) — and, where this GPU
+  // has an interior range, WHILE the interior rows are multiplied.
   const bool overlap_p = D && dist.lev[0].intA.end > dist.lev[0].intA.begin;
   if (overlap_p) {
     const RowRange in = dist.lev[0].intA;
@@ -474,13 +476,15 @@ void Solver::enqueue_pcg_iteration() {
     lo.begin = rb; lo.end = in.begin; hi.begin = in.end; hi.end = re;
     parked += launch_spmv_dot_sell_part(ctx, levels[0].sA, cg_p, cg_y, partials, sc, lo, parked, false);
     launch_spmv_dot_sell_part(ctx, levels[0].sA, cg_p, cg_y, partials, sc, hi, parked, true);
-  } else if (levels[0].sA.ready()) launch_spmv_dot_sell(ctx, levels[0].sA, cg_p, cg_y, partials, sc, rr);
-  else launch_spmv_dot(ctx, levels[0].A, cg_p, cg_y, partials, sc);
+  } else {
+    if (D) exchange_chan(kChanP, cg_p, cg_p, &sc->done);
+    if (levels[0].sA.ready()) launch_spmv_dot_sell(ctx, levels[0].sA, cg_p, cg_y, partials, sc, rr);
+    else launch_spmv_dot(ctx, levels[0].A, cg_p, cg_y, partials, sc);
+  }
   launch_cg_update(ctx, nown, cg_x.get() + rb, cg_r.get() + rb, cg_p.get() + rb, cg_y.get() + rb, partials, sc, hist);  // x += alpha p, r -= alpha y, ||r||, test
   vcycle(0, cg_r, nullptr, cg_z, nullptr, nullptr);                          // z = M^-1 r
   launch_dot(ctx, nown, cg_r.get() + rb, cg_z.get() + rb, partials, sc, 2);  // rz_new, beta
   launch_cg_pdir(ctx, nown, cg_p.get() + rb, cg_z.get() + rb, sc, 0);        // p = z + beta p
-  if (D && !overlap_p) exchange_chan(kChanP, cg_p, cg_p, &sc->done);  // p across the cut for the next SpMV
 }
 
 void Solver::pcg(const double* b_user, double* x_user) {
@@ -531,7 +535,7 @@ void Solver::pcg(const double* b_user, double* x_user) {
   else launch_spmv(ctx, L0.A, cg_x, cg_r, 1, cg_b, nullptr, "residual"); // r = b - A x
   vcycle(0, cg_r, nullptr, cg_z, nullptr, nullptr);                // z = M^-1 r
   launch_cg_pdir(ctx, nown, cg_p.get() + rb, cg_z.get() + rb, sc, 1);  // p = z
-  if (D && !(dist.lev[0].intA.end > dist.lev[0].intA.begin)) exchange_chan(kChanP, cg_p, cg_p, nullptr);  // (else: first thing of the iteration)
+  // (sharded: p crosses the cut as the first thing of every iteration)
   launch_dot(ctx, nown, cg_r.get() + rb, cg_z.get() + rb, partials, sc, 1);  // rz_old
   FSB_CUDA(cudaStreamSynchronize(s));
 

@@ -65,7 +65,7 @@ def test_sharded_solve_matches_single_gpu(world, all_levels):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("all_levels", [0, 1, 2])
+@pytest.mark.parametrize("all_levels", [0, 1, 2, 3])
 def test_sharded_solve_two_ranks_on_one_gpu(all_levels):
     """The sharded code path on a ONE-GPU box: two processes time-slice cuda:0 and exchange through CUDA IPC
     exactly as they would over NVLink (slow — every cross-rank wait costs a time slice — but it is the same
@@ -73,7 +73,9 @@ def test_sharded_solve_two_ranks_on_one_gpu(all_levels):
     env = {"FSB_DIST_SAME_GPU": "1"}
     if all_levels:
         env.update({"FSB_SHARD_MINROWS": "1", "FSB_DENSE_TAIL": "0", "FSB_EXPECT_SHARDED_LEVELS": "2"})
-    if all_levels == 2:  # also the interior / boundary split: exchanges on their own stream next to the interior rows of their consumers
+    if all_levels >= 2:  # also the interior / boundary split: exchanges on their own stream next to the interior rows of their consumers
         env.update({"FSB_OVERLAP_MINROWS": "1", "FSB_EXPECT_OVERLAP": "1"})
-    r = launch(2, ["gpu", "40" if all_levels == 2 else "32"], 1200, env)
+    if all_levels == 3:  # ... on one of the two ranks only (GPUs decide independently; the exchange sequence must stay uniform)
+        env.update({"FSB_OVERLAP_ODD_RANKS": "1", "FSB_EXPECT_OVERLAP": "odd"})
+    r = launch(2, ["gpu", "40" if all_levels >= 2 else "32"], 1200, env)
     assert r.returncode == 0 and "GPU_DIST_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-6000:]
