@@ -353,8 +353,12 @@ void Solver::dist_prepare(int rank, int nranks) {
                       D.sendUp, cmask);
     }
   }
-  // 2b. interior ranges of the big sharded levels: where the consumer of an exchange can start before the halo is in
-  static const int overlap_min_rows = getenv("FSB_OVERLAP_MINROWS") ? atoi(getenv("FSB_OVERLAP_MINROWS")) : 262144;  // tuning knob, 0: no overlap
+  // 2b. interior ranges of the big sharded levels: where the consumer of an exchange can start before the halo is in.
+  // OFF by default (0): measured on 8 B200 with the ~100 M-tet cube (2.1 M rows per GPU, interior = 57 % of the rows) the
+  // split costs more than it hides — 33.5 ms per solve with it, 32.3 ms without (profiles/r2_bench_cube255_8gpu*.json): an
+  // exchange is ~14 us, while cutting a 35-100 us streaming kernel into three launches adds two ramps and two tails.
+  // FSB_OVERLAP_MINROWS=<rows per GPU> switches it on for levels at least that large.
+  static const int overlap_min_rows = getenv("FSB_OVERLAP_MINROWS") ? atoi(getenv("FSB_OVERLAP_MINROWS")) : 0;
   for (int l = 0; l < nshard; l++) {
     LevelData& L = levels[l];
     DistLevel& D = dist.lev[l];
