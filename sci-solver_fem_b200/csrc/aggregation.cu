@@ -369,10 +369,18 @@ __global__ void induced_offsets(int size, const uint64_t* __restrict__ u, int* _
   if (last) xout[value + 1] = idx;
 }
 
+__global__ void count_nonmonotone(int n, const int* __restrict__ off, int* __restrict__ bad) {
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a < n && off[a + 1] < off[a]) atomicAdd(bad, 1);
+}
+
 // getInducedGraph (misHelpers.cu:1078-1107).  As upstream, the first unique pair is assumed to
-// be the (-1,-1) marker and is dropped unconditionally.
+// be the (-1,-1) marker and is dropped unconditionally.  Upstream silently builds non-monotone offsets when an
+// aggregate has no edge to any other aggregate (a vertex no element connects to the rest of the mesh, or a small
+// disconnected component: findPartIndicesNegStartKernel never writes its offset); here that is an error the caller sees.
 void induced_graph(const Ctx& c, int n, const int* xadj, const int* adj, int nedges, const int* label, int nlabels, IBuf& xout, IBuf& aout) {
   cudaStream_t s = c.stream;
+  if (nedges <= 0) throw std::invalid_argument("aggregation: the graph of this level has no edges (every vertex is isolated)");
   DevBuf<uint64_t> k0(nedges, s), k1(nedges, s);
   induced_pairs<<<cdiv(n, 256), 256, 0, s>>>(n, xadj, adj, label, k0);
   sort_keys_u64(k0, k1, nedges, 32 + bits_for(nlabels), s);
@@ -391,8 +399,13 @@ void induced_graph(const Ctx& c, int n, const int* xadj, const int* adj, int ned
   if (size > 1) induced_offsets<<<cdiv(size - 1, 256), 256, 0, s>>>(size, k0, xout, aout);
   int lastv = size - 1;
   FSB_CUDA(cudaMemcpyAsync(xout.get() + (maxPart + 1), &lastv, sizeof(int), cudaMemcpyHostToDevice, s));
-  FSB_CUDA(cudaStreamSynchronize(s));
+  IBuf bad(1, s);
+  bad.zero();
+  count_nonmonotone<<<cdiv(maxPart + 1, 256), 256, 0, s>>>(maxPart + 1, xout, bad);
   FSB_CHECK_LAUNCH();
+  if (bad.read(0) != 0 || maxPart + 1 != nlabels)
+    throw std::invalid_argument("aggregation: an aggregate has no edge to the rest of the graph (the mesh has a vertex that no element "
+                                "connects to the others, or a small disconnected component); upstream builds a corrupt coarse graph here");
 }
 
 // ---------------------------------------------------------------- small index kernels
@@ -475,7 +488,7 @@ void compute_permutation(const Ctx& c, int n, const int* xadj, const int* adj, i
   diff_i32<<<cdiv(nAgg, 256), 256, 0, s>>>(nAgg, aggIdx, weights);
 
   induced_graph(c, n, xadj, adj, nedges, fineAggregate, nAgg, out.xadjOut, out.adjOut);
-  if ((int)out.xadjOut.size() != nAgg + 1) throw std::runtime_error("induced graph: an aggregate has no external edge");
+  if ((int)out.xadjOut.size() != nAgg + 1) throw std::invalid_argument("induced graph: an aggregate has no external edge");
   int nInducedEdges = (int)out.adjOut.size();
   tr.lap("sort + induced graph", nInducedEdges);
 

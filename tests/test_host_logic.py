@@ -246,3 +246,51 @@ def test_triangle_mesh_formats_python_and_dropin_agree(tmp_path):
     if have_exe:
         assert subprocess.run([exe, os.path.join(str(tmp_path), "bad.xyz")], capture_output=True).returncode == 1
 
+
+
+def test_bench_parity_block_and_byte_models(monkeypatch):
+    """bench.py's parity block (oracle golden + single-GPU comparison of a sharded solve) accepts rounding-level
+    differences, rejects a wrong iteration count / history / solution, and the stage byte models add up."""
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    rng = np.random.default_rng(0)
+    x = rng.uniform(-1, 1, 1000)
+    hist = np.geomspace(1.0, 1e-9, 30)
+    g = {"iterations": 29, "resid_history": list(hist), "sample_idx": [0, 10, 999], "x_samples": [float(x[i]) for i in (0, 10, 999)],
+         "x_norm2": float(np.linalg.norm(x)), "levels": [1000, 40]}
+    monkeypatch.setattr(bench, "golden_for", lambda N: (g, "tests/golden/fake.json"))
+    levels = [(1000, 15000), (40, 900)]
+    ok = bench.parity_block(7, x * (1 + 1e-13), 29, hist * (1 + 1e-9), levels, x_single=x, iters_single=29)
+    assert ok["ok"] and ok["checks"] == ["oracle_golden", "vs_single_gpu"] and ok["oracle_golden"]["iters_equal"]
+    assert not bench.parity_block(7, x, 33, hist, levels)["ok"]                      # iterations off by more than 2
+    assert not bench.parity_block(7, x, 29, hist * (1 + 1e-4), levels)["ok"]         # residual history differs
+    assert not bench.parity_block(7, x * (1 + 1e-4), 29, hist, levels)["ok"]         # solution differs
+    assert not bench.parity_block(7, x, 29, hist, [(1000, 15000), (41, 900)])["ok"]  # different aggregates
+    assert not bench.parity_block(7, x, 29, hist, levels, x_single=x + 1e-3, iters_single=29)["ok"]
+    monkeypatch.setattr(bench, "golden_for", lambda N: (None, None))
+    assert bench.parity_block(7, x, 29, hist, levels)["oracle_golden"] is None
+    assert bench.setup_bytes(levels, [3000, 0], [4000, 0]) == 24 * 15000 + 10 * 11000 + 12 * 4000 + 24 * 3000 + 12 * (15000 + 6000 + 900) + 16 * 1000
+    assert bench.host_threads() >= 1
+    assert bench.workload_name(255).startswith("Kuhn tet cube N=255 (16777216 DOF, 99488250 tets)")
+
+
+def test_oracle_goldens_are_complete():
+    """The committed full-size goldens (tests/golden/make_oracle_golden.py) carry what the GPU tests and bench.py read, and the
+    problem builder shared with them is self-consistent."""
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("make_oracle_golden", os.path.join(ROOT, "tests", "golden", "make_oracle_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    for N, variant, iters in ((118, "", 33), (255, "", 39), (149, "contrast", 36), (149, "anisotropic", 60)):
+        g = json.load(open(m.golden_path(N, variant)))
+        assert g["cube"] == N and g["iterations"] == iters and g["levels"][0] == (N + 1) ** 3
+        assert len(g["resid_history"]) >= iters and len(g["sample_idx"]) == len(g["x_samples"]) >= 3
+        assert g["x_norm2"] > 0 and g["b_norm2"] > 0 and max(g["sample_idx"]) == (N + 1) ** 3 - 1
+        if variant != "anisotropic":
+            assert g["relres"] <= 1e-8
+    v, t, lab, xs, prm = m.problem(6, "contrast")
+    assert v.shape == (343, 3) and t.shape == (6 * 216, 4) and lab.shape == (6 * 216,) and xs.shape == (343,) and prm["maxIters"] == 400
+    v, t, lab, xs, prm = m.problem(6, "anisotropic")
+    assert lab is None and abs(v[:, 2].max() - 1.0 / 64.0) < 1e-7 and prm["tolerance"] == 1e-30
