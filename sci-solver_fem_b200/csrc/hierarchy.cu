@@ -137,16 +137,28 @@ __global__ void spgemm_rows(int n, const int* __restrict__ ptrA, const int* __re
 // product order, the same order as a sequential accumulation, so the result stays bit-identical to the
 // host-order sum.  (The first version let every lane walk over ALL products of the row and pick its own:
 // 91 % of the kernel's instructions, 10 of the 46 ms of the setup at N=118; profiles/r2_spgemm_before.txt.)
-constexpr int WG_CHUNK = 512;     // products staged per step
-constexpr int WG_MAXROW = 512;    // entries of the A-row (prefix table + staged A-row)
-constexpr int WG_HASH = 256;      // hash-set size; rows with more than WG_MAXD distinct columns fall back
-constexpr int WG_MAXD = 192;
-constexpr int WG_WARPS = 4;
-constexpr int WG_SMEM_PER_WARP = WG_CHUNK * 8 + WG_CHUNK * 4 + WG_CHUNK + WG_HASH * 4 + WG_HASH * 4 + (WG_MAXROW + 1) * 4 + WG_MAXROW * 12 + 12 +
-                                 WG_CHUNK * 8 + WG_CHUNK * 2 + 16;  // + products grouped by slot, rank of a product inside its slot
+// Two instantiations: the small one (4 warps per CTA, two CTAs per SM) takes the rows of R (A P) on the big levels; rows
+// it cannot hold (more than 512 entries in the A-row or more than 192 distinct output columns — the coarse rows of the
+// last levels, whose operator rows span a good part of a few-hundred-column level) go to the large one (one warp per CTA),
+// and only what exceeds that too falls back to the thread-per-row kernel.
+template <int CHUNK_, int MAXROW_, int HASHBITS_, int MAXD_, int WARPS_>
+struct WgCfg {
+  static constexpr int CHUNK = CHUNK_;      // products staged per step
+  static constexpr int MAXROW = MAXROW_;    // entries of the A-row (prefix table + staged A-row)
+  static constexpr int HASHBITS = HASHBITS_;
+  static constexpr int HASH = 1 << HASHBITS_;  // hash-set size; rows with more than MAXD distinct columns fall back
+  static constexpr int MAXD = MAXD_;
+  static constexpr int WARPS = WARPS_;
+  // pval | pcol | pslot (u16) | hash | dist | pref | pb | va | sorted | prank (u16)
+  static constexpr int SMEM_PER_WARP = CHUNK * 8 + CHUNK * 4 + CHUNK * 2 + HASH * 4 + HASH * 4 + (MAXROW + 1) * 4 + MAXROW * 4 + 8 + MAXROW * 8 +
+                                       CHUNK * 8 + CHUNK * 2 + 16;
+};
+typedef WgCfg<512, 512, 8, 192, 4> WgSmall;
+typedef WgCfg<512, 2048, 11, 1024, 1> WgLarge;
 
 // products q0 .. q0+WG_CHUNK of the row: the A-row (B-row starts pb, values va) is staged in shared
 // memory, so a product costs one global hop (colB / valB); four products per lane are in flight.
+template <int WG_CHUNK>
 __device__ __forceinline__ void wg_expand(int q0, int m, int na, int lane, const int* pref, const int* pb, const double* va,
                                           const int* __restrict__ colB, const double* __restrict__ valB, int* pcol, double* pval) {
   const int qe = min(m, q0 + WG_CHUNK);
@@ -167,27 +179,30 @@ __device__ __forceinline__ void wg_expand(int q0, int m, int na, int lane, const
   }
 }
 
-__global__ void __launch_bounds__(32 * WG_WARPS) spgemm_warp_kernel(int n, const int* __restrict__ ptrA, const int* __restrict__ colA,
-                                                                    const double* __restrict__ valA, const int* __restrict__ ptrB,
-                                                                    const int* __restrict__ colB, const double* __restrict__ valB,
-                                                                    const long long* __restrict__ sbase, int* __restrict__ scol,
-                                                                    double* __restrict__ sval, int* __restrict__ count) {
+template <typename Cfg, bool RETRY>
+__global__ void __launch_bounds__(32 * Cfg::WARPS) spgemm_warp_kernel(int n, const int* __restrict__ ptrA, const int* __restrict__ colA,
+                                                                      const double* __restrict__ valA, const int* __restrict__ ptrB,
+                                                                      const int* __restrict__ colB, const double* __restrict__ valB,
+                                                                      const long long* __restrict__ sbase, int* __restrict__ scol,
+                                                                      double* __restrict__ sval, int* __restrict__ count) {
+  constexpr int WG_CHUNK = Cfg::CHUNK, WG_MAXROW = Cfg::MAXROW, WG_HASH = Cfg::HASH, WG_MAXD = Cfg::MAXD, WG_WARPS = Cfg::WARPS;
   extern __shared__ __align__(16) unsigned char wg_smem[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned char* base = wg_smem + (size_t)w * ((WG_SMEM_PER_WARP + 15) & ~15);
+  unsigned char* base = wg_smem + (size_t)w * ((Cfg::SMEM_PER_WARP + 15) & ~15);
   double* pval = reinterpret_cast<double*>(base);
   int* pcol = reinterpret_cast<int*>(base + WG_CHUNK * 8);
-  unsigned char* pslot = base + WG_CHUNK * 12;
-  int* hash = reinterpret_cast<int*>(base + WG_CHUNK * 13);
+  unsigned short* pslot = reinterpret_cast<unsigned short*>(base + WG_CHUNK * 12);
+  int* hash = reinterpret_cast<int*>(base + WG_CHUNK * 14);
   int* dist = hash + WG_HASH;
   int* pref = dist + WG_HASH;
   int* pb = pref + (WG_MAXROW + 1);
-  double* va = reinterpret_cast<double*>(base + ((WG_CHUNK * 13 + WG_HASH * 8 + (WG_MAXROW + 1) * 4 + WG_MAXROW * 4 + 7) & ~7));
+  double* va = reinterpret_cast<double*>(base + ((WG_CHUNK * 14 + WG_HASH * 8 + (WG_MAXROW + 1) * 4 + WG_MAXROW * 4 + 7) & ~7));
   double* sorted = va + WG_MAXROW;                                        // products of the chunk grouped by slot
   unsigned short* prank = reinterpret_cast<unsigned short*>(sorted + WG_CHUNK);
   int* scnt = hash;                                                       // the hash set is free after pass 1: per-slot counts / offsets
   const int i = blockIdx.x * WG_WARPS + w;
   if (i >= n) return;
+  if (RETRY && count[i] != -1) return;  // second instantiation: only the rows the first one flagged
   const int a0 = ptrA[i], na = ptrA[i + 1] - a0;
   const int m = (int)(sbase[i + 1] - sbase[i]);
   if (na > WG_MAXROW) { if (lane == 0) count[i] = -1; return; }  // fallback row
@@ -209,11 +224,11 @@ __global__ void __launch_bounds__(32 * WG_WARPS) spgemm_warp_kernel(int n, const
   // pass 1: distinct columns
   int overflow = 0;
   for (int q0 = 0; q0 < m; q0 += WG_CHUNK) {
-    wg_expand(q0, m, na, lane, pref, pb, va, colB, valB, pcol, nullptr);
+    wg_expand<WG_CHUNK>(q0, m, na, lane, pref, pb, va, colB, valB, pcol, nullptr);
     __syncwarp();
     for (int q = q0 + lane; q < min(m, q0 + WG_CHUNK); q += 32) {
       const int c = pcol[q - q0];
-      unsigned h = ((unsigned)c * 2654435761u) >> 24;
+      unsigned h = ((unsigned)c * 2654435761u) >> (32 - Cfg::HASHBITS);
       for (int probe = 0; probe < WG_HASH; probe++) {
         const int old = atomicCAS(&hash[h], -1, c);
         if (old == -1 || old == c) break;
@@ -252,7 +267,7 @@ __global__ void __launch_bounds__(32 * WG_WARPS) spgemm_warp_kernel(int n, const
   for (int j = 0; j < WG_MAXD / 32; j++) acc[j] = 0.0;
   for (int q0 = 0; q0 < m; q0 += WG_CHUNK) {
     const int mc = min(m, q0 + WG_CHUNK) - q0;
-    wg_expand(q0, m, na, lane, pref, pb, va, colB, valB, pcol, pval);
+    wg_expand<WG_CHUNK>(q0, m, na, lane, pref, pb, va, colB, valB, pcol, pval);
     __syncwarp();
     for (int h = lane; h < WG_HASH; h += 32) scnt[h] = 0;
     __syncwarp();
@@ -266,7 +281,7 @@ __global__ void __launch_bounds__(32 * WG_WARPS) spgemm_warp_kernel(int n, const
         int lo = 0, hi = nd - 1;
         while (lo < hi) { const int mid = (lo + hi) >> 1; if (dist[mid] < c) lo = mid + 1; else hi = mid; }
         sl = lo;
-        pslot[q] = (unsigned char)lo;
+        pslot[q] = (unsigned short)lo;
       }
       const unsigned peers = __match_any_sync(0xffffffffu, sl);
       if (q < mc) prank[q] = (unsigned short)(scnt[sl] + __popc(peers & ((1u << lane) - 1u)));
@@ -468,10 +483,21 @@ void spgemm(const Ctx& c, const DCsr& A, const DCsr& B, DCsr& C) {
   const bool long_rows = (double)A.nnz > 64.0 * n;
   if (long_rows) {
     static PerDeviceOnce attr_once;
-    const size_t smem = (size_t)((WG_SMEM_PER_WARP + 15) & ~15) * WG_WARPS;
-    if (attr_once.first(c.device)) FSB_CUDA(cudaFuncSetAttribute(spgemm_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    spgemm_warp_kernel<<<cdiv(n, WG_WARPS), 32 * WG_WARPS, smem, s>>>(n, A.ptr, A.col, A.val, B.ptr, B.col, B.val, sbase, scol, sval, count);
-    // rows it could not take (very long A-rows / too many distinct columns): thread-per-row kernel, restricted to them
+    const size_t smemS = (size_t)((WgSmall::SMEM_PER_WARP + 15) & ~15) * WgSmall::WARPS, smemL = (size_t)((WgLarge::SMEM_PER_WARP + 15) & ~15) * WgLarge::WARPS;
+    if (attr_once.first(c.device)) {
+      FSB_CUDA(cudaFuncSetAttribute(spgemm_warp_kernel<WgSmall, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemS));
+      FSB_CUDA(cudaFuncSetAttribute(spgemm_warp_kernel<WgLarge, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemL));
+      FSB_CUDA(cudaFuncSetAttribute(spgemm_warp_kernel<WgLarge, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemL));
+    }
+    const char* env = getenv("FSB_SPGEMM_LARGE");  // test knob, read at every call: 1 = every row through the large instantiation
+    if (env && atoi(env) == 1)
+      spgemm_warp_kernel<WgLarge, false><<<cdiv(n, WgLarge::WARPS), 32 * WgLarge::WARPS, smemL, s>>>(n, A.ptr, A.col, A.val, B.ptr, B.col, B.val, sbase, scol, sval, count);
+    else {
+      spgemm_warp_kernel<WgSmall, false><<<cdiv(n, WgSmall::WARPS), 32 * WgSmall::WARPS, smemS, s>>>(n, A.ptr, A.col, A.val, B.ptr, B.col, B.val, sbase, scol, sval, count);
+      // rows it flagged (long A-rows / many distinct columns): the large instantiation, restricted to them
+      spgemm_warp_kernel<WgLarge, true><<<cdiv(n, WgLarge::WARPS), 32 * WgLarge::WARPS, smemL, s>>>(n, A.ptr, A.col, A.val, B.ptr, B.col, B.val, sbase, scol, sval, count);
+    }
+    // rows that exceed that too: thread-per-row kernel, restricted to them
     spgemm_rows<<<cdiv(n, 64), 64, 0, s>>>(n, A.ptr, A.col, A.val, B.ptr, B.col, B.val, sbase, scol, sval, count, 1);
   } else {
     spgemm_rows<<<cdiv(n, 64), 64, 0, s>>>(n, A.ptr, A.col, A.val, B.ptr, B.col, B.val, sbase, scol, sval, count, 0);

@@ -59,8 +59,12 @@ def _setup_pair(verts, elems, labels=None, **params):
     return o, s, nl
 
 
-@pytest.mark.parametrize("N,seed", [(12, 0), (20, 0), (20, 7)])
-def test_hierarchy_bit_exact(N, seed):
+@pytest.mark.parametrize("N,seed,large", [(12, 0, 0), (20, 0, 0), (20, 7, 0), (20, 0, 1), (28, 0, 1)])
+def test_hierarchy_bit_exact(N, seed, large, monkeypatch):
+    """large=1 sends every row of R (A P) through the LARGE instantiation of the warp SpGEMM (the one that otherwise only
+    takes the rows with > 512 A-entries or > 192 distinct output columns, i.e. the last levels of the big cubes)."""
+    if large:
+        monkeypatch.setenv("FSB_SPGEMM_LARGE", "1")
     v, t = kuhn(N)
     o, s, nl = _setup_pair(v, t, seed=seed)
     assert s.num_levels() == nl
