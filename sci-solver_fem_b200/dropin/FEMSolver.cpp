@@ -85,8 +85,12 @@ TetMesh* TetMesh::read(const char* nodefilename, const char* elefilename, const 
 // ASCII PLY with x y z first (TriMesh_io.cu:259, :874-878 use %lf)
 // ---- triangle-mesh input.  TriMesh::read upstream recognises the format from the first bytes of the file
 // (TriMesh_io.cu:160-256).  Covered: PLY (ascii, binary little/big endian; any scalar property types, the
-// vertex_indices list with any integer count/index types, other elements skipped), OBJ, OFF, old-style SM.
-// Polygons are cut into triangles by upstream's rule (:1239-1270).  Not covered: 3DS, VVD, RAY, PLY strips/grids.
+// vertex_indices list with any integer count/index types, faces as `element face` or as `element tristrips`, other
+// elements — also range_grid, whose upstream reader is commented out — skipped), 3DS, VVD, RAY, OBJ, OFF, old-style SM.
+// Polygons are cut into triangles by upstream's rule (:1239-1270).
+// Deviations where upstream cannot work: its 3DS loop returns false at the end of every well-formed file (feof is only set
+// by the failing read, :508-513); its RAY reader scans "%f" into doubles (:634, undefined behaviour); it reads triangle
+// strips but never unpacks them (convert_strips / need_faces commented out, :478) — here all three deliver the mesh.
 namespace {
 
 struct PlyProp { bool list; std::string name; int size, csize; char kind, ckind; };  // kind: 'i' signed, 'u' unsigned, 'f' float
@@ -139,6 +143,21 @@ bool finish(TriMesh* m, const std::vector<std::vector<int> >& polys) {
     tessellate(m->vertices, p, m->faces);
   }
   return !(m->vertices.empty() && m->faces.empty());
+}
+
+// strips separated by -1 -> triangles, orientation flipped on every second triangle; degenerate ones only stitch strips
+void unpack_tstrips(const std::vector<int>& idx, std::vector<std::vector<int> >& polys) {
+  std::vector<int> run;
+  auto flush = [&]() {
+    for (size_t i = 0; i + 2 < run.size(); i++) {
+      const int a = run[i], b = run[i + 1], c = run[i + 2];
+      if (a == b || b == c || a == c) continue;
+      if (i % 2 == 0) polys.push_back({a, b, c}); else polys.push_back({b, a, c});
+    }
+    run.clear();
+  };
+  for (int v : idx) { if (v < 0) flush(); else run.push_back(v); }
+  flush();
 }
 
 bool parse_ply(const std::string& data, TriMesh* m) {
@@ -211,6 +230,7 @@ bool parse_ply(const std::string& data, TriMesh* m) {
             poly.push_back((int)v);
           }
           if (is_face && (pr.name == "vertex_indices" || pr.name == "vertex_index")) polys.push_back(poly);
+          if (e.name == "tristrips" && pr.name == "vertex_indices") unpack_tstrips(poly, polys);
         }
       }
     }
@@ -281,6 +301,105 @@ bool parse_counted(const std::vector<std::string>& t, size_t pos, bool off_style
   return finish(m, polys);
 }
 
+template <typename T>
+bool get_bin(const std::string& d, size_t& pos, bool big_endian, T& v) {
+  if (pos + sizeof(T) > d.size()) return false;
+  unsigned char b[sizeof(T)];
+  const unsigned short probe = 1;
+  const bool host_le = *reinterpret_cast<const unsigned char*>(&probe) == 1;
+  for (size_t i = 0; i < sizeof(T); i++) b[i] = (unsigned char)d[pos + ((big_endian == host_le) ? sizeof(T) - 1 - i : i)];
+  std::memcpy(&v, b, sizeof(T));
+  pos += sizeof(T);
+  return true;
+}
+
+// 3D Studio chunks (TriMesh_io.cu:503-576)
+bool parse_3ds(const std::string& d, TriMesh* m) {
+  std::vector<std::vector<int> > polys;
+  size_t pos = 0;
+  int mstart = 0;
+  while (pos + 6 <= d.size()) {
+    unsigned short id; unsigned len;
+    get_bin(d, pos, false, id); get_bin(d, pos, false, len);
+    if (id == 0x4d4d || id == 0x3d3d) continue;                       // entered
+    if (id == 0x4000) {                                               // object: zero-terminated name, then entered
+      const size_t e = d.find('\0', pos);
+      if (e == std::string::npos) return false;
+      pos = e + 1;
+    } else if (id == 0x4100) mstart = (int)m->vertices.size();
+    else if (id == 0x4110) {
+      unsigned short nv;
+      if (!get_bin(d, pos, false, nv)) return false;
+      for (int i = 0; i < nv; i++) {
+        float x, y, z;
+        if (!get_bin(d, pos, false, x) || !get_bin(d, pos, false, y) || !get_bin(d, pos, false, z)) return false;
+        point q; q[0] = x; q[1] = y; q[2] = z;
+        m->vertices.push_back(q);
+      }
+    } else if (id == 0x4120) {
+      unsigned short nf;
+      if (!get_bin(d, pos, false, nf)) return false;
+      for (int i = 0; i < nf; i++) {
+        unsigned short a, b, c, flags;
+        if (!get_bin(d, pos, false, a) || !get_bin(d, pos, false, b) || !get_bin(d, pos, false, c) || !get_bin(d, pos, false, flags)) return false;
+        polys.push_back({mstart + a, mstart + b, mstart + c});
+      }
+    } else pos += len >= 6 ? len - 6 : 0;
+  }
+  return finish(m, polys);
+}
+
+// VIVID range scans, big-endian (TriMesh_io.cu:580-621)
+bool parse_vvd(const std::string& d, TriMesh* m) {
+  size_t pos = 5 + 127;
+  int nv, nf;
+  if (!get_bin(d, pos, true, nv) || nv < 0) { std::cerr << "Couldn't read vertex count" << std::endl; return false; }
+  for (int i = 0; i < nv; i++) {
+    double x, y, z;
+    if (!get_bin(d, pos, true, x) || !get_bin(d, pos, true, y) || !get_bin(d, pos, true, z)) { std::cerr << "Couldn't read vertex" << std::endl; return false; }
+    point q; q[0] = x; q[1] = y; q[2] = z;
+    m->vertices.push_back(q);
+  }
+  if (!get_bin(d, pos, true, nf)) { std::cerr << "Couldn't read face count" << std::endl; return false; }
+  std::vector<std::vector<int> > polys;
+  for (int f = 0; f < nf; f++) {
+    int k;
+    if (!get_bin(d, pos, true, k) || k < 0) return false;
+    std::vector<int> poly(k);
+    for (int j = 0; j < k; j++) if (!get_bin(d, pos, true, poly[j])) return false;
+    polys.push_back(poly);
+  }
+  return finish(m, polys);
+}
+
+// ray-tracer scene text (TriMesh_io.cu:625-647)
+bool parse_ray(const std::string& d, TriMesh* m) {
+  std::istringstream ds(d);
+  std::vector<std::string> t;
+  std::string w;
+  while (ds >> w) t.push_back(w);
+  std::vector<std::vector<int> > polys;
+  for (size_t i = 0; i < t.size();) {
+    if (t[i].compare(0, 7, "#vertex") == 0 && i + 3 < t.size()) {
+      point q;
+      for (int j = 0; j < 3; j++) q[j] = std::strtod(t[i + 1 + j].c_str(), NULL);
+      m->vertices.push_back(q);
+      i += 4;
+    } else if (t[i].compare(0, 15, "#shape_triangle") == 0 && i + 4 < t.size()) {
+      polys.push_back({std::atoi(t[i + 2].c_str()), std::atoi(t[i + 3].c_str()), std::atoi(t[i + 4].c_str())});
+      i += 5;
+    } else i++;
+  }
+  return finish(m, polys);
+}
+
+bool is_ray(const std::string& d) {  // the word after '#': material / vertex / shape_... (TriMesh_io.cu:211-219)
+  std::istringstream ds(d.substr(1, 64));
+  std::string w;
+  if (!(ds >> w)) return false;
+  return w.compare(0, 8, "material") == 0 || w.compare(0, 6, "vertex") == 0 || w.compare(0, 6, "shape_") == 0;
+}
+
 }  // namespace
 
 TriMesh* TriMesh::read(const char* filename) {
@@ -292,6 +411,9 @@ TriMesh* TriMesh::read(const char* filename) {
   bool ok = false;
   if (data.empty()) std::cerr << "Can't read header" << std::endl;
   else if (data.compare(0, 3, "ply") == 0) ok = parse_ply(data, m);
+  else if (data.compare(0, 2, "MM") == 0) ok = parse_3ds(data, m);
+  else if (data.compare(0, 5, "VIVID") == 0) ok = parse_vvd(data, m);
+  else if (data[0] == '#' && is_ray(data)) ok = parse_ray(data, m);
   else if (data.compare(0, 3, "OFF") == 0) { std::vector<std::string> t = text_tokens(data); ok = parse_counted(t, 1, true, m); }
   else if (std::strchr("#vufgso", data[0])) ok = parse_obj(data, m);
   else if (std::isdigit((unsigned char)data[0])) ok = parse_counted(text_tokens(data), 0, false, m);

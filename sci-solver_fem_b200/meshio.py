@@ -2,7 +2,7 @@
 
 Mirrors what the reference reads/writes around FEMSolver:
   * TetGen .node/.ele      -> reference src/core/cuda/tetmesh.cu:251-376 (TetMesh::read)
-  * ASCII PLY              -> reference src/core/aggmis/cuda/TriMesh_io.cu:259,874-878
+  * triangle meshes        -> reference src/core/aggmis/cuda/TriMesh_io.cu:146-1276 (PLY, 3DS, VVD, RAY, OBJ, OFF, SM)
   * MATLAB v5 (-v6) .mat   -> reference src/FEMSolver.cu:177-356 (sparse), :358-449 (array), :451-517 (writer)
   * synthetic Kuhn cubes   -> SURVEY.md section 4 / section 8(d): the generator of
                               CubeMesh_size256step16_correct and of the BASELINE.json configs.
@@ -137,8 +137,8 @@ def write_node_ele(base: str, verts, tets, labels=None):
 # ------------------------------------------------------------------------------------- triangle meshes
 # TriMesh::read (aggmis/cuda/TriMesh_io.cu:146-256) recognises the format from the first bytes of the file.
 # Covered here: PLY (ascii, binary little/big endian; any scalar property types, the vertex_indices list with
-# any integer count/index types; other elements are skipped), OBJ, OFF and old-style SM.  Polygons are cut into
-# triangles by upstream's rule (tess, :1239-1270).  Not covered: 3DS, VVD, RAY, PLY triangle strips / range grids.
+# any integer count/index types, face lists or triangle strips; other elements — also range_grid — are skipped), 3DS,
+# VVD, RAY, OBJ, OFF and old-style SM.  Polygons are cut into triangles by upstream's rule (tess, :1239-1270).
 _PLY_TYPES = {"char": "i1", "int8": "i1", "uchar": "u1", "uint8": "u1", "short": "i2", "int16": "i2", "ushort": "u2",
               "uint16": "u2", "int": "i4", "int32": "i4", "uint": "u4", "uint32": "u4", "float": "f4", "float32": "f4",
               "double": "f8", "float64": "f8"}
@@ -172,8 +172,27 @@ def _finish_trimesh(verts, polys):
     return verts, tris
 
 
+def unpack_tstrips(idx):
+    """Triangle strips as PLY stores them (`element tristrips`, one index list, strips separated by -1) -> triangles, the
+    orientation flipped on every second triangle of a strip.  Upstream reads the list (TriMesh_io.cu:1021-1063) but never
+    unpacks it in this code base (`need_faces()` / `convert_strips` are commented out, :478), i.e. a strip file gives it a
+    mesh without faces; here the strips become the faces they encode."""
+    tris, run = [], []
+    for v in list(idx) + [-1]:
+        if v < 0:
+            for i in range(len(run) - 2):
+                a, b, c = run[i], run[i + 1], run[i + 2]
+                if a != b and b != c and a != c:  # degenerate triangles only stitch strips together
+                    tris.append([a, b, c] if i % 2 == 0 else [b, a, c])
+            run = []
+        else:
+            run.append(int(v))
+    return tris
+
+
 def read_ply(path: str):
-    """PLY, ascii or binary (either endianness)."""
+    """PLY, ascii or binary (either endianness); faces as `element face` lists or as `element tristrips`; a `range_grid`
+    element is skipped as upstream does (its reader is commented out, TriMesh_io.cu:1066-1108)."""
     with open(path, "rb") as f:
         data = f.read()
     end = data.find(b"end_header")
@@ -218,6 +237,8 @@ def read_ply(path: str):
             elif name == "face":
                 key = "vertex_indices" if (rows and "vertex_indices" in rows[0]) else "vertex_index"
                 polys = [r[key] for r in rows]
+            elif name == "tristrips":
+                polys = [tri for r in rows for tri in unpack_tstrips(r["vertex_indices"])]
     else:
         e = "<" if fmt == "binary_little_endian" else ">"
         mv = memoryview(body)
@@ -245,6 +266,8 @@ def read_ply(path: str):
             if name == "face":
                 key = "vertex_indices" if (rows and "vertex_indices" in rows[0]) else "vertex_index"
                 polys = [r[key] for r in rows]
+            elif name == "tristrips":
+                polys = [tri for r in rows for tri in unpack_tstrips(r["vertex_indices"])]
     return _finish_trimesh(verts, polys)
 
 
@@ -309,18 +332,105 @@ def read_sm(path: str):
     return _finish_trimesh(verts, polys)
 
 
+def read_3ds(path: str):
+    """3D Studio: little-endian chunks (id u16, length u32).  0x4d4d / 0x3d3d are entered, 0x4000 is entered after its
+    zero-terminated name, 0x4100 starts a mesh (indices are relative to its first vertex), 0x4110 = u16 count + float32
+    xyz, 0x4120 = u16 count + 4 x u16 per face (a, b, c, flags), everything else is skipped (TriMesh_io.cu:503-576).
+    Deviation: upstream's loop `while (!feof(f)) { if (!fread(...)) return false; ...}` returns false at the end of EVERY
+    well-formed file (feof is only set by the failing read), so it cannot read 3DS at all; here a clean end is success."""
+    import struct
+    with open(path, "rb") as f:
+        data = f.read()
+    pos, mstart, verts, polys = 0, 0, [], []
+    while pos + 6 <= len(data):
+        cid, clen = struct.unpack_from("<HI", data, pos)
+        pos += 6
+        if cid in (0x4D4D, 0x3D3D):
+            continue
+        if cid == 0x4000:
+            end = data.find(b"\0", pos)
+            if end < 0:
+                raise ValueError("truncated 3DS object name")
+            pos = end + 1
+        elif cid == 0x4100:
+            mstart = len(verts)
+        elif cid == 0x4110:
+            (nv,) = struct.unpack_from("<H", data, pos)
+            pos += 2
+            verts.extend(np.frombuffer(data, dtype="<f4", count=3 * nv, offset=pos).astype(np.float64).reshape(nv, 3).tolist())
+            pos += 12 * nv
+        elif cid == 0x4120:
+            (nf,) = struct.unpack_from("<H", data, pos)
+            pos += 2
+            fa = np.frombuffer(data, dtype="<u2", count=4 * nf, offset=pos).reshape(nf, 4)
+            polys.extend((fa[:, :3].astype(np.int64) + mstart).tolist())
+            pos += 8 * nf
+        else:
+            pos += max(clen - 6, 0)
+    return _finish_trimesh(np.array(verts, dtype=np.float64).reshape(-1, 3), polys)
+
+
+def read_vvd(path: str):
+    """VIVID (Minolta) range scans, big-endian: "VIVID", 127 bytes of header, int32 vertex count, 3 float64 per vertex,
+    int32 face count, per face an int32 index count followed by that many int32 indices (TriMesh_io.cu:580-621,
+    read_faces_bin with face_len = 4, face_count = 0, face_idx = 4)."""
+    import struct
+    with open(path, "rb") as f:
+        data = f.read()
+    if data[:5] != b"VIVID":
+        raise ValueError("not a VVD file")
+    pos = 5 + 127
+    (nv,) = struct.unpack_from(">i", data, pos); pos += 4
+    if nv < 0 or pos + 24 * nv > len(data):
+        raise ValueError("Couldn't read vertex")
+    verts = np.frombuffer(data, dtype=">f8", count=3 * nv, offset=pos).astype(np.float64).reshape(nv, 3)
+    pos += 24 * nv
+    (nf,) = struct.unpack_from(">i", data, pos); pos += 4
+    polys = []
+    for _ in range(nf):
+        (k,) = struct.unpack_from(">i", data, pos); pos += 4
+        polys.append([int(i) for i in struct.unpack_from(">%di" % k, data, pos)]); pos += 4 * k
+    return _finish_trimesh(verts, polys)
+
+
+def read_ray(path: str):
+    """Ray-tracer scene text: `#vertex x y z` and `#shape_triangle material a b c` (0-based), every other token ignored
+    (TriMesh_io.cu:625-647).  Deviation: upstream scans the coordinates with "%f" into doubles (undefined behaviour: the
+    low halves of the doubles get float bit patterns), so its RAY vertices are garbage; here they are parsed as written."""
+    with open(path) as f:
+        t = f.read().split()
+    verts, polys, i = [], [], 0
+    while i < len(t):
+        if t[i].startswith("#vertex") and i + 3 < len(t):
+            verts.append([float(t[i + 1]), float(t[i + 2]), float(t[i + 3])]); i += 4
+        elif t[i].startswith("#shape_triangle") and i + 4 < len(t):
+            polys.append([int(t[i + 2]), int(t[i + 3]), int(t[i + 4])]); i += 5
+        else:
+            i += 1
+    return _finish_trimesh(np.array(verts, dtype=np.float64).reshape(-1, 3), polys)
+
+
 def read_trimesh(path: str):
     """Format by the first bytes, as TriMesh::read_helper does (TriMesh_io.cu:160-256)."""
     with open(path, "rb") as f:
-        head = f.read(4)
+        head = f.read(64)
     if not head:
         raise ValueError("Can't read header")
     c = head[:1]
     if head[:3] == b"ply":
         return read_ply(path)
+    if head[:2] == b"MM":
+        return read_3ds(path)
+    if head[:5] == b"VIVID":
+        return read_vvd(path)
     if head[:3] == b"OFF":
         return read_off(path)
-    if c in (b"#", b"v", b"u", b"f", b"g", b"s", b"o"):
+    if c == b"#":  # the word after '#': material / vertex / shape_... = a ray file, anything else an OBJ comment
+        w = head[1:].split()
+        if w and (w[0].startswith(b"material") or w[0].startswith(b"vertex") or w[0].startswith(b"shape_")):
+            return read_ray(path)
+        return read_obj(path)
+    if c in (b"v", b"u", b"f", b"g", b"s", b"o"):
         return read_obj(path)
     if c.isdigit():
         return read_sm(path)

@@ -248,6 +248,115 @@ def test_triangle_mesh_formats_python_and_dropin_agree(tmp_path):
 
 
 
+def _cmp_with_dropin(path, v, t):
+    """The C++ reader of the drop-in (bin/mesh_info) must see the same mesh as the Python reader."""
+    import subprocess
+    exe = os.path.join(ROOT, "sci-solver_fem_b200", "dropin", "bin", "mesh_info")
+    if not os.path.exists(exe):
+        return
+    r = subprocess.run([exe, path], capture_output=True, text=True)
+    assert r.returncode == 0, path + r.stderr
+    out = r.stdout.split("\n")
+    assert int(out[0]) == len(v) and int(out[1]) == len(t), path
+    cs = sum((i % 97 + 1) * (j + 1) * v[i, j] for i in range(len(v)) for j in range(3))
+    fs = sum((i % 89 + 1) * (j + 1) * int(t[i, j]) for i in range(len(t)) for j in range(3))
+    assert abs(float(out[2]) - cs) <= 1e-9 * max(1.0, abs(cs)), path
+    assert int(out[3]) == fs, path
+
+
+def test_remaining_triangle_mesh_formats(tmp_path):
+    """The rest of TriMesh::read's formats (TriMesh_io.cu:146-256): PLY triangle strips (ascii and binary), 3D Studio,
+    VIVID (big-endian) and ray-tracer scenes, in Python and in the drop-in's C++ reader; a PLY range grid gives vertices
+    without faces, as upstream (its grid reader is commented out)."""
+    import struct
+    verts, polys = _mesh_with_polygons()
+    v32 = verts.astype(np.float32).astype(np.float64)
+    nv = len(verts)
+    d = str(tmp_path)
+    # --- PLY tristrips: two strips, the second stitched with a degenerate triangle
+    strips = [0, 1, 2, 3, 4, -1, 5, 6, 7, 7, 8, -1]
+    want = [(0, 1, 2), (2, 1, 3), (2, 3, 4), (5, 6, 7)]   # (6,7,7) and (7,7,8) are degenerate: dropped
+    assert [tuple(x) for x in meshio.unpack_tstrips(strips)] == want
+    head = "ply\nformat %s 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\nelement tristrips 1\nproperty list int int vertex_indices\nend_header\n"
+    pa = os.path.join(d, "strips_ascii.ply")
+    with open(pa, "w") as f:
+        f.write(head % ("ascii", nv))
+        for v in verts:
+            f.write("%.9g %.9g %.9g\n" % tuple(v))
+        f.write("%d %s\n" % (len(strips), " ".join(map(str, strips))))
+    for order, e in (("binary_little_endian", "<"), ("binary_big_endian", ">")):
+        pb = os.path.join(d, "strips_%s.ply" % order)
+        with open(pb, "wb") as f:
+            f.write((head % (order, nv)).encode())
+            f.write(verts.astype(e + "f4").tobytes())
+            f.write(struct.pack(e + "i", len(strips)) + np.array(strips, dtype=e + "i4").tobytes())
+        v, t = meshio.read_trimesh(pb)
+        assert np.allclose(v, v32, atol=1e-7) and [tuple(x) for x in t.tolist()] == want
+        _cmp_with_dropin(pb, v, t)
+    v, t = meshio.read_trimesh(pa)
+    assert np.allclose(v, verts, atol=1e-6) and [tuple(x) for x in t.tolist()] == want
+    _cmp_with_dropin(pa, v, t)
+    # --- PLY range grid: vertices only
+    pg = os.path.join(d, "grid.ply")
+    with open(pg, "w") as f:
+        f.write("ply\nformat ascii 1.0\nobj_info num_cols 3\nobj_info num_rows 3\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\n"
+                "element range_grid 9\nproperty list uchar int vertex_indices\nend_header\n" % nv)
+        for v in verts:
+            f.write("%.9g %.9g %.9g\n" % tuple(v))
+        for k in range(9):
+            f.write("1 %d\n" % k)
+    v, t = meshio.read_trimesh(pg)
+    assert len(v) == nv and len(t) == 0
+    _cmp_with_dropin(pg, v, t)
+    # --- 3D Studio: main > model > two objects, the second with its own vertex numbering and a sub-chunk to skip
+    tris = [t for p in polys for t in meshio.tessellate(verts, p)]
+    ha, hb = nv // 2, nv - nv // 2
+    ta = [t for t in tris if max(t) < ha]
+    tb = [tuple(i - ha for i in t) for t in tris if min(t) >= ha]
+    def chunk(cid, payload):
+        return struct.pack("<HI", cid, 6 + len(payload)) + payload
+    def mesh(vs, ts, extra=b""):
+        vc = chunk(0x4110, struct.pack("<H", len(vs)) + np.asarray(vs, dtype="<f4").tobytes())
+        fc = chunk(0x4120, struct.pack("<H", len(ts)) + b"".join(struct.pack("<4H", a, b, c, 7) for a, b, c in ts) + extra)
+        return chunk(0x4100, vc + fc)
+    objs = chunk(0x4000, b"first\0" + mesh(verts[:ha], ta)) + chunk(0xAFFF, b"material junk") + \
+        chunk(0x4000, b"second\0" + mesh(verts[ha:], tb, chunk(0x4150, struct.pack("<%dI" % max(len(tb), 1), *([1] * max(len(tb), 1))))))
+    p3 = os.path.join(d, "m.3ds")
+    with open(p3, "wb") as f:
+        f.write(chunk(0x4D4D, chunk(0x0002, struct.pack("<I", 3)) + chunk(0x3D3D, objs)))
+    v, t = meshio.read_trimesh(p3)
+    assert np.allclose(v, v32, atol=1e-7)
+    assert [tuple(x) for x in t.tolist()] == ta + [tuple(i + ha for i in q) for q in tb]
+    _cmp_with_dropin(p3, v, t)
+    # --- VIVID: big-endian doubles, polygons with their index counts
+    pv = os.path.join(d, "m.vvd")
+    with open(pv, "wb") as f:
+        f.write(b"VIVID" + bytes(127) + struct.pack(">i", nv) + verts.astype(">f8").tobytes() + struct.pack(">i", len(polys)))
+        for p in polys:
+            f.write(struct.pack(">i", len(p)) + np.array(p, dtype=">i4").tobytes())
+    v, t = meshio.read_trimesh(pv)
+    assert np.array_equal(v, verts) and [tuple(x) for x in t.tolist()] == tris
+    _cmp_with_dropin(pv, v, t)
+    # --- RAY: '#vertex x y z' / '#shape_triangle material a b c' among other tokens
+    pr = os.path.join(d, "m.ray")
+    with open(pr, "w") as f:
+        f.write("#material 0 0 0  1 1 1\n#camera 0 0 5\n")
+        for v in verts:
+            f.write("#vertex %.17g %.17g %.17g\n" % tuple(v))
+        for a, b, c in tris:
+            f.write("#shape_triangle 0 %d %d %d\n" % (a, b, c))
+    v, t = meshio.read_trimesh(pr)
+    assert np.array_equal(v, verts) and [tuple(x) for x in t.tolist()] == tris
+    _cmp_with_dropin(pr, v, t)
+    # an OBJ that starts with an ordinary comment is still an OBJ
+    po = os.path.join(d, "c.obj")
+    with open(po, "w") as f:
+        f.write("# exported by something\nv 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3\n")
+    v, t = meshio.read_trimesh(po)
+    assert len(v) == 3 and t.tolist() == [[0, 1, 2]]
+    _cmp_with_dropin(po, v, t)
+
+
 def test_bench_parity_block_and_byte_models(monkeypatch):
     """bench.py's parity block (oracle golden + single-GPU comparison of a sharded solve) accepts rounding-level
     differences, rejects a wrong iteration count / history / solution, and the stage byte models add up."""
