@@ -26,16 +26,36 @@ __global__ void row_lengths_permuted(int n, const int* __restrict__ ptr, const i
   if (i < n) len[perm[i]] = ptr[i + 1] - ptr[i];
 }
 
-// matrixpermute_kernel: (row, col) -> (perm[row], perm[col]); rows re-sorted by column
-__global__ void permute_rows(int n, const int* __restrict__ ptrA, const int* __restrict__ colA, const double* __restrict__ valA,
-                             const int* __restrict__ perm, const int* __restrict__ ptrB, int* __restrict__ colB, double* __restrict__ valB) {
+// matrixpermute_kernel: (row, col) -> (perm[row], perm[col]); rows re-sorted by column.  Rows of up to PR_CAP entries are
+// sorted in a per-thread list in shared memory (entry q of thread t at [q * PR_THREADS + t]) and written out once; longer
+// rows (coarse levels) are insertion-sorted in place in the destination row.
+constexpr int PR_THREADS = 64, PR_CAP = 32;
+__global__ void __launch_bounds__(PR_THREADS) permute_rows(int n, const int* __restrict__ ptrA, const int* __restrict__ colA,
+                                                           const double* __restrict__ valA, const int* __restrict__ perm,
+                                                           const int* __restrict__ ptrB, int* __restrict__ colB, double* __restrict__ valB) {
+  __shared__ int sh_c[PR_CAP * PR_THREADS];
+  __shared__ double sh_v[PR_CAP * PR_THREADS];
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  int base = ptrB[perm[i]], cnt = 0;
-  for (int e = ptrA[i]; e < ptrA[i + 1]; e++) {
+  const int base = ptrB[perm[i]], e0 = ptrA[i], len = ptrA[i + 1] - e0;
+  if (len <= PR_CAP) {
+    int* lc = sh_c + threadIdx.x;
+    double* lv = sh_v + threadIdx.x;
+    for (int k = 0; k < len; k++) {
+      const int cnew = perm[colA[e0 + k]];
+      const double v = valA[e0 + k];
+      int q = k;
+      while (q > 0 && lc[(q - 1) * PR_THREADS] > cnew) { lc[q * PR_THREADS] = lc[(q - 1) * PR_THREADS]; lv[q * PR_THREADS] = lv[(q - 1) * PR_THREADS]; q--; }
+      lc[q * PR_THREADS] = cnew; lv[q * PR_THREADS] = v;
+    }
+    for (int q = 0; q < len; q++) { colB[base + q] = lc[q * PR_THREADS]; valB[base + q] = lv[q * PR_THREADS]; }
+    return;
+  }
+  int cnt = 0;
+  for (int e = e0; e < e0 + len; e++) {
     int cnew = perm[colA[e]];
     double v = valA[e];
-    int q = base + cnt;  // insertion sort into the (short) destination row
+    int q = base + cnt;  // insertion sort into the destination row
     while (q > base && colB[q - 1] > cnew) { colB[q] = colB[q - 1]; valB[q] = valB[q - 1]; q--; }
     colB[q] = cnew; valB[q] = v;
     cnt++;
@@ -66,23 +86,52 @@ __device__ __forceinline__ int acc_insert(int* cols, double* vals, int cnt, int 
   return cnt + 1;
 }
 
+// The same sorted-list accumulate on a per-thread list in SHARED memory (entry i of thread t at [i * ROW_THREADS + t]):
+// the global scratch rows of the thread-per-row kernels are ~100 B apart per thread and were read-modify-written once per
+// product.  Returns the new count, or -1 when a new column does not fit (the caller redoes the row on the global scratch).
+constexpr int ROW_THREADS = 64;   // threads per CTA of the thread-per-row setup kernels
+constexpr int ROW_CAP = 32;       // list entries per thread in shared memory (24.5 KB per CTA)
+__device__ __forceinline__ int acc_insert_sh(int* cols, double* vals, int cnt, int j, double v) {
+  int lo = 0, hi = cnt;
+  while (lo < hi) { int mid = (lo + hi) >> 1; if (cols[mid * ROW_THREADS] < j) lo = mid + 1; else hi = mid; }
+  if (lo < cnt && cols[lo * ROW_THREADS] == j) { vals[lo * ROW_THREADS] += v; return cnt; }
+  if (cnt == ROW_CAP) return -1;
+  for (int q = cnt; q > lo; q--) { cols[q * ROW_THREADS] = cols[(q - 1) * ROW_THREADS]; vals[q * ROW_THREADS] = vals[(q - 1) * ROW_THREADS]; }
+  cols[lo * ROW_THREADS] = j; vals[lo * ROW_THREADS] = 0.0 + v;
+  return cnt + 1;
+}
+
 // P = T - omega D^-1 A T, row-wise.  Terms of one (row, aggregate) are added in column order
 // and the tentative 1 last — the order the reference's stable sort + reduce_by_key produces.
 __global__ void prolongator_rows(int n, const int* __restrict__ ptr, const int* __restrict__ col, const double* __restrict__ val,
                                  const double* __restrict__ diag, const int* __restrict__ aggOf, double omega,
                                  int* __restrict__ scol, double* __restrict__ sval, int* __restrict__ count) {
+  __shared__ int sh_c[ROW_CAP * ROW_THREADS];
+  __shared__ double sh_v[ROW_CAP * ROW_THREADS];
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   long long base = (long long)ptr[i] + i;  // room for row length + 1 entries
   int* cols = scol + base;
   double* vals = sval + base;
-  int cnt = 0;
   double d = diag[i];
-  for (int e = ptr[i]; e < ptr[i + 1]; e++) {
+  int* lc = sh_c + threadIdx.x;
+  double* lv = sh_v + threadIdx.x;
+  int cnt = 0;
+  for (int e = ptr[i]; e < ptr[i + 1] && cnt >= 0; e++) {
     double term = (-omega * val[e] * 1.0) / d;
-    cnt = acc_insert(cols, vals, cnt, aggOf[col[e]], term);
+    cnt = acc_insert_sh(lc, lv, cnt, aggOf[col[e]], term);
   }
-  cnt = acc_insert(cols, vals, cnt, aggOf[i], 1.0);
+  if (cnt >= 0) cnt = acc_insert_sh(lc, lv, cnt, aggOf[i], 1.0);
+  if (cnt >= 0) {
+    for (int q = 0; q < cnt; q++) { cols[q] = lc[q * ROW_THREADS]; vals[q] = lv[q * ROW_THREADS]; }
+  } else {  // more distinct aggregates than the shared list holds: the same accumulation on the global scratch row
+    cnt = 0;
+    for (int e = ptr[i]; e < ptr[i + 1]; e++) {
+      double term = (-omega * val[e] * 1.0) / d;
+      cnt = acc_insert(cols, vals, cnt, aggOf[col[e]], term);
+    }
+    cnt = acc_insert(cols, vals, cnt, aggOf[i], 1.0);
+  }
   count[i] = cnt;
 }
 
@@ -112,17 +161,31 @@ __global__ void spgemm_rows(int n, const int* __restrict__ ptrA, const int* __re
                             const int* __restrict__ ptrB, const int* __restrict__ colB, const double* __restrict__ valB,
                             const long long* __restrict__ sbase, int* __restrict__ scol, double* __restrict__ sval, int* __restrict__ count,
                             long long min_products) {
+  __shared__ int sh_c[ROW_CAP * ROW_THREADS];
+  __shared__ double sh_v[ROW_CAP * ROW_THREADS];
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   // second pass after spgemm_warp_kernel: only the rows it flagged (count == -1) are redone here
   if (min_products > 0 && count[i] != -1) return;
   int* cols = scol + sbase[i];
   double* vals = sval + sbase[i];
+  int* lc = sh_c + threadIdx.x;
+  double* lv = sh_v + threadIdx.x;
   int cnt = 0;
-  for (int e = ptrA[i]; e < ptrA[i + 1]; e++) {
+  for (int e = ptrA[i]; e < ptrA[i + 1] && cnt >= 0; e++) {
     int k = colA[e];
     double a = valA[e];
-    for (int f = ptrB[k]; f < ptrB[k + 1]; f++) cnt = acc_insert(cols, vals, cnt, colB[f], a * valB[f]);
+    for (int f = ptrB[k]; f < ptrB[k + 1] && cnt >= 0; f++) cnt = acc_insert_sh(lc, lv, cnt, colB[f], a * valB[f]);
+  }
+  if (cnt >= 0) {
+    for (int q = 0; q < cnt; q++) { cols[q] = lc[q * ROW_THREADS]; vals[q] = lv[q * ROW_THREADS]; }
+  } else {  // more distinct columns than the shared list holds: the same accumulation on the global scratch row
+    cnt = 0;
+    for (int e = ptrA[i]; e < ptrA[i + 1]; e++) {
+      int k = colA[e];
+      double a = valA[e];
+      for (int f = ptrB[k]; f < ptrB[k + 1]; f++) cnt = acc_insert(cols, vals, cnt, colB[f], a * valB[f]);
+    }
   }
   count[i] = cnt;
 }
@@ -423,7 +486,7 @@ void permute_csr(const Ctx& c, const DCsr& A, const int* perm, DCsr& B) {
   B.ptr.alloc(n + 1, s);
   exclusive_scan_i32(len, B.ptr, n + 1, s);
   B.col.alloc(A.nnz, s); B.val.alloc(A.nnz, s);
-  permute_rows<<<cdiv(n, 128), 128, 0, s>>>(n, A.ptr, A.col, A.val, perm, B.ptr, B.col, B.val);
+  permute_rows<<<cdiv(n, PR_THREADS), PR_THREADS, 0, s>>>(n, A.ptr, A.col, A.val, perm, B.ptr, B.col, B.val);
   FSB_CHECK_LAUNCH();
 }
 
@@ -442,7 +505,7 @@ void build_prolongator(const Ctx& c, const DCsr& A, const double* diag, const in
   IBuf scol(cap, s); DBuf sval(cap, s);
   DevBuf<long long> sbase(n, s);
   prolongator_bases<<<cdiv(n, 256), 256, 0, s>>>(n, A.ptr, sbase);
-  prolongator_rows<<<cdiv(n, 128), 128, 0, s>>>(n, A.ptr, A.col, A.val, diag, aggOf, omega, scol, sval, count);
+  prolongator_rows<<<cdiv(n, ROW_THREADS), ROW_THREADS, 0, s>>>(n, A.ptr, A.col, A.val, diag, aggOf, omega, scol, sval, count);
   FSB_CHECK_LAUNCH();
   P.nrows = n; P.ncols = nAgg;
   P.nnz = counts_to_ptr(c, count, n, P.ptr);
@@ -498,9 +561,9 @@ void spgemm(const Ctx& c, const DCsr& A, const DCsr& B, DCsr& C) {
       spgemm_warp_kernel<WgLarge, true><<<cdiv(n, WgLarge::WARPS), 32 * WgLarge::WARPS, smemL, s>>>(n, A.ptr, A.col, A.val, B.ptr, B.col, B.val, sbase, scol, sval, count);
     }
     // rows that exceed that too: thread-per-row kernel, restricted to them
-    spgemm_rows<<<cdiv(n, 64), 64, 0, s>>>(n, A.ptr, A.col, A.val, B.ptr, B.col, B.val, sbase, scol, sval, count, 1);
+    spgemm_rows<<<cdiv(n, ROW_THREADS), ROW_THREADS, 0, s>>>(n, A.ptr, A.col, A.val, B.ptr, B.col, B.val, sbase, scol, sval, count, 1);
   } else {
-    spgemm_rows<<<cdiv(n, 64), 64, 0, s>>>(n, A.ptr, A.col, A.val, B.ptr, B.col, B.val, sbase, scol, sval, count, 0);
+    spgemm_rows<<<cdiv(n, ROW_THREADS), ROW_THREADS, 0, s>>>(n, A.ptr, A.col, A.val, B.ptr, B.col, B.val, sbase, scol, sval, count, 0);
   }
   FSB_CHECK_LAUNCH();
   C.nrows = n; C.ncols = B.ncols;
@@ -655,48 +718,64 @@ __global__ void fill_ell_kernel(long long nthreads, int G, const int* __restrict
 // in which an earlier lane already reads the same address, then for a slot whose bank (either copy) is
 // still unused, then for the least loaded one; padding slots point at an unused bank.
 // One thread per (warp slab, half): setup-time work.
-__global__ void ell_assign_slots(int nwarps, int G, const int* __restrict__ warpPart, const int* __restrict__ pstart, const int* __restrict__ pwarp,
-                                 const long long* __restrict__ wptr, const int* __restrict__ lenSorted, double* __restrict__ ellval,
-                                 unsigned short* __restrict__ ellcol) {
+// Storage: the per-thread tables (2.2 KB per thread as local arrays) thrashed L1 at full occupancy — every access went to
+// L2 and the kernel was one long latency chain (3.4 ms on level 0 of N=118).  They now live in shared memory, thread-fastest
+// (index * AS_THREADS + thread), sized by the level's widest slab (MAXK = 16: 68 KB per 64-thread CTA, three CTAs per SM).
+constexpr int AS_THREADS = 64;
+template <int MAXK>
+__global__ void __launch_bounds__(AS_THREADS) ell_assign_slots(int nwarps, int G, const int* __restrict__ warpPart, const int* __restrict__ pstart,
+                                                               const int* __restrict__ pwarp, const long long* __restrict__ wptr,
+                                                               const int* __restrict__ lenSorted, double* __restrict__ ellval,
+                                                               unsigned short* __restrict__ ellcol) {
+  extern __shared__ __align__(16) unsigned char as_smem[];
+  double* s_ev = reinterpret_cast<double*>(as_smem);                        // [MAXK][T] entries of the current row, as stored
+  double* s_ov = s_ev + MAXK * AS_THREADS;                                  // [MAXK][T] ... as placed
+  short* s_elem = reinterpret_cast<short*>(s_ov + MAXK * AS_THREADS);       // [MAXK * 16][T] first address assigned to (slot, bank), -1 = unused
+  unsigned short* s_ec = reinterpret_cast<unsigned short*>(s_elem + MAXK * 16 * AS_THREADS);  // [MAXK][T]
+  unsigned short* s_oc = s_ec + MAXK * AS_THREADS;                          // [MAXK][T]
+  unsigned char* s_cnt = reinterpret_cast<unsigned char*>(s_oc + MAXK * AS_THREADS);          // [MAXK * 16][T] distinct addresses in the bank
+  const int tid = threadIdx.x;
+#define bankElem(k, q) s_elem[((k) * 16 + (q)) * AS_THREADS + tid]
+#define bankCnt(k, q) s_cnt[((k) * 16 + (q)) * AS_THREADS + tid]
+#define EC(e) s_ec[(e) * AS_THREADS + tid]
+#define OC(e) s_oc[(e) * AS_THREADS + tid]
+#define EV(e) s_ev[(e) * AS_THREADS + tid]
+#define OV(e) s_ov[(e) * AS_THREADS + tid]
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   int w = gid >> 1, h = gid & 1;
   if (w >= nwarps) return;
   int p = warpPart[w], r0 = pstart[p], np = pstart[p + 1] - r0, t0 = 32 * (w - pwarp[p]) + 16 * h;
   if (t0 >= np * G) return;
   const int K = (int)((wptr[w + 1] - wptr[w]) >> 5), nl = min(16, np * G - t0);
-  if (K == 0) return;
+  if (K == 0 || K > MAXK) return;
   const long long base = wptr[w] + 16 * h;
-  short bankElem[32][16];          // first address (column | copy << 15) assigned to the bank, -1 = unused
-  unsigned char bankCnt[32][16];   // distinct addresses in the bank
   unsigned occ[16];                // per bank: slots in which it is already used (bit k <=> bankCnt[k][bank] > 0)
   for (int k = 0; k < K; k++)
-    for (int q = 0; q < 16; q++) { bankElem[k][q] = -1; bankCnt[k][q] = 0; }
+    for (int q = 0; q < 16; q++) { bankElem(k, q) = -1; bankCnt(k, q) = 0; }
   for (int q = 0; q < 16; q++) occ[q] = 0u;
   for (int l = 0; l < nl; l++) {
     const int srow = (t0 + l) / G, g = (t0 + l) % G;
     const int len = min(max(lenSorted[r0 + srow] - g + G - 1, 0) / G, K);
-    unsigned short ec[32], oc[32];
-    double ev[32], ov[32];
-    for (int e = 0; e < len; e++) { ec[e] = ellcol[base + 32LL * e + l]; ev[e] = ellval[base + 32LL * e + l]; }
+    for (int e = 0; e < len; e++) { EC(e) = ellcol[base + 32LL * e + l]; EV(e) = ellval[base + 32LL * e + l]; }
     unsigned freeSlots = K == 32 ? 0xffffffffu : ((1u << K) - 1u), todo = len == 32 ? 0xffffffffu : ((1u << len) - 1u);
     auto place = [&](int e, int k, int copy) {
-      const int cc = ec[e], b = (cc + 8 * copy) & 15;
+      const int cc = EC(e), b = (cc + 8 * copy) & 15;
       const short addr = (short)(cc | (copy << 15));
-      oc[k] = (unsigned short)addr; ov[k] = ev[e];
+      OC(k) = (unsigned short)addr; OV(k) = EV(e);
       freeSlots &= ~(1u << k); todo &= ~(1u << e);
-      if (bankElem[k][b] != addr) { bankCnt[k][b]++; occ[b] |= 1u << k; if (bankElem[k][b] == -1) bankElem[k][b] = addr; }
+      if (bankElem(k, b) != addr) { bankCnt(k, b)++; occ[b] |= 1u << k; if (bankElem(k, b) == -1) bankElem(k, b) = addr; }
     };
     for (int e = 0; e < len; e++) {  // 1. share an address with an earlier lane (only slots whose bank is in use can match)
-      const int cc = ec[e], bA = cc & 15, bB = (cc + 8) & 15;
+      const int cc = EC(e), bA = cc & 15, bB = (cc + 8) & 15;
       for (unsigned f = freeSlots & (occ[bA] | occ[bB]); f; f &= f - 1) {
         int k = __ffs(f) - 1;
-        if (bankElem[k][bA] == (short)cc) { place(e, k, 0); break; }
-        if (bankElem[k][bB] == (short)(cc | 0x8000)) { place(e, k, 1); break; }
+        if (bankElem(k, bA) == (short)cc) { place(e, k, 0); break; }
+        if (bankElem(k, bB) == (short)(cc | 0x8000)) { place(e, k, 1); break; }
       }
     }
     for (int e = 0; e < len; e++) {  // 2. an unused bank: the lowest free slot in which copy A's or copy B's bank is unused
       if (!(todo >> e & 1u)) continue;
-      const int cc = ec[e], bA = cc & 15, bB = (cc + 8) & 15;
+      const int cc = EC(e), bA = cc & 15, bB = (cc + 8) & 15;
       const unsigned fa = freeSlots & ~occ[bA], fb = freeSlots & ~occ[bB];
       if (fa | fb) {
         const int k = __ffs(fa | fb) - 1;
@@ -705,12 +784,12 @@ __global__ void ell_assign_slots(int nwarps, int G, const int* __restrict__ warp
     }
     for (int e = 0; e < len; e++) {  // 3. the least loaded bank
       if (!(todo >> e & 1u)) continue;
-      const int cc = ec[e];
+      const int cc = EC(e);
       int best = 1 << 30, bk = 0, bc = 0;
       for (unsigned f = freeSlots; f; f &= f - 1) {
         int k = __ffs(f) - 1;
         for (int copy = 0; copy < 2; copy++) {
-          int load = bankCnt[k][(cc + 8 * copy) & 15];
+          int load = bankCnt(k, (cc + 8 * copy) & 15);
           if (load < best) { best = load; bk = k; bc = copy; }
         }
       }
@@ -721,12 +800,20 @@ __global__ void ell_assign_slots(int nwarps, int G, const int* __restrict__ warp
       for (int q = 0; q < 16; q++)
         if (!(occ[q] >> k & 1u) && q < np) { cc = q; break; }
       const int b = cc & 15;
-      oc[k] = (unsigned short)cc; ov[k] = 0.0;
-      if (bankElem[k][b] != (short)cc) { bankCnt[k][b]++; occ[b] |= 1u << k; if (bankElem[k][b] == -1) bankElem[k][b] = (short)cc; }
+      OC(k) = (unsigned short)cc; OV(k) = 0.0;
+      if (bankElem(k, b) != (short)cc) { bankCnt(k, b)++; occ[b] |= 1u << k; if (bankElem(k, b) == -1) bankElem(k, b) = (short)cc; }
     }
-    for (int k = 0; k < K; k++) { ellcol[base + 32LL * k + l] = oc[k]; ellval[base + 32LL * k + l] = ov[k]; }
+    for (int k = 0; k < K; k++) { ellcol[base + 32LL * k + l] = OC(k); ellval[base + 32LL * k + l] = OV(k); }
   }
+#undef bankElem
+#undef bankCnt
+#undef EC
+#undef OC
+#undef EV
+#undef OV
 }
+template <int MAXK>
+constexpr size_t assign_slots_smem() { return (size_t)AS_THREADS * (MAXK * 8 * 2 + MAXK * 16 * 2 + MAXK * 2 * 2 + MAXK * 16); }
 
 }  // namespace
 
@@ -836,7 +923,20 @@ void split_partitions(const Ctx& c, LevelData& L) {
     fill_ell_kernel<<<cdiv(32LL * nw, 256), 256, 0, s>>>(32LL * nw, G, warpPart, L.pstart, L.pwarp, L.ellwptr, L.ellrow, pos, L.A.ptr, L.A.col, L.A.val,
                                                          L.ellval, L.ellcol);
     lap("fill");
-    ell_assign_slots<<<cdiv(2LL * nw, 64), 64, 0, s>>>(nw, G, warpPart, L.pstart, L.pwarp, L.ellwptr, lenSorted, L.ellval, L.ellcol);
+    {
+      // widest slab of the level: K = ceil(longest row / G) rounded up to even
+      int kmax = (L.ellMaxK + G - 1) / G;
+      kmax += kmax & 1;
+      static PerDeviceOnce attr_once;
+      if (attr_once.first(c.device)) {
+        FSB_CUDA(cudaFuncSetAttribute(ell_assign_slots<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)assign_slots_smem<16>()));
+        FSB_CUDA(cudaFuncSetAttribute(ell_assign_slots<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)assign_slots_smem<32>()));
+      }
+      if (kmax <= 16)
+        ell_assign_slots<16><<<cdiv(2LL * nw, AS_THREADS), AS_THREADS, assign_slots_smem<16>(), s>>>(nw, G, warpPart, L.pstart, L.pwarp, L.ellwptr, lenSorted, L.ellval, L.ellcol);
+      else
+        ell_assign_slots<32><<<cdiv(2LL * nw, AS_THREADS), AS_THREADS, assign_slots_smem<32>(), s>>>(nw, G, warpPart, L.pstart, L.pwarp, L.ellwptr, lenSorted, L.ellval, L.ellcol);
+    }
     lap("assign_slots");
     // per-partition descriptors and the lists by size class (host side: nparts is a few thousand)
     std::vector<int> ps = L.pstart.to_vector(), pw = L.pwarp.to_vector();
