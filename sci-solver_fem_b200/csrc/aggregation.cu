@@ -14,6 +14,7 @@
 // 64-bit radix sorts for the induced graph, device-side convergence counters.
 #include <cstdlib>
 #include <ctime>
+#include <mutex>
 
 #include "fsb_internal.h"
 
@@ -99,9 +100,23 @@ __global__ void mis_iterate(int n, const int* __restrict__ originIn, int* __rest
 
 void randomized_mis(const Ctx& c, int n, const int* xadj, const int* adj, int k, unsigned seed, int* mis) {
   cudaStream_t s = c.stream;
-  std::vector<unsigned> seeds_h(32768);
-  srand(seed);  // upstream: srand(time(NULL)); the seed is a solver parameter here
-  for (int i = 0; i < 32768; i++) seeds_h[i] = (unsigned)rand();
+  // upstream: srand(time(NULL)) and 32768 rand() calls per MIS; the seed is a solver parameter here, so the table is a pure
+  // function of it: six MIS calls per setup share one table (libc's rand() takes a lock: 0.7 ms per table), and concurrent
+  // solvers on other threads cannot interleave their rand() sequences.
+  std::vector<unsigned> seeds_h;
+  {
+    static std::mutex mu;
+    static std::vector<unsigned> table;
+    static unsigned table_seed = 0;
+    std::lock_guard<std::mutex> lock(mu);
+    if (table.empty() || table_seed != seed) {
+      table.resize(32768);
+      srand(seed);
+      for (int i = 0; i < 32768; i++) table[i] = (unsigned)rand();
+      table_seed = seed;
+    }
+    seeds_h = table;
+  }
   DevBuf<unsigned> seeds(32768, s), randoms(n, s);
   seeds.from_host(seeds_h.data(), 32768);
   IBuf bestA(n, s), bestB(n, s), orgA(n, s), orgB(n, s), incomplete(1, s);
