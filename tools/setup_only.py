@@ -7,6 +7,8 @@ ap = argparse.ArgumentParser(); ap.add_argument("--cube", type=int, default=118)
 v, t = fsb.meshio.kuhn_cube(a.cube)
 s = fsb.FEMSolver.from_arrays(v, t)
 s.solverType_, s.seed_ = 1, 0
+for r in range(a.repeat - 1):   # warm-pool stage timings of the rebuilds
+    s.getMatrixFromMesh(); print("rebuild", {k: round(s.time_ms(k), 2) for k in ("pattern", "assemble")}, flush=True)
 for r in range(a.repeat):   # --repeat 2 with FSB_SETUP_TRACE=1: the second pass shows the warm-pool laps
     print(f"-- pass {r}", file=sys.stderr, flush=True)
     s.setup()
